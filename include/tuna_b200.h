@@ -1,0 +1,99 @@
+/*
+ * tuna_b200.h — C ABI of libtuna_b200.so: the B200 (sm_100a) provider for TUNA's SCF two-electron hot path.
+ *
+ * Drop-in boundary.  Each entry point names the reference interface it replaces;
+ * paths are relative to h-brough/TUNA, "pyx" = TUNA/tuna_integrals/tuna_integral.pyx.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status (0 = ok); no exceptions
+ * or Python objects cross; the caller owns every host buffer; the library owns only memory behind the
+ * opaque context; a context is not thread-safe; one context per (device, geometry, basis).  All matrices and
+ * tensors are dense, C-order, IEEE double.  Entry points ending in _dev take DEVICE pointers and enqueue on
+ * the context's stream without synchronising; all others take HOST pointers and return when the result is
+ * in the caller's buffer.  There is no CPU fallback anywhere behind this header.
+ */
+#ifndef TUNA_B200_H
+#define TUNA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tuna_ctx tuna_ctx;
+
+enum {
+    TUNA_OK = 0,
+    TUNA_ERR_ARG = 1,      /* bad argument            -> Python raises TunaError                       */
+    TUNA_ERR_NOMEM = 2,    /* host or device OOM      -> MemoryError (pyx:1120, :1290 raise the same)   */
+    TUNA_ERR_CUDA = 3,     /* CUDA runtime failure    -> TunaError                                      */
+    TUNA_ERR_STATE = 4     /* call order / missing prerequisite -> TunaError                            */
+};
+
+/* Context life cycle.  `device` is the CUDA ordinal.  Uploads the Boys-function table. */
+int tuna_ctx_create(int device, tuna_ctx** out);
+int tuna_ctx_destroy(tuna_ctx* ctx);
+const char* tuna_last_error(const tuna_ctx* ctx);
+/* Use an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = the context's own. */
+int tuna_set_stream(tuna_ctx* ctx, void* cuda_stream);
+
+/* The basis: one entry per CARTESIAN COMPONENT, exactly the list[Basis] the reference passes
+ * (Basis: pyx:78-235; ordered as tuna_molecule.py:532-585 builds it).  coef_eff[k] = Basis.norm[k] * Basis.coefs[k]
+ * (pyx:1070).  All centres must lie on the z axis (tuna_kernel.py:386-388); origins_z holds their z.
+ * Builds the class-sorted AO-pair / primitive-pair table once (replaces pyx:1050-1128, :1300-1308). */
+int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int32_t* lmn, const int32_t* nprim,
+                   const int64_t* prim_offset, const double* exps, const double* coef_eff);
+
+/* Cartesian -> spherical map U (nbf x ncart, row-major) = molecule.spherical_harmonic_transformation_matrix
+ * (tuna_kernel.py:540-649).  Pass the identity for CARTHARM (tuna_kernel.py:481-483). */
+int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U);
+
+/* calculate_electron_repulsion_integrals (pyx:1267-1355): fill the dense Cartesian tensor ncart^4 on the device. */
+int tuna_eri_fill_cart(tuna_ctx* ctx);
+/* transform_to_spherical_harmonics, ERI part (tuna_kernel.py:504-523): (U (x) U) ERI (U (x) U)^T on the device.
+ * keep_cart != 0 keeps the Cartesian tensor resident as well. */
+int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart);
+/* Copy a resident tensor to the host: which = 0 Cartesian (ncart^4), 1 spherical (nbf^4). */
+int tuna_eri_download(tuna_ctx* ctx, int which, double* host_out);
+/* Adopt a dense n^4 tensor supplied by the caller as the stored tensor for tuna_jk_stored (a plain ndarray
+ * handed to tuna_scf.calculate_coulomb_matrix / calculate_exchange_matrix). */
+int tuna_eri_upload(tuna_ctx* ctx, int n, const double* host_in);
+/* calculate_electron_repulsion_integral (pyx:1376-1414) for functions (i j | k l) of the current basis. */
+int tuna_eri_single(tuna_ctx* ctx, int i, int j, int k, int l, double* out);
+/* Schwarz factors Q_ij = sqrt((ij|ij)) as a dense ncart x ncart matrix (not in the reference). */
+int tuna_schwarz(tuna_ctx* ctx, double* host_out);
+
+/* Stored-ERI Fock contraction: for each of nD densities P[d] (n x n),
+ *   J[d]_ij = sum_kl (ij|kl) P_kl   (tuna_scf.calculate_coulomb_matrix,  tuna_scf.py:55-72)
+ *   K[d]_ij = sum_kl (il|kj) P_kl   (tuna_scf.calculate_exchange_matrix, tuna_scf.py:27-44)
+ * in ONE pass over the resident tensor.  J or K may be NULL.  n is the stored tensor's dimension. */
+int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K);
+int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK);
+
+/* Direct (integral-driven) Fock contraction: same J and K, in the basis of U (nbf x nbf matrices), never
+ * materialising the tensor: 8-fold symmetry, Schwarz screening |Q_ij Q_kl| max|P| < tau skipped.
+ * P must be symmetric (SCF densities are); tau <= 0 disables screening. */
+int tuna_jk_direct(tuna_ctx* ctx, int nD, const double* P, double* J, double* K, double tau);
+int tuna_jk_direct_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK, double tau);
+/* Multi-GPU sharding of the quartet list for tuna_jk_direct*: this context evaluates only its share and
+ * returns PARTIAL J/K, to be summed over ranks by the caller (one all-reduce per build). */
+int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks);
+
+/* Introspection for tests and bench.py.
+ * counts[0] AO pairs, [1] unique AO quartets, [2] quartets passing the x/y parity test (pyx:1324-1327),
+ * [3] primitive quartets among those, [4] quartets evaluated by the last direct build (after screening, this rank),
+ * [5] kernels launched by this context so far, [6] ncart, [7] nbf. */
+int tuna_get_counts(const tuna_ctx* ctx, int64_t counts[8]);
+/* Device time (ms, CUDA events on the launching stream) of the dominant kernel of the last call:
+ * which = 0 ERI fill, 1 cart->sph, 2 stored J/K, 3 direct J/K.  Synchronises the stream. */
+int tuna_last_kernel_ms(tuna_ctx* ctx, int which, float* ms);
+/* Algorithmic FP64 flop count of the reference algorithm for the parity-surviving unique quartets of the
+ * current basis (formula F(a,b) of SURVEY.md section 8d), and the J/K digestion flops per density. */
+int tuna_algorithmic_flops(const tuna_ctx* ctx, double* eri_flops, double* digest_flops_per_density);
+/* Dependency-free DFMA stream used to measure the FP64 pipe peak of this device (TFLOP/s). */
+int tuna_fp64_peak_probe(tuna_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

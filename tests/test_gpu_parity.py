@@ -1,0 +1,220 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle, the reference's compiled engine
+and the committed golden fixtures.  Tolerances are the north star's: ERIs 1e-12 Eh absolute (1e-13 relative above
+10 Eh), J/K 1e-11, energies 1e-10 Eh."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from test_oracle import H2_KAT
+from util import basis_objects, context_for, eri_tolerance, load_golden, oracle_basis
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import tuna_b200
+    return tuna_b200
+
+
+def _check_eri(got, ref):
+    bad = np.abs(got - ref) > eri_tolerance(ref)
+    assert not bad.any(), f"{int(bad.sum())} elements out of tolerance, max abs diff {np.abs(got - ref).max():.3e}"
+
+
+def test_h2_known_answers(tb, oracle):
+    g = load_golden("h2_631g")
+    ctx = context_for(g)
+    ctx.eri_fill_cart()
+    E = ctx.eri_download(0)
+    for idx, val in H2_KAT.items():
+        assert abs(E[idx] - val) < 1e-12, idx
+    _check_eri(E, oracle.eri_fill(oracle_basis(oracle, g)))
+    for idx, val in list(H2_KAT.items())[:6]:
+        assert abs(ctx.eri_single(*idx) - val) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["n2_ccpvtz", "co_b3lyp_ccpvtz", "et100"])
+def test_eri_cart_vs_oracle(tb, oracle, name):
+    g = load_golden(name)
+    ctx = context_for(g)
+    ctx.eri_fill_cart()
+    E = ctx.eri_download(0)
+    ref = oracle.eri_fill(oracle_basis(oracle, g))
+    _check_eri(E, ref)
+    assert np.array_equal(E == 0.0, ref == 0.0)                       # parity zeros are exact zeros (pyx:1324-1327)
+    _check_eri(E[tuple(g["eri_cart_idx"].T)], g["eri_cart_val"])      # the reference's own values
+    assert abs(E.sum() - float(g["eri_cart_sum"])) < 1e-9 * abs(float(g["eri_cart_sum"]))
+    # 8-fold permutational symmetry is exact by construction
+    assert np.array_equal(E, E.transpose(1, 0, 2, 3)) and np.array_equal(E, E.transpose(0, 1, 3, 2)) and np.array_equal(E, E.transpose(2, 3, 0, 1))
+    c = ctx.counts()
+    assert (c["unique_quartets"], c["surviving_quartets"]) == oracle.parity_surviving_quartets(g["lmn"])
+
+
+def test_eri_ne2_ccpvqz_vs_compiled_reference(tb, oracle):
+    """Full Cartesian tensor (140^4) against the UNMODIFIED reference engine from oracle/_ref (g functions, T up to ~3e6)."""
+    g = load_golden("ne2_uhf_ccpvqz")
+    ctx = context_for(g)
+    ctx.eri_fill_cart()
+    E = ctx.eri_download(0)
+    _check_eri(E[tuple(g["eri_cart_idx"].T)], g["eri_cart_val"])
+    eng = oracle.reference_engine()
+    fb = oracle_basis(oracle, g)
+    n = fb.ncart
+    if eng is not None:
+        ref = np.asarray(eng.calculate_electron_repulsion_integrals(n, np.empty((n,) * 4), oracle.reference_basis_objects(fb), oracle.max_threads()))
+    else:
+        ref = oracle.eri_fill(fb)
+    _check_eri(E, ref)
+    assert abs(np.abs(E).max() - float(g["eri_cart_max"])) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["n2_ccpvtz", "ne2_uhf_ccpvqz", "et100"])
+def test_cart_to_sph_and_stored_jk(tb, oracle, name):
+    g = load_golden(name)
+    ctx = context_for(g)
+    ctx.set_transform(g["U"])
+    ctx.eri_fill_cart()
+    ctx.eri_cart_to_sph()
+    nbf = int(g["nbf"])
+    Es = ctx.eri_download(1)
+    assert Es.shape == (nbf,) * 4
+    ref = g["eri_sph_val"]
+    assert np.abs(Es[tuple(g["eri_sph_idx"].T)] - ref).max() < 2e-12
+    assert abs(np.linalg.norm(Es) - float(g["eri_sph_fro"])) < 1e-11 * float(g["eri_sph_fro"])
+    P = tb.workloads.fixed_density(nbf)
+    J, K = ctx.jk_stored(P)
+    assert np.abs(J - g["Jfix"]).max() < 1e-11 * max(1.0, np.abs(g["Jfix"]).max())
+    assert np.abs(K - g["Kfix"]).max() < 1e-11 * max(1.0, np.abs(g["Kfix"]).max())
+    # against the oracle's einsums on the SAME tensor: isolates the contraction kernel
+    assert np.abs(J - oracle.coulomb(P, Es)).max() < 1e-11 and np.abs(K - oracle.exchange(P, Es)).max() < 1e-11
+    # a general (non-symmetric) density and a stack of densities
+    rng = np.random.default_rng(7)
+    Ps = rng.standard_normal((3, nbf, nbf))
+    Js, Ks = ctx.jk_stored(Ps)
+    for d in range(3):
+        assert np.abs(Js[d] - oracle.coulomb(Ps[d], Es)).max() < 1e-10
+        assert np.abs(Ks[d] - oracle.exchange(Ps[d], Es)).max() < 1e-10
+    # linearity
+    J2, K2 = ctx.jk_stored(2.0 * Ps[0] - 0.5 * Ps[1])
+    assert np.abs(J2 - (2.0 * Js[0] - 0.5 * Js[1])).max() < 1e-10 and np.abs(K2 - (2.0 * Ks[0] - 0.5 * Ks[1])).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "co_b3lyp_ccpvtz", "ne2_uhf_ccpvqz", "et100", "n2_ccpvtz_cartharm"])
+def test_scf_sequence_stored_and_direct(tb, name):
+    """The reference's own SCF sequence: every recorded P_i must give the recorded J_i, K_i (1e-11), in both modes,
+    and the final J/K must reproduce the reference's Coulomb/exchange energies (tuna_scf.py:376,380 / :454-459) to 1e-10."""
+    g = load_golden(name)
+    ctx = context_for(g)
+    ctx.set_transform(g["U"])
+    ctx.eri_fill_cart()
+    ctx.eri_cart_to_sph()
+    keys = sorted(k for k in g.files if k.startswith("seq") and k.endswith("_P"))
+    assert keys
+    for k in keys:
+        P, ref = g[k], g[k[:-2] + "_out"]
+        kind = k.split("_")[2]
+        J, K = ctx.jk_stored(P)
+        got = J if kind == "J" else K
+        assert np.abs(got - ref).max() < 1e-11, (k, "stored")
+        Jd, Kd = ctx.jk_direct(P)
+        gotd = Jd if kind == "J" else Kd
+        assert np.abs(gotd - ref).max() < 1e-11, (k, "direct")
+    # What a J/K error does to the energy: the reference forms E_J = 1/2 sum P_new J(P_old), E_K = -1/4 sum P_new K(P_old)
+    # (tuna_scf.py:376,380 with the old-J/new-P convention of :1141; UHF analogues :454-459).  With the converged P_new on
+    # both sides, our J/K on the last recorded P_old must give the same energies as the reference's recorded J/K to 1e-10.
+    last = int(g["kept_iterations"][-1])
+    P_new = g["P_final"]
+    for k in [k for k in keys if k.startswith(f"seq{last}_")]:
+        P, ref = g[k], g[k[:-2] + "_out"]
+        kind = k.split("_")[2]
+        J, K = ctx.jk_direct(P)
+        got = J if kind == "J" else K
+        assert abs(0.5 * np.sum(P_new * (got - ref))) < 1e-10, (k, "energy")
+
+
+@pytest.mark.parametrize("name", ["n2_ccpvtz", "et100"])
+def test_direct_jk_fixed_density_and_screening(tb, name):
+    g = load_golden(name)
+    ctx = context_for(g)
+    ctx.set_transform(g["U"])
+    P = tb.workloads.fixed_density(int(g["nbf"]))
+    J0, K0 = ctx.jk_direct(P, tau=0.0)
+    assert ctx.counts()["evaluated_last_direct"] == ctx.counts()["surviving_quartets"]
+    scale = max(1.0, np.abs(g["Kfix"]).max())
+    assert np.abs(J0 - g["Jfix"]).max() < 1e-11 * scale and np.abs(K0 - g["Kfix"]).max() < 1e-11 * scale
+    J1, K1 = ctx.jk_direct(P)      # default Schwarz threshold
+    assert np.abs(J1 - g["Jfix"]).max() < 1e-11 * scale and np.abs(K1 - g["Kfix"]).max() < 1e-11 * scale
+    assert ctx.counts()["evaluated_last_direct"] <= ctx.counts()["surviving_quartets"]
+    # Schwarz bound |(ij|kl)| <= Q_ij Q_kl on a sample
+    Q = ctx.schwarz()
+    idx = g["eri_cart_idx"]
+    bound = Q[idx[:, 0], idx[:, 1]] * Q[idx[:, 2], idx[:, 3]]
+    assert np.all(np.abs(g["eri_cart_val"]) <= bound * (1 + 1e-12) + 1e-15)
+    # two-rank sharding of the quartet list: partial J/K sum to the whole
+    parts = []
+    for r in range(2):
+        ctx.set_shard(r, 2)
+        parts.append(ctx.jk_direct(P, tau=0.0))
+    ctx.set_shard(0, 1)
+    assert np.abs(parts[0][0] + parts[1][0] - J0).max() < 1e-11 * scale
+    assert np.abs(parts[0][1] + parts[1][1] - K0).max() < 1e-11 * scale
+
+
+def test_provider_reference_signatures(tb, oracle):
+    """The six reference entry points, called the way tuna_kernel / tuna_scf call them."""
+    g = load_golden("n2_ccpvtz")
+    bfs = basis_objects(g)
+    n, nbf = int(g["ncart"]), int(g["nbf"])
+    # tuna_integral.calculate_electron_repulsion_integrals(n_basis, ERI_AO, bfs, num_threads): fills and returns the buffer
+    buf = np.empty((n,) * 4)
+    ret = tb.calculate_electron_repulsion_integrals(n, buf, bfs, 4)
+    assert ret is buf
+    _check_eri(buf[tuple(g["eri_cart_idx"].T)], g["eri_cart_val"])
+    # single quartet, incl. an x-parity zero
+    for q in [(0, 0, 0, 0), (7, 40, 1, 41), (17, 60, 18, 58), (30, 69, 22, 50)]:
+        v = tb.calculate_electron_repulsion_integral(*[bfs[i] for i in q])
+        assert abs(v - buf[q]) < 1e-12
+    # tuna_kernel flow: two-electron integrals -> spherical transformation -> tuna_scf J/K
+    calc = SimpleNamespace(cartesian_harmonics=False, number_of_threads=4, method=SimpleNamespace(method_base="HF"))
+    mol = SimpleNamespace(spherical_harmonic_transformation_matrix=g["U"])
+    for mode in ("stored", "direct"):
+        tb.configure(mode=mode)
+        h = tb.calculate_two_electron_integrals(n, bfs, calc)
+        assert h.shape == (n,) * 4
+        one = np.eye(n)
+        S, T, V, D, Q, eri = tb.transform_to_spherical_harmonics(one, one, one, np.stack([one] * 3), np.stack([one] * 3), h, mol, calc, True)
+        assert S.shape == (nbf, nbf) and D.shape == (3, nbf, nbf) and eri.shape == (nbf,) * 4
+        np.testing.assert_allclose(S, g["U"] @ g["U"].T, atol=1e-14)
+        P = tb.workloads.fixed_density(nbf)
+        J = tb.calculate_coulomb_matrix(P, eri)
+        K = tb.calculate_exchange_matrix(P, eri)
+        assert np.abs(J - g["Jfix"]).max() < 1e-11 * 14 and np.abs(K - g["Kfix"]).max() < 1e-11 * 14
+        assert J.flags.c_contiguous and J.dtype == np.float64
+    tb.configure(mode="auto")
+    # post-HF consumers need ndarray behaviour from the handle (tuna_mp.py:632 does 2*ERI - ERI.swapaxes(1,3))
+    dense = np.asarray(eri)
+    assert isinstance(dense, np.ndarray) and dense.shape == (nbf,) * 4
+    assert np.abs(dense[tuple(g["eri_sph_idx"].T)] - g["eri_sph_val"]).max() < 2e-12
+    mix = 2 * eri - eri.swapaxes(1, 3)
+    assert np.allclose(mix, 2 * dense - dense.swapaxes(1, 3))
+    # a plain ndarray handed to the J/K functions (what post-HF code and the unpatched glue do)
+    J = tb.calculate_coulomb_matrix(P, dense)
+    assert np.abs(J - g["Jfix"]).max() < 1e-11 * 14
+
+
+def test_error_behaviour(tb):
+    g = load_golden("h2_631g")
+    bfs = basis_objects(g)
+    bfs[1].origin = np.array([0.1, 0.0, 0.0])
+    with pytest.raises(tb.TunaError):
+        tb.calculate_electron_repulsion_integral(*bfs)
+    ctx = context_for(g)
+    with pytest.raises(tb.TunaError):
+        ctx.jk_stored(np.eye(4))              # no tensor resident
+    ctx.set_transform(g["U"])
+    with pytest.raises(tb.TunaError):
+        ctx.jk_direct(np.eye(5))              # wrong shape
+    with pytest.raises(tb.TunaError):
+        ctx.eri_single(0, 0, 0, 9)

@@ -1,0 +1,93 @@
+"""CPU tests of the host logic and the C-ABI boundary (no compute calls: there is no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from util import basis_objects, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """libtuna_b200.so loads and exports exactly what include/tuna_b200.h declares."""
+    from tuna_b200 import _lib
+    from tuna_b200.build import build
+    build()
+    header = open(os.path.join(ROOT, "include", "tuna_b200.h")).read()
+    declared = set(re.findall(r"\b(tuna_[a-z0-9_]+)\s*\(", header)) - {"tuna_ctx"}
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import tuna_b200
+    with pytest.raises(tuna_b200.TunaError):
+        tuna_b200.Context(0)
+    g = load_golden("h2_631g")
+    with pytest.raises(tuna_b200.TunaError):
+        tuna_b200.calculate_electron_repulsion_integral(*basis_objects(g))
+
+
+def test_basis_mirror_normalisation():
+    """tuna_b200.Basis reproduces Basis.normalize (pyx:174-210) on the reference's own numbers."""
+    from tuna_b200.basis import Basis, flatten
+    for name in ("h2_631g", "n2_ccpvtz", "ne2_uhf_ccpvqz"):
+        g = load_golden(name)
+        off = np.concatenate([[0], np.cumsum(g["nprim"])])
+        bfs = []
+        for i in range(int(g["ncart"])):
+            s = slice(off[i], off[i + 1])
+            b = Basis(g["origins"][i], g["lmn"][i], int(g["nprim"][i]), g["exps"][s], g["coefs"][s])
+            np.testing.assert_allclose(b.norm, g["norms"][s], rtol=1e-14)
+            np.testing.assert_allclose(b.coefs, g["coefs"][s], rtol=1e-13)     # normalising normalised coefficients is idempotent
+            bfs.append(b)
+        oz, lmn, nprim, exps, ceff = flatten(bfs)
+        np.testing.assert_allclose(ceff, g["norms"] * g["coefs"], rtol=1e-13)
+        assert lmn.dtype == np.int32 and oz.shape == (int(g["ncart"]),)
+    raw = Basis([0, 0, 0], [0, 0, 0], 1, [1.0], [1.0])
+    assert abs(raw.norm[0] - 0.71270547) < 1e-8 and abs(raw.coefs[0] - 1.0) < 1e-14
+
+
+def test_flatten_rejects_off_axis_centres():
+    from tuna_b200.basis import Basis, flatten
+    with pytest.raises(ValueError):
+        flatten([Basis([0.0, 0.2, 0.0], [0, 0, 0], 1, [1.0], [1.0])])
+
+
+def test_even_tempered_workloads(oracle):
+    from tuna_b200 import workloads as w
+    expect = {100: (112, 381.4697265625), 200: (242, None), 400: (524, 26214.4), 800: (1102, None)}
+    for nbf, (ncart, amax) in expect.items():
+        b = w.even_tempered_diatomic(nbf)
+        assert len(b["nprim"]) == ncart and w.spherical_count(b["lmn"]) == nbf
+        if amax:
+            assert abs(b["exps"].max() - amax) < 1e-9
+    # the nbf=100 point is the basis of the et100 fixture (which came through the reference's CUSTOM basis reader)
+    g = load_golden("et100")
+    b = w.even_tempered_diatomic(100)
+    np.testing.assert_array_equal(b["lmn"], g["lmn"])
+    np.testing.assert_allclose(b["exps"], g["exps"], rtol=1e-9)      # the CUSTOM reader round-trips exponents through text
+    np.testing.assert_allclose(b["origins"], g["origins"], rtol=1e-15)
+    P = w.fixed_density(5)
+    assert np.array_equal(P, P.T)
+    # quartet counts of SURVEY.md 8(d): 2.00e7 unique / 5.37e6 surviving for ET100
+    u, s = oracle.parity_surviving_quartets(b["lmn"])
+    assert abs(u / 2.00e7 - 1) < 0.01 and abs(s / 5.37e6 - 1) < 0.01
+
+
+def test_handle_forwards_ndarray_protocol():
+    from tuna_b200.provider import ERIHandle
+    h = ERIHandle(None, 3, "sph", "stored")
+    h._host = np.arange(81.0).reshape(3, 3, 3, 3)
+    assert h.shape == (3, 3, 3, 3) and h.ndim == 4
+    assert np.array_equal(np.asarray(h), h._host)
+    assert np.array_equal(2 * h - h.swapaxes(1, 3), 2 * h._host - h._host.swapaxes(1, 3))
+    assert np.array_equal(np.einsum("ijkl,kl->ij", h, np.eye(3)), np.einsum("ijkl,kl->ij", h._host, np.eye(3)))
+    assert h[1, 2, 0, 1] == h._host[1, 2, 0, 1]

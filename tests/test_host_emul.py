@@ -1,0 +1,55 @@
+"""The kernel math (tuna_b200/csrc/eri_core.cuh + pairtable.hpp, `__host__ __device__`) compiled for the CPU and
+checked against the oracle.  This is a development aid for a container without a GPU — the package never loads it."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import load_golden, oracle_basis
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(HERE, "host_emul", "libemul.so")
+    src = os.path.join(HERE, "host_emul", "emul.cpp")
+    subprocess.run(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-x", "c++", "-o", so, src, "-lm"], check=True)
+    lib = ctypes.CDLL(so)
+    lib.emul_boys.restype = ctypes.c_double
+    lib.emul_boys.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double]
+    return lib
+
+
+def test_boys_kernel_function(emul, oracle):
+    rng = np.random.default_rng(3)
+    Ts = np.concatenate([[0.0, 1e-12, 0.03125, 39.999, 40.0, 40.001, 1e3, 3e6, 1e13], rng.uniform(0, 45, 200), 10 ** rng.uniform(-6, 6, 100)])
+    worst = 0.0
+    for T in Ts:
+        for M in (0, 1, 5, 12, 20):
+            for m in {0, M // 2, M}:
+                got, ref = emul.emul_boys(M, m, float(T)), oracle.boys(m, float(T))
+                worst = max(worst, abs(got - ref) / abs(ref))
+    assert worst < 2e-14, worst
+    assert emul.emul_boys(20, 20, 0.0) == 1.0 / 41.0 and emul.emul_boys(20, 0, 0.0) == 1.0      # T == 0 branch is exact (pyx:1557-1563)
+
+
+@pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "et100"])
+def test_quartet_math_vs_oracle(emul, oracle, name):
+    g = load_golden(name)
+    fb = oracle_basis(oracle, g)
+    n = fb.ncart
+    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    oz = np.ascontiguousarray(fb.origins[:, 2])
+    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
+    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
+    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
+    out = np.empty((n,) * 4)
+    emul.emul_eri_fill(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                       fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    ref = oracle.eri_fill(fb)
+    assert np.all(np.abs(out - ref) <= np.maximum(1e-12, 1e-13 * np.abs(ref)))
+    assert np.array_equal(out == 0.0, ref == 0.0)

@@ -1,0 +1,914 @@
+// tuna_b200.cu — sm_100a kernels + C ABI (include/tuna_b200.h) of the TUNA SCF two-electron provider.
+//
+// Kernels (DESIGN.md has the roofline of each):
+//   k_eri_fill        FP64 ERI over class-sorted AO-pair quartets, 8-fold symmetric scatter into the dense tensor
+//   k_schwarz         Q_ij = sqrt((ij|ij))
+//   k_rotate_axis     one index of the Cartesian->spherical rotation (sparse U), used 4x for the tensor, 2x for matrices
+//   k_jk_stored<ND>   fused single-pass J+K over the resident dense tensor (HBM-bound), atomic-free
+//   k_jk_direct       integral-driven J/K with 8-fold symmetry + Schwarz screening (FP64-pipe-bound)
+// Reference being replaced: TUNA/tuna_integrals/tuna_integral.pyx:1267-1355 (ERI driver), TUNA/tuna_kernel.py:504-523
+// (rotation), TUNA/tuna_scf.py:27-72 (J/K einsums).  No CPU fallback exists in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/tuna_b200.h"
+#include "eri_core.cuh"
+#include "pairtable.hpp"
+
+using namespace tuna;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct CsrDev {
+    int rows = 0, cols = 0;
+    int* rowptr = nullptr;
+    int* col = nullptr;
+    double* val = nullptr;
+};
+
+struct tuna_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    double* d_boys = nullptr;
+    double* d_herm = nullptr;
+
+    // basis + pair table
+    HostBasis hb;
+    PairTable pt;
+    int ncart = 0;
+    int* d_pi = nullptr; int* d_pj = nullptr; int* d_cls = nullptr; int* d_npp = nullptr;
+    int64_t* d_ppoff = nullptr;
+    double* d_pp = nullptr;
+    double* d_Q = nullptr;            // Schwarz factor per sorted pair (lazy)
+    int64_t task_begin[5] = {0, 0, 0, 0, 0};
+    int64_t n_unique = 0, n_surviving = 0, n_primq = 0, n_eval_last = 0;
+    double alg_eri_flops = 0, alg_digest_flops = 0;
+
+    // transform
+    int nbf = 0;
+    bool U_identity = false;
+    CsrDev U, Ut;
+
+    // dense tensors
+    double* d_eri_cart = nullptr;
+    double* d_eri_sph = nullptr;      // "stored" tensor of dimension n_stored
+    int n_stored = 0;
+
+    // J/K workspaces
+    double* d_P = nullptr; double* d_J = nullptr; double* d_K = nullptr;   // nD * n^2 staging (spherical)
+    double* d_Pc = nullptr; double* d_Jc = nullptr; double* d_Kc = nullptr; double* d_tmp = nullptr;  // Cartesian
+    double* d_Kpart = nullptr;
+    size_t cap_mat = 0, cap_cart = 0, cap_kpart = 0;
+    double* h_pin = nullptr; size_t cap_pin = 0;
+    unsigned long long* d_scalars = nullptr;   // [0] max|P| bits, [1] evaluated-quartet counter
+
+    int shard_rank = 0, shard_n = 1;
+    cudaEvent_t ev[4][2] = {};
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return (e_ == cudaErrorMemoryAllocation) ? TUNA_ERR_NOMEM : TUNA_ERR_CUDA;             \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+template <typename T>
+static int dev_alloc(tuna_ctx* ctx, T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return TUNA_OK;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        cudaGetLastError();
+        ctx->err = "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e);
+        return TUNA_ERR_NOMEM;
+    }
+    return TUNA_OK;
+}
+template <typename T>
+static void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+struct PairTableDev {
+    const int* pi; const int* pj; const int* cls; const int* npp; const int64_t* ppoff; const double* pp;
+    int64_t gbeg[5];     // pair index range of each parity group
+    int64_t tbeg[5];     // task (quartet) index range of each parity group
+};
+
+__device__ __forceinline__ PairClass unpack_cls(int c) { return PairClass{c & 255, (c >> 8) & 255, c >> 16}; }
+
+// task index -> (a >= b) sorted pair indices within a parity group
+__device__ __forceinline__ void decode_task(const PairTableDev& T, int64_t t, int64_t& a, int64_t& b) {
+    int g = 0;
+    if (t >= T.tbeg[1]) g = 1;
+    if (t >= T.tbeg[2]) g = 2;
+    if (t >= T.tbeg[3]) g = 3;
+    int64_t u = t - T.tbeg[g];
+    int64_t r = (int64_t)((sqrt(8.0 * (double)u + 1.0) - 1.0) * 0.5);
+    while (r * (r + 1) / 2 > u) --r;
+    while ((r + 1) * (r + 2) / 2 <= u) ++r;
+    a = T.gbeg[g] + r;
+    b = T.gbeg[g] + (u - r * (r + 1) / 2);
+}
+
+__device__ __forceinline__ double quartet_value(const PairTableDev& T, int64_t a, int64_t b, const double* boys, const double* herm) {
+    return eri_ao_quartet(T.pp + T.ppoff[a] * PP_DOUBLES, T.npp[a], T.pp + T.ppoff[b] * PP_DOUBLES, T.npp[b],
+                          unpack_cls(T.cls[a]), unpack_cls(T.cls[b]), boys, herm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// Dense fill: one thread per unique parity-surviving AO quartet; parity-forbidden entries stay zero from the memset.
+__global__ void __launch_bounds__(128) k_eri_fill(PairTableDev T, const double* __restrict__ boys, const double* __restrict__ herm,
+                                                  double* __restrict__ out, int n) {
+    const int64_t ntask = T.tbeg[4];
+    const int64_t n1 = n, n2 = n1 * n1, n3 = n2 * n1;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntask; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t a, b;
+        decode_task(T, t, a, b);
+        const double v = quartet_value(T, a, b, boys, herm);
+        const int64_t i = T.pi[a], j = T.pj[a], k = T.pi[b], l = T.pj[b];
+        out[i * n3 + j * n2 + k * n1 + l] = v; out[k * n3 + l * n2 + i * n1 + j] = v;
+        out[j * n3 + i * n2 + l * n1 + k] = v; out[l * n3 + k * n2 + j * n1 + i] = v;
+        out[j * n3 + i * n2 + k * n1 + l] = v; out[l * n3 + k * n2 + i * n1 + j] = v;
+        out[i * n3 + j * n2 + l * n1 + k] = v; out[k * n3 + l * n2 + j * n1 + i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_schwarz(PairTableDev T, const double* __restrict__ boys, const double* __restrict__ herm,
+                                                 double* __restrict__ Q, int64_t npair) {
+    for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < npair; a += (int64_t)gridDim.x * blockDim.x)
+        Q[a] = sqrt(fabs(quartet_value(T, a, a, boys, herm)));
+}
+
+__global__ void k_eri_single(const double* __restrict__ ppA, int nA, int clsA, const double* __restrict__ ppB, int nB, int clsB,
+                             const double* __restrict__ boys, const double* __restrict__ herm, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *out = eri_ao_quartet(ppA, nA, ppB, nB, unpack_cls(clsA), unpack_cls(clsB), boys, herm);
+}
+
+// out[o, p, r] = sum_e val[e] * in[o, col[e], r] over the CSR row p: one index of a tensor rotated by a sparse matrix.
+__global__ void __launch_bounds__(256) k_rotate_axis(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ rowptr,
+                                                     const int* __restrict__ col, const double* __restrict__ val, int64_t outer, int n_in,
+                                                     int n_out, int64_t inner) {
+    const int64_t total = outer * n_out * inner;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = x % inner;
+        const int64_t op = x / inner;
+        const int p = (int)(op % n_out);
+        const int64_t o = op / n_out;
+        const double* src = in + o * n_in * inner + r;
+        double s = 0.0;
+        for (int e = rowptr[p]; e < rowptr[p + 1]; ++e) s = fma(val[e], src[(int64_t)col[e] * inner], s);
+        out[x] = s;
+    }
+}
+
+// Fused stored-mode J+K.  Block (chunk c, row i) owns the contiguous slabs E[i, l, :, :], l in the chunk.
+// Thread (rt, j): j = tid % n fixed, k = rt, rt + r, ...;  one coalesced read of each element serves
+//   J[i,l]  += E[i,l,k,j] * P[k,j]     (block reduction, written once)
+//   K[i,j]  += E[i,l,k,j] * P[k,l]     (register accumulator over k and l, written once per block to Kpart)
+template <int ND>
+__global__ void __launch_bounds__(1024) k_jk_stored(const double* __restrict__ E, const double* __restrict__ P, double* __restrict__ J,
+                                                    double* __restrict__ Kpart, int n, int r, int lch, int nchunk) {
+    extern __shared__ double sm[];
+    const int i = blockIdx.y, c = blockIdx.x;
+    const int tid = threadIdx.x, j = tid % n, rt = tid / n;
+    const bool active = tid < n * r;                   // blockDim.x is n * r rounded up to a whole warp
+    const int nwarp = blockDim.x >> 5, warp = tid >> 5, lane = tid & 31;
+    const int l0 = c * lch, l1 = min(n, l0 + lch);
+    const size_t nn = (size_t)n * n;
+    double* sJ = sm;                                   // [ND][lch][nwarp]
+    double* sK = sm + (size_t)ND * lch * nwarp;        // [ND][r][n]
+    double accK[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) accK[d] = 0.0;
+    for (int l = l0; l < l1; ++l) {
+        const double* Eb = E + ((size_t)i * n + l) * nn;
+        double accJ[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) accJ[d] = 0.0;
+#pragma unroll 4
+        for (int k = active ? rt : n; k < n; k += r) {
+            const double e = __ldcs(Eb + (size_t)k * n + j);   // streamed once: evict-first
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                accJ[d] = fma(e, __ldg(P + d * nn + (size_t)k * n + j), accJ[d]);
+                accK[d] = fma(e, __ldg(P + d * nn + (size_t)k * n + l), accK[d]);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double v = accJ[d];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) sJ[((size_t)d * lch + (l - l0)) * nwarp + warp] = v;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+        if (active) sK[((size_t)d * r + rt) * n + j] = accK[d];
+    __syncthreads();
+    for (int x = tid; x < ND * (l1 - l0); x += blockDim.x) {
+        const int d = x / (l1 - l0), ll = x % (l1 - l0);
+        double v = 0.0;
+        for (int w = 0; w < nwarp; ++w) v += sJ[((size_t)d * lch + ll) * nwarp + w];
+        if (J) J[d * nn + (size_t)i * n + l0 + ll] = v;
+    }
+    if (Kpart)
+        for (int x = tid; x < ND * n; x += blockDim.x) {
+            const int d = x / n, jj = x % n;
+            double v = 0.0;
+            for (int q = 0; q < r; ++q) v += sK[((size_t)d * r + q) * n + jj];
+            Kpart[(((size_t)d * n + i) * nchunk + c) * n + jj] = v;
+        }
+}
+
+__global__ void k_kpart_reduce(const double* __restrict__ Kpart, double* __restrict__ K, int nD, int n, int nchunk) {
+    const int64_t total = (int64_t)nD * n * n;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        const int jj = (int)(x % n);
+        const int64_t di = x / n;
+        double v = 0.0;
+        for (int c = 0; c < nchunk; ++c) v += Kpart[(di * nchunk + c) * n + jj];
+        K[x] = v;
+    }
+}
+
+__global__ void k_absmax(const double* __restrict__ x, int64_t count, unsigned long long* out) {
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) m = fmax(m, fabs(x[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// out = acc + sign * acc^T  (J = Jacc + Jacc^T, K = Kacc + Kacc^T; see k_jk_direct)
+__global__ void k_add_transpose(const double* __restrict__ acc, double* __restrict__ out, int nD, int n) {
+    const int64_t nn = (int64_t)n * n, total = nD * nn;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = x / nn, ij = x % nn;
+        const int i = (int)(ij / n), j = (int)(ij % n);
+        out[x] = acc[x] + acc[d * nn + (int64_t)j * n + i];
+    }
+}
+
+// Direct J/K: one thread per unique parity-surviving AO quartet (a >= b in the sorted pair order), Schwarz-screened.
+// Symmetric P.  With v' = v * (1/2 if i==j) * (1/2 if k==l) * (1/2 if a==b), the 8 images of (ij|kl) reduce to
+//   Jacc[i,j] += v' (P[k,l] + P[l,k])      Jacc[k,l] += v' (P[i,j] + P[j,i])
+//   Kacc[i,l] += v' P[k,j]   Kacc[j,l] += v' P[k,i]   Kacc[i,k] += v' P[l,j]   Kacc[j,k] += v' P[l,i]
+// followed by J = Jacc + Jacc^T, K = Kacc + Kacc^T (k_add_transpose).
+__global__ void __launch_bounds__(128) k_jk_direct(PairTableDev T, const double* __restrict__ boys, const double* __restrict__ herm,
+                                                   const double* __restrict__ Q, const double* __restrict__ P, double* __restrict__ Jacc,
+                                                   double* __restrict__ Kacc, int n, int nD, double tau,
+                                                   const unsigned long long* scalars_in, unsigned long long* counter,
+                                                   int rank, int nranks) {
+    const int64_t ntask = T.tbeg[4];
+    const int64_t nn = (int64_t)n * n;
+    const double dmax = __longlong_as_double((long long)scalars_in[0]);
+    const double thr = (tau > 0.0 && dmax > 0.0) ? tau / dmax : 0.0;
+    constexpr int64_t CHUNK = 1024;
+    const int64_t nchunks = (ntask + CHUNK - 1) / CHUNK;
+    unsigned long long evaluated = 0;
+    for (int64_t ch = (int64_t)blockIdx.x * nranks + rank; ch < nchunks; ch += (int64_t)gridDim.x * nranks) {
+        const int64_t tend = min(ntask, (ch + 1) * CHUNK);
+        for (int64_t t = ch * CHUNK + threadIdx.x; t < tend; t += blockDim.x) {
+            int64_t a, b;
+            decode_task(T, t, a, b);
+            if (Q[a] * Q[b] < thr) continue;
+            ++evaluated;
+            double v = quartet_value(T, a, b, boys, herm);
+            const int i = T.pi[a], j = T.pj[a], k = T.pi[b], l = T.pj[b];
+            if (i == j) v *= 0.5;
+            if (k == l) v *= 0.5;
+            if (a == b) v *= 0.5;
+            for (int d = 0; d < nD; ++d) {
+                const double* Pd = P + d * nn;
+                double* Jd = Jacc + d * nn;
+                double* Kd = Kacc + d * nn;
+                atomicAdd(Jd + (int64_t)i * n + j, v * (Pd[(int64_t)k * n + l] + Pd[(int64_t)l * n + k]));
+                atomicAdd(Jd + (int64_t)k * n + l, v * (Pd[(int64_t)i * n + j] + Pd[(int64_t)j * n + i]));
+                atomicAdd(Kd + (int64_t)i * n + l, v * Pd[(int64_t)k * n + j]);
+                atomicAdd(Kd + (int64_t)j * n + l, v * Pd[(int64_t)k * n + i]);
+                atomicAdd(Kd + (int64_t)i * n + k, v * Pd[(int64_t)l * n + j]);
+                atomicAdd(Kd + (int64_t)j * n + k, v * Pd[(int64_t)l * n + i]);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) evaluated += __shfl_down_sync(0xffffffffu, evaluated, o);
+    if ((threadIdx.x & 31) == 0 && evaluated) atomicAdd(counter, evaluated);
+}
+
+// FP64 pipe peak probe: 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters, double x) {
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double y = 1.0 - x;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+        a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PairTableDev table_dev(const tuna_ctx* ctx) {
+    PairTableDev T;
+    T.pi = ctx->d_pi; T.pj = ctx->d_pj; T.cls = ctx->d_cls; T.npp = ctx->d_npp; T.ppoff = ctx->d_ppoff; T.pp = ctx->d_pp;
+    for (int g = 0; g < 5; ++g) { T.gbeg[g] = ctx->pt.group_begin[g]; T.tbeg[g] = ctx->task_begin[g]; }
+    return T;
+}
+
+static int grid_for(const tuna_ctx* ctx, int64_t work_items, int block, int per_sm) {
+    int64_t want = (work_items + block - 1) / block;
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    if (want < 1) want = 1;
+    return (int)std::min(want, cap);
+}
+
+// F(a,b) of SURVEY.md section 8(d): flops of the reference algorithm per primitive quartet.
+static double reference_flops(int cls_a, int cls_b) {
+    const int lxa = cls_a & 255, lya = (cls_a >> 8) & 255, lza = cls_a >> 16;
+    const int lxb = cls_b & 255, lyb = (cls_b >> 8) & 255, lzb = cls_b >> 16;
+    const int Nmax = lxa + lya + lza + lxb + lyb + lzb, Vmax = lza + lzb;
+    const double nx = (lxa / 2 + 1) * (lxb / 2 + 1), nxy = nx * (lya / 2 + 1) * (lyb / 2 + 1), nzz = (lza + 1) * (lzb + 1);
+    double rt = Nmax + 1;
+    for (int v = 1; v <= Vmax; ++v) rt += (Nmax - v + 1) * (v == 1 ? 1 : 3);
+    return 6 + 32 + 3 * Nmax + (Nmax + 1) + rt + 2 * nx + 3 * nxy + 5 * nxy * nzz + 8;
+}
+
+static void count_work(tuna_ctx* ctx) {
+    const PairTable& T = ctx->pt;
+    const int64_t np = T.npair;
+    ctx->n_unique = np * (np + 1) / 2;
+    ctx->n_surviving = 0; ctx->n_primq = 0; ctx->alg_eri_flops = 0;
+    ctx->task_begin[0] = 0;
+    for (int g = 0; g < 4; ++g) {
+        const int64_t ng = T.group_begin[g + 1] - T.group_begin[g];
+        ctx->task_begin[g + 1] = ctx->task_begin[g] + ng * (ng + 1) / 2;
+        std::map<std::pair<int, int>, int64_t> hist;   // (class, npp) -> count
+        for (int64_t a = T.group_begin[g]; a < T.group_begin[g + 1]; ++a) hist[{T.cls[a], T.npp[a]}]++;
+        std::vector<std::pair<std::pair<int, int>, int64_t>> keys(hist.begin(), hist.end());
+        for (size_t x = 0; x < keys.size(); ++x)
+            for (size_t y = 0; y <= x; ++y) {
+                const double cnt = (x == y) ? (double)keys[x].second * (keys[x].second + 1) / 2 : (double)keys[x].second * keys[y].second;
+                const double primq = cnt * keys[x].first.second * keys[y].first.second;
+                ctx->n_primq += (int64_t)primq;
+                ctx->alg_eri_flops += primq * reference_flops(keys[x].first.first, keys[y].first.first);
+            }
+    }
+    ctx->n_surviving = ctx->task_begin[4];
+    ctx->alg_digest_flops = 12.0 * (double)ctx->n_surviving;
+}
+
+static int build_csr(tuna_ctx* ctx, CsrDev& M, int rows, int cols, const std::vector<double>& dense) {
+    std::vector<int> rowptr(rows + 1, 0), col;
+    std::vector<double> val;
+    for (int r = 0; r < rows; ++r) {
+        for (int c = 0; c < cols; ++c) {
+            const double v = dense[(size_t)r * cols + c];
+            if (v != 0.0) { col.push_back(c); val.push_back(v); }
+        }
+        rowptr[r + 1] = (int)col.size();
+    }
+    M.rows = rows; M.cols = cols;
+    int rc;
+    if ((rc = dev_alloc(ctx, &M.rowptr, rowptr.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &M.col, std::max<size_t>(col.size(), 1)))) return rc;
+    if ((rc = dev_alloc(ctx, &M.val, std::max<size_t>(val.size(), 1)))) return rc;
+    CK(cudaMemcpyAsync(M.rowptr, rowptr.data(), rowptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (!col.empty()) {
+        CK(cudaMemcpyAsync(M.col, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(M.val, val.data(), val.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TUNA_OK;
+}
+
+static int rotate(tuna_ctx* ctx, const CsrDev& M, const double* in, double* out, int64_t outer, int64_t inner) {
+    const int64_t total = outer * M.rows * inner;
+    if (total == 0) return TUNA_OK;
+    k_rotate_axis<<<grid_for(ctx, total, 256, 16), 256, 0, ctx->stream>>>(in, out, M.rowptr, M.col, M.val, outer, M.cols, M.rows, inner);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TUNA_OK;
+}
+
+static int ensure_mats(tuna_ctx* ctx, int nD, int n, int ncart) {
+    int rc;
+    const size_t need = (size_t)nD * n * n;
+    if (need > ctx->cap_mat) {
+        if ((rc = dev_alloc(ctx, &ctx->d_P, need))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_J, need))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_K, need))) return rc;
+        ctx->cap_mat = need;
+    }
+    const size_t needc = (size_t)nD * ncart * ncart;
+    if (ncart > 0 && needc > ctx->cap_cart) {
+        if ((rc = dev_alloc(ctx, &ctx->d_Pc, needc))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_Jc, needc))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_Kc, needc))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_tmp, needc))) return rc;
+        ctx->cap_cart = needc;
+    }
+    const size_t needp = 3 * need * sizeof(double);
+    if (needp > ctx->cap_pin) {
+        if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+        ctx->h_pin = nullptr;
+        cudaError_t e = cudaMallocHost((void**)&ctx->h_pin, needp);
+        if (e != cudaSuccess) { cudaGetLastError(); ctx->cap_pin = 0; FAIL(TUNA_ERR_NOMEM, "pinned host allocation failed"); }
+        ctx->cap_pin = needp;
+    }
+    return TUNA_OK;
+}
+
+static int ensure_schwarz(tuna_ctx* ctx) {
+    if (ctx->d_Q) return TUNA_OK;
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_Q, (size_t)ctx->pt.npair))) return rc;
+    k_schwarz<<<grid_for(ctx, ctx->pt.npair, 128, 16), 128, 0, ctx->stream>>>(table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->pt.npair);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TUNA_OK;
+}
+
+extern "C" {
+
+int tuna_ctx_create(int device, tuna_ctx** out) {
+    if (!out) return TUNA_ERR_ARG;
+    *out = nullptr;
+    tuna_ctx* ctx = new (std::nothrow) tuna_ctx;
+    if (!ctx) return TUNA_ERR_NOMEM;
+    ctx->device = device;
+    *out = ctx;   // returned even on failure so that tuna_last_error can be read; caller destroys it
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) FAIL(TUNA_ERR_ARG, "no such CUDA device: " + std::to_string(device));
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (int w = 0; w < 4; ++w)
+        for (int s = 0; s < 2; ++s) CK(cudaEventCreate(&ctx->ev[w][s]));
+    std::vector<double> boys, herm;
+    build_boys_table(boys);
+    build_hermite_poly_table(herm);
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_boys, boys.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_herm, herm.size()))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_scalars, (size_t)4))) return rc;
+    CK(cudaMemcpy(ctx->d_boys, boys.data(), boys.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_herm, herm.data(), herm.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_scalars, 0, 4 * sizeof(unsigned long long)));
+    return TUNA_OK;
+}
+
+int tuna_ctx_destroy(tuna_ctx* ctx) {
+    if (!ctx) return TUNA_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    dev_free(&ctx->d_boys); dev_free(&ctx->d_herm); dev_free(&ctx->d_scalars);
+    dev_free(&ctx->d_pi); dev_free(&ctx->d_pj); dev_free(&ctx->d_cls); dev_free(&ctx->d_npp); dev_free(&ctx->d_ppoff); dev_free(&ctx->d_pp);
+    dev_free(&ctx->d_Q);
+    dev_free(&ctx->U.rowptr); dev_free(&ctx->U.col); dev_free(&ctx->U.val);
+    dev_free(&ctx->Ut.rowptr); dev_free(&ctx->Ut.col); dev_free(&ctx->Ut.val);
+    dev_free(&ctx->d_eri_cart); dev_free(&ctx->d_eri_sph);
+    dev_free(&ctx->d_P); dev_free(&ctx->d_J); dev_free(&ctx->d_K);
+    dev_free(&ctx->d_Pc); dev_free(&ctx->d_Jc); dev_free(&ctx->d_Kc); dev_free(&ctx->d_tmp); dev_free(&ctx->d_Kpart);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (int w = 0; w < 4; ++w)
+        for (int s = 0; s < 2; ++s) if (ctx->ev[w][s]) cudaEventDestroy(ctx->ev[w][s]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return TUNA_OK;
+}
+
+const char* tuna_last_error(const tuna_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int tuna_set_stream(tuna_ctx* ctx, void* s) {
+    if (!ctx) return TUNA_ERR_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return TUNA_OK;
+}
+
+int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int32_t* lmn, const int32_t* nprim, const int64_t* prim_offset,
+                   const double* exps, const double* coef_eff) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (ncart <= 0 || !origins_z || !lmn || !nprim || !prim_offset || !exps || !coef_eff) FAIL(TUNA_ERR_ARG, "tuna_set_basis: null or empty basis");
+    CK(cudaSetDevice(ctx->device));
+    HostBasis& B = ctx->hb;
+    B = HostBasis();
+    B.ncart = ncart;
+    int64_t total = 0;
+    for (int i = 0; i < ncart; ++i) {
+        if (nprim[i] <= 0) FAIL(TUNA_ERR_ARG, "tuna_set_basis: basis function without primitives");
+        for (int c = 0; c < 3; ++c)
+            if (lmn[3 * i + c] < 0 || lmn[3 * i + c] > 5) FAIL(TUNA_ERR_ARG, "tuna_set_basis: angular momentum outside 0..5 (only up to H functions, tuna_molecule.py:612-618)");
+        if (lmn[3 * i] + lmn[3 * i + 1] + lmn[3 * i + 2] > 5) FAIL(TUNA_ERR_ARG, "tuna_set_basis: shell angular momentum above 5");
+        total = std::max<int64_t>(total, prim_offset[i] + nprim[i]);
+    }
+    try {
+        B.oz.assign(origins_z, origins_z + ncart);
+        B.lmn.assign(lmn, lmn + 3 * (size_t)ncart);
+        B.nprim.assign(nprim, nprim + ncart);
+        B.off.assign(prim_offset, prim_offset + ncart);
+        B.exps.assign(exps, exps + total);
+        B.ceff.assign(coef_eff, coef_eff + total);
+        for (int64_t k = 0; k < total; ++k)
+            if (!(B.exps[k] > 0.0)) FAIL(TUNA_ERR_ARG, "tuna_set_basis: non-positive exponent");
+        build_pair_table(B, ctx->pt);
+    } catch (const std::bad_alloc&) {
+        FAIL(TUNA_ERR_NOMEM, "host allocation failed while building the pair table");
+    }
+    ctx->ncart = ncart;
+    const PairTable& T = ctx->pt;
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_pi, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_pj, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_cls, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_npp, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ppoff, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_pp, T.pp.size()))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_pi, T.pi.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pj, T.pj.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_cls, T.cls.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_npp, T.npp.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ppoff, T.ppoff.data(), T.npair * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pp, T.pp.data(), T.pp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dev_free(&ctx->d_Q);
+    dev_free(&ctx->d_eri_cart);
+    dev_free(&ctx->d_eri_sph);
+    ctx->n_stored = 0;
+    ctx->nbf = 0;
+    count_work(ctx);
+    return TUNA_OK;
+}
+
+int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_set_transform: call tuna_set_basis first");
+    if (nbf <= 0 || !U) FAIL(TUNA_ERR_ARG, "tuna_set_transform: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int nc = ctx->ncart;
+    std::vector<double> u(U, U + (size_t)nbf * nc), ut((size_t)nc * nbf);
+    for (int p = 0; p < nbf; ++p)
+        for (int a = 0; a < nc; ++a) ut[(size_t)a * nbf + p] = u[(size_t)p * nc + a];
+    int rc;
+    if ((rc = build_csr(ctx, ctx->U, nbf, nc, u))) return rc;
+    if ((rc = build_csr(ctx, ctx->Ut, nc, nbf, ut))) return rc;
+    ctx->nbf = nbf;
+    ctx->U_identity = (nbf == nc);
+    for (int p = 0; p < nbf && ctx->U_identity; ++p)
+        for (int a = 0; a < nc; ++a)
+            if (u[(size_t)p * nc + a] != (p == a ? 1.0 : 0.0)) { ctx->U_identity = false; break; }
+    return TUNA_OK;
+}
+
+int tuna_eri_fill_cart(tuna_ctx* ctx) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_eri_fill_cart: call tuna_set_basis first");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = ctx->ncart, count = n * n * n * n;
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_eri_cart, count))) return rc;
+    CK(cudaMemsetAsync(ctx->d_eri_cart, 0, count * sizeof(double), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
+    k_eri_fill<<<grid_for(ctx, ctx->task_begin[4], 128, 16), 128, 0, ctx->stream>>>(table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_eri_cart, ctx->ncart);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[0][1], ctx->stream));
+    return TUNA_OK;
+}
+
+int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (!ctx->d_eri_cart) FAIL(TUNA_ERR_STATE, "tuna_eri_cart_to_sph: no Cartesian tensor resident (call tuna_eri_fill_cart)");
+    if (ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_eri_cart_to_sph: call tuna_set_transform first");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t nc = ctx->ncart, nb = ctx->nbf;
+    double* t1 = nullptr; double* t2 = nullptr; double* t3 = nullptr;
+    int rc;
+    dev_free(&ctx->d_eri_sph);
+    ctx->n_stored = 0;
+    CK(cudaEventRecord(ctx->ev[1][0], ctx->stream));
+    if (ctx->U_identity) {   // CARTHARM: no rotation (tuna_kernel.py:481-483)
+        if (keep_cart) {
+            if ((rc = dev_alloc(ctx, &ctx->d_eri_sph, (size_t)(nc * nc * nc * nc)))) return rc;
+            CK(cudaMemcpyAsync(ctx->d_eri_sph, ctx->d_eri_cart, (size_t)(nc * nc * nc * nc) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            ctx->d_eri_sph = ctx->d_eri_cart;
+            ctx->d_eri_cart = nullptr;
+        }
+        CK(cudaEventRecord(ctx->ev[1][1], ctx->stream));
+        ctx->n_stored = (int)nc;
+        return TUNA_OK;
+    }
+    if ((rc = dev_alloc(ctx, &t1, (size_t)(nb * nc * nc * nc)))) return rc;
+    if ((rc = rotate(ctx, ctx->U, ctx->d_eri_cart, t1, 1, nc * nc * nc))) { dev_free(&t1); return rc; }
+    if (!keep_cart) { CK(cudaStreamSynchronize(ctx->stream)); dev_free(&ctx->d_eri_cart); }
+    if ((rc = dev_alloc(ctx, &t2, (size_t)(nb * nb * nc * nc)))) { dev_free(&t1); return rc; }
+    if ((rc = rotate(ctx, ctx->U, t1, t2, nb, nc * nc))) { dev_free(&t1); dev_free(&t2); return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    dev_free(&t1);
+    if ((rc = dev_alloc(ctx, &t3, (size_t)(nb * nb * nb * nc)))) { dev_free(&t2); return rc; }
+    if ((rc = rotate(ctx, ctx->U, t2, t3, nb * nb, nc))) { dev_free(&t2); dev_free(&t3); return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    dev_free(&t2);
+    if ((rc = dev_alloc(ctx, &ctx->d_eri_sph, (size_t)(nb * nb * nb * nb)))) { dev_free(&t3); return rc; }
+    if ((rc = rotate(ctx, ctx->U, t3, ctx->d_eri_sph, nb * nb * nb, 1))) { dev_free(&t3); return rc; }
+    CK(cudaEventRecord(ctx->ev[1][1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dev_free(&t3);
+    ctx->n_stored = (int)nb;
+    return TUNA_OK;
+}
+
+int tuna_eri_download(tuna_ctx* ctx, int which, double* host_out) {
+    if (!ctx || !host_out) return TUNA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const double* src = which == 0 ? ctx->d_eri_cart : ctx->d_eri_sph;
+    const size_t n = which == 0 ? ctx->ncart : ctx->n_stored;
+    if (!src) FAIL(TUNA_ERR_STATE, "tuna_eri_download: requested tensor is not resident");
+    CK(cudaMemcpyAsync(host_out, src, n * n * n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TUNA_OK;
+}
+
+int tuna_eri_upload(tuna_ctx* ctx, int n, const double* host_in) {
+    if (!ctx || !host_in || n <= 0) return TUNA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t count = (size_t)n * n * n * n;
+    int rc;
+    ctx->n_stored = 0;
+    if ((rc = dev_alloc(ctx, &ctx->d_eri_sph, count))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_eri_sph, host_in, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_stored = n;
+    return TUNA_OK;
+}
+
+int tuna_eri_single(tuna_ctx* ctx, int i, int j, int k, int l, double* out) {
+    if (!ctx || !out) return TUNA_ERR_ARG;
+    const int n = ctx->ncart;
+    if (n == 0) FAIL(TUNA_ERR_STATE, "tuna_eri_single: call tuna_set_basis first");
+    if (i < 0 || j < 0 || k < 0 || l < 0 || i >= n || j >= n || k >= n || l >= n) FAIL(TUNA_ERR_ARG, "tuna_eri_single: index out of range");
+    CK(cudaSetDevice(ctx->device));
+    const HostBasis& B = ctx->hb;
+    auto cls_of = [&](int a, int b) {
+        return (B.lmn[3 * a] + B.lmn[3 * b]) | ((B.lmn[3 * a + 1] + B.lmn[3 * b + 1]) << 8) | ((B.lmn[3 * a + 2] + B.lmn[3 * b + 2]) << 16);
+    };
+    const int cA = cls_of(i, j), cB = cls_of(k, l);
+    if ((((cA & 255) + (cB & 255)) & 1) || ((((cA >> 8) & 255) + ((cB >> 8) & 255)) & 1)) { *out = 0.0; return TUNA_OK; }   // pyx:1397-1400
+    const int nA = B.nprim[i] * B.nprim[j], nB = B.nprim[k] * B.nprim[l];
+    std::vector<double> rec((size_t)(nA + nB) * PP_DOUBLES), scratch;
+    double* r = rec.data();
+    for (int a = 0; a < B.nprim[i]; ++a)
+        for (int b = 0; b < B.nprim[j]; ++b, r += PP_DOUBLES) fill_prim_record(r, B, i, j, B.off[i] + a, B.off[j] + b, scratch);
+    for (int a = 0; a < B.nprim[k]; ++a)
+        for (int b = 0; b < B.nprim[l]; ++b, r += PP_DOUBLES) fill_prim_record(r, B, k, l, B.off[k] + a, B.off[l] + b, scratch);
+    double* d = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d, rec.size() + 1))) return rc;
+    CK(cudaMemcpyAsync(d + 1, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_eri_single<<<1, 32, 0, ctx->stream>>>(d + 1, nA, cA, d + 1 + (size_t)nA * PP_DOUBLES, nB, cB, ctx->d_boys, ctx->d_herm, d);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dev_free(&d);
+    return TUNA_OK;
+}
+
+int tuna_schwarz(tuna_ctx* ctx, double* host_out) {
+    if (!ctx || !host_out) return TUNA_ERR_ARG;
+    if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_schwarz: call tuna_set_basis first");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_schwarz(ctx))) return rc;
+    std::vector<double> q((size_t)ctx->pt.npair);
+    CK(cudaMemcpyAsync(q.data(), ctx->d_Q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int n = ctx->ncart;
+    for (int64_t a = 0; a < ctx->pt.npair; ++a) {
+        host_out[(size_t)ctx->pt.pi[a] * n + ctx->pt.pj[a]] = q[a];
+        host_out[(size_t)ctx->pt.pj[a] * n + ctx->pt.pi[a]] = q[a];
+    }
+    return TUNA_OK;
+}
+
+int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (!ctx->d_eri_sph || ctx->n_stored == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_stored: no stored tensor resident");
+    if (nD <= 0 || !dP) FAIL(TUNA_ERR_ARG, "tuna_jk_stored: bad arguments");
+    const int n = ctx->n_stored;
+    if (n > 1024) FAIL(TUNA_ERR_ARG, "tuna_jk_stored: stored mode supports n <= 1024");
+    const int r = std::max(1, 256 / n);
+    const int threads = (n * r + 31) / 32 * 32;
+    const int lch = 4;
+    const int nchunk = (n + lch - 1) / lch;
+    const int nwarp = (threads + 31) / 32;
+    int rc;
+    const size_t need_kpart = (size_t)std::min(nD, 4) * n * nchunk * n;
+    if (dK && need_kpart > ctx->cap_kpart) {
+        if ((rc = dev_alloc(ctx, &ctx->d_Kpart, need_kpart))) return rc;
+        ctx->cap_kpart = need_kpart;
+    }
+    CK(cudaEventRecord(ctx->ev[2][0], ctx->stream));
+    const size_t nn = (size_t)n * n;
+    for (int d0 = 0; d0 < nD; d0 += 4) {
+        const int nd = std::min(4, nD - d0);
+        const size_t smem = ((size_t)nd * lch * nwarp + (size_t)nd * r * n) * sizeof(double);
+        dim3 grid(nchunk, n);
+        const double* P = dP + d0 * nn;
+        double* J = dJ ? dJ + d0 * nn : nullptr;
+        double* Kp = dK ? ctx->d_Kpart : nullptr;
+        switch (nd) {
+            case 1: k_jk_stored<1><<<grid, threads, smem, ctx->stream>>>(ctx->d_eri_sph, P, J, Kp, n, r, lch, nchunk); break;
+            case 2: k_jk_stored<2><<<grid, threads, smem, ctx->stream>>>(ctx->d_eri_sph, P, J, Kp, n, r, lch, nchunk); break;
+            case 3: k_jk_stored<3><<<grid, threads, smem, ctx->stream>>>(ctx->d_eri_sph, P, J, Kp, n, r, lch, nchunk); break;
+            default: k_jk_stored<4><<<grid, threads, smem, ctx->stream>>>(ctx->d_eri_sph, P, J, Kp, n, r, lch, nchunk); break;
+        }
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (dK) {
+            k_kpart_reduce<<<grid_for(ctx, (int64_t)nd * nn, 256, 8), 256, 0, ctx->stream>>>(ctx->d_Kpart, dK + d0 * nn, nd, n, nchunk);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[2][1], ctx->stream));
+    return TUNA_OK;
+}
+
+int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (!ctx->d_eri_sph || ctx->n_stored == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_stored: no stored tensor resident");
+    if (nD <= 0 || !P) FAIL(TUNA_ERR_ARG, "tuna_jk_stored: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n_stored;
+    int rc;
+    if ((rc = ensure_mats(ctx, nD, n, 0))) return rc;
+    const size_t bytes = (size_t)nD * n * n * sizeof(double);
+    double* hP = ctx->h_pin;
+    double* hJ = hP + (size_t)nD * n * n;
+    double* hK = hJ + (size_t)nD * n * n;
+    std::memcpy(hP, P, bytes);
+    CK(cudaMemcpyAsync(ctx->d_P, hP, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = tuna_jk_stored_dev(ctx, nD, ctx->d_P, J ? ctx->d_J : nullptr, K ? ctx->d_K : nullptr))) return rc;
+    if (J) CK(cudaMemcpyAsync(hJ, ctx->d_J, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (K) CK(cudaMemcpyAsync(hK, ctx->d_K, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (J) std::memcpy(J, hJ, bytes);
+    if (K) std::memcpy(K, hK, bytes);
+    return TUNA_OK;
+}
+
+int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks) FAIL(TUNA_ERR_ARG, "tuna_set_shard: bad rank / nranks");
+    ctx->shard_rank = rank; ctx->shard_n = nranks;
+    return TUNA_OK;
+}
+
+int tuna_jk_direct_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK, double tau) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: call tuna_set_basis first");
+    if (ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: call tuna_set_transform first");
+    if (nD <= 0 || !dP) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments");
+    const int nc = ctx->ncart, nb = ctx->nbf;
+    int rc;
+    if ((rc = ensure_mats(ctx, nD, nb, nc))) return rc;
+    if ((rc = ensure_schwarz(ctx))) return rc;
+    const size_t ncc = (size_t)nc * nc;
+    // P_cart = U^T P U
+    if ((rc = rotate(ctx, ctx->Ut, dP, ctx->d_tmp, nD, nb))) return rc;               // [d][a][q] = sum_p U[p,a] P[d][p][q]
+    if ((rc = rotate(ctx, ctx->Ut, ctx->d_tmp, ctx->d_Pc, (int64_t)nD * nc, 1))) return rc;   // [d][a][b] = sum_q U[q,b] tmp[d][a][q]
+    CK(cudaMemsetAsync(ctx->d_scalars, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    k_absmax<<<grid_for(ctx, (int64_t)nD * ncc, 256, 4), 256, 0, ctx->stream>>>(ctx->d_Pc, (int64_t)nD * ncc, ctx->d_scalars);
+    ctx->launches++;
+    CK(cudaMemsetAsync(ctx->d_Jc, 0, nD * ncc * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_Kc, 0, nD * ncc * sizeof(double), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
+    k_jk_direct<<<grid_for(ctx, ctx->task_begin[4] / ctx->shard_n + 1, 128, 16), 128, 0, ctx->stream>>>(
+        table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, nc, nD, tau, ctx->d_scalars, ctx->d_scalars + 1,
+        ctx->shard_rank, ctx->shard_n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
+    // J = U (Jacc + Jacc^T) U^T, same for K
+    for (int which = 0; which < 2; ++which) {
+        double* acc = which == 0 ? ctx->d_Jc : ctx->d_Kc;
+        double* out = which == 0 ? dJ : dK;
+        if (!out) continue;
+        k_add_transpose<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(acc, ctx->d_Pc, nD, nc);   // d_Pc reused as scratch
+        ctx->launches++;
+        if ((rc = rotate(ctx, ctx->U, ctx->d_Pc, ctx->d_tmp, nD, nc))) return rc;          // [d][p][b]
+        if ((rc = rotate(ctx, ctx->U, ctx->d_tmp, out, (int64_t)nD * nb, 1))) return rc;    // [d][p][q]
+    }
+    CK(cudaGetLastError());
+    return TUNA_OK;
+}
+
+int tuna_jk_direct(tuna_ctx* ctx, int nD, const double* P, double* J, double* K, double tau) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (ctx->ncart == 0 || ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: basis and transform must be set first");
+    if (nD <= 0 || !P) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int nb = ctx->nbf;
+    int rc;
+    if ((rc = ensure_mats(ctx, nD, nb, ctx->ncart))) return rc;
+    const size_t bytes = (size_t)nD * nb * nb * sizeof(double);
+    double* hP = ctx->h_pin;
+    double* hJ = hP + (size_t)nD * nb * nb;
+    double* hK = hJ + (size_t)nD * nb * nb;
+    std::memcpy(hP, P, bytes);
+    CK(cudaMemcpyAsync(ctx->d_P, hP, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = tuna_jk_direct_dev(ctx, nD, ctx->d_P, J ? ctx->d_J : nullptr, K ? ctx->d_K : nullptr, tau))) return rc;
+    if (J) CK(cudaMemcpyAsync(hJ, ctx->d_J, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (K) CK(cudaMemcpyAsync(hK, ctx->d_K, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (J) std::memcpy(J, hJ, bytes);
+    if (K) std::memcpy(K, hK, bytes);
+    return TUNA_OK;
+}
+
+int tuna_get_counts(const tuna_ctx* c, int64_t counts[8]) {
+    if (!c || !counts) return TUNA_ERR_ARG;
+    tuna_ctx* ctx = const_cast<tuna_ctx*>(c);
+    unsigned long long ev = 0;
+    if (ctx->d_scalars) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(&ev, ctx->d_scalars + 1, sizeof(ev), cudaMemcpyDeviceToHost);
+    }
+    counts[0] = ctx->pt.npair; counts[1] = ctx->n_unique; counts[2] = ctx->n_surviving; counts[3] = ctx->n_primq;
+    counts[4] = (int64_t)ev; counts[5] = ctx->launches; counts[6] = ctx->ncart; counts[7] = ctx->nbf;
+    return TUNA_OK;
+}
+
+int tuna_last_kernel_ms(tuna_ctx* ctx, int which, float* ms) {
+    if (!ctx || !ms || which < 0 || which > 3) return TUNA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+    return TUNA_OK;
+}
+
+int tuna_algorithmic_flops(const tuna_ctx* ctx, double* eri_flops, double* digest) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (eri_flops) *eri_flops = ctx->alg_eri_flops;
+    if (digest) *digest = ctx->alg_digest_flops;
+    return TUNA_OK;
+}
+
+int tuna_fp64_peak_probe(tuna_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return TUNA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d, (size_t)1))) return rc;
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = (double)blocks * threads * iters * 8 * 2 / (ms * 1e-3) * 1e-12;
+        if (rep > 0) best = std::max(best, tf);
+    }
+    ctx->launches += 5;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dev_free(&d);
+    *tflops = best;
+    return TUNA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,322 @@
+"""Drop-in ERI / Fock provider: the reference's Python call signatures over the CUDA library.
+
+Each public function keeps the name, argument order and return convention of the reference function it
+replaces; `install()` rebinds those names on the reference's flat modules so that
+tuna_scf, tuna_dft (hybrid exact exchange goes through K) and the post-HF modules use this provider with
+no reference edits.  The only compute path is libtuna_b200.so on a CUDA device — there is no CPU fallback.
+
+    reference                                                             here
+    tuna_integral.calculate_electron_repulsion_integrals  pyx:1267-1355   calculate_electron_repulsion_integrals
+    tuna_integral.calculate_electron_repulsion_integral   pyx:1376-1414   calculate_electron_repulsion_integral
+    tuna_kernel.calculate_two_electron_integrals          tuna_kernel.py:331-359
+    tuna_kernel.transform_to_spherical_harmonics          tuna_kernel.py:454-529
+    tuna_scf.calculate_coulomb_matrix                     tuna_scf.py:55-72
+    tuna_scf.calculate_exchange_matrix                    tuna_scf.py:27-44
+"""
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib
+from .basis import flatten
+
+DEFAULT_TAU = float(os.environ.get("TUNA_B200_TAU", "1e-16"))      # Schwarz threshold of direct mode
+_settings = {"mode": os.environ.get("TUNA_B200_MODE", "auto"), "device": int(os.environ.get("TUNA_B200_DEVICE", "0")),
+             "stored_fraction": 0.40, "tau": DEFAULT_TAU}
+
+
+def configure(mode=None, device=None, tau=None, stored_fraction=None):
+    """mode: 'stored' (dense tensor on the device), 'direct' (integral-driven J/K) or 'auto' (stored when
+    8*ncart^4 bytes fit in `stored_fraction` of free device memory or a post-HF consumer needs the tensor)."""
+    if mode is not None:
+        if mode not in ("stored", "direct", "auto"):
+            raise _lib.error_class(f"tuna_b200: unknown mode {mode!r}")
+        _settings["mode"] = mode
+    if device is not None:
+        _settings["device"] = int(device)
+    if tau is not None:
+        _settings["tau"] = float(tau)
+    if stored_fraction is not None:
+        _settings["stored_fraction"] = float(stored_fraction)
+
+
+def _free_device_bytes():
+    import torch  # plumbing only: device memory query
+    free, _ = torch.cuda.mem_get_info(_settings["device"])
+    return free
+
+
+class ERIHandle:
+    """What flows through `Integrals.ERI_AO` (TUNA/tuna_util.py:152-194) instead of a host ndarray.
+
+    J/K consumers use the device-resident tensor (stored mode) or the pair table (direct mode) behind `ctx`.
+    Post-HF consumers that need a real ndarray (tuna_ci.py:229, tuna_mp.py:632, tuna_cc.py:1851 ...) get one on
+    first touch: the tensor is copied device->host once and every ndarray attribute/operator is forwarded to it.
+    """
+
+    __array_priority__ = 100.0
+
+    def __init__(self, ctx, n, basis_kind, mode):
+        self.ctx, self.n, self.basis_kind, self.mode = ctx, int(n), basis_kind, mode
+        self._host = None
+        self._jk_cache = []     # [(P, J, K)] most recent first
+
+    shape = property(lambda self: (self.n,) * 4)
+    ndim = 4
+    dtype = np.dtype(np.float64)
+    size = property(lambda self: self.n ** 4)
+
+    def materialise(self) -> np.ndarray:
+        if self._host is None:
+            if self.mode == "direct":
+                self._materialise_direct()
+            else:
+                self._host = self.ctx.eri_download(0 if self.basis_kind == "cart" else 1)
+        return self._host
+
+    def _materialise_direct(self):
+        ctx = self.ctx
+        need = 8 * ctx.ncart ** 4
+        if need > 0.8 * _free_device_bytes():
+            raise MemoryError(f"tuna_b200: a dense ERI tensor was requested in direct mode but {need / 1e9:.1f} GB do not fit on the device")
+        ctx.eri_fill_cart()
+        if self.basis_kind == "cart":
+            self._host = ctx.eri_download(0)
+        else:
+            ctx.eri_cart_to_sph()
+            self._host = ctx.eri_download(1)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialise()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __getitem__(self, idx):
+        return self.materialise()[idx]
+
+    def __len__(self):
+        return self.n
+
+    def __getattr__(self, name):          # reshape, swapaxes, transpose, T, sum, ...
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialise(), name)
+
+
+def _binary(op):
+    def f(self, other):
+        return getattr(self.materialise(), op)(np.asarray(other) if isinstance(other, ERIHandle) else other)
+    return f
+
+
+for _op in ("add", "radd", "sub", "rsub", "mul", "rmul", "truediv", "rtruediv", "neg", "matmul", "rmatmul", "pow"):
+    if _op == "neg":
+        setattr(ERIHandle, "__neg__", lambda self: -self.materialise())
+    else:
+        setattr(ERIHandle, f"__{_op}__", _binary(f"__{_op}__"))
+
+
+def _context_for(bfs):
+    ctx = _lib.Context(_settings["device"])
+    try:
+        oz, lmn, nprim, exps, ceff = flatten(bfs)
+    except ValueError as e:
+        raise _lib.error_class(f"tuna_b200: {e}")
+    ctx.set_basis(oz, lmn, nprim, exps, ceff)
+    return ctx
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tuna_integral level (pyx)
+# ---------------------------------------------------------------------------------------------------------
+def calculate_electron_repulsion_integrals(n_basis, ERI_AO, bfs, num_threads):
+    """Fill the caller's dense (n,n,n,n) buffer in place and return it (pyx:1267-1355).  `num_threads` is advisory
+    (OpenMP threads of the reference); the GPU path ignores it."""
+    if len(bfs) != n_basis:
+        raise _lib.error_class("tuna_b200: n_basis does not match the basis-function list")
+    out = np.asarray(ERI_AO)
+    if out.shape != (n_basis,) * 4 or out.dtype != np.float64:
+        raise _lib.error_class("tuna_b200: ERI_AO must be a float64 array of shape (n_basis,)*4")
+    ctx = _context_for(bfs)
+    ctx.eri_fill_cart()
+    if out.flags.c_contiguous:
+        ctx.eri_download(0, out)
+    else:
+        out[...] = ctx.eri_download(0)
+    ctx.close()
+    return ERI_AO
+
+
+def calculate_electron_repulsion_integral(bf_1, bf_2, bf_3, bf_4):
+    """(12|34) for four basis functions (pyx:1376-1414)."""
+    ctx = _context_for([bf_1, bf_2, bf_3, bf_4])
+    v = ctx.eri_single(0, 1, 2, 3)
+    ctx.close()
+    return v
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tuna_kernel level
+# ---------------------------------------------------------------------------------------------------------
+def _dense_needed(calculation) -> bool:
+    """True if kern.run_post_SCF_energy_calculation will hand ERI_AO to a consumer needing an ndarray
+    (dispatch conditions at tuna_kernel.py:1146, :1152, :1161, :1175)."""
+    m = getattr(calculation, "method", None)
+    return bool(getattr(calculation, "stability_analysis", False) or getattr(m, "perturbative_method", False)
+                or getattr(calculation, "MPC_prop", 0) != 0 or getattr(m, "method_base", "") == "CC"
+                or getattr(m, "excited_state_method", False) or getattr(calculation, "time_dependent", False))
+
+
+def _choose_mode(n_cart, calculation):
+    mode = _settings["mode"]
+    if mode != "auto":
+        return mode
+    need = 8 * n_cart ** 4
+    if calculation is not None and _dense_needed(calculation):
+        return "stored"
+    return "stored" if 2.2 * need <= _settings["stored_fraction"] * _free_device_bytes() else "direct"
+
+
+def calculate_two_electron_integrals(n_basis, basis_functions, calculation):
+    """Cartesian two-electron integrals (tuna_kernel.py:331-359).  Returns an ERIHandle: the tensor (stored mode)
+    or just the pair table (direct mode) stays on the device; timers keep the reference's names."""
+    timer = _ref_timer()
+    timer("Two-electron integrals", 0)
+    mode = _choose_mode(n_basis, calculation)
+    ctx = _context_for(basis_functions)
+    if mode == "stored":
+        ctx.eri_fill_cart()
+    handle = ERIHandle(ctx, n_basis, "cart", mode)
+    timer("Two-electron integrals", 1)
+    return handle
+
+
+def transform_to_spherical_harmonics(S_cart, T_cart, V_NE_cart, D_cart, Q_cart, ERI_AO_cart, molecule, calculation, silent):
+    """Cartesian -> spherical rotation of all integrals (tuna_kernel.py:454-529); the ERI part runs on the device."""
+    U = np.asarray(molecule.spherical_harmonic_transformation_matrix, dtype=np.float64)
+    cartharm = bool(getattr(calculation, "cartesian_harmonics", False))
+    if not isinstance(ERI_AO_cart, ERIHandle):
+        raise _lib.error_class("tuna_b200: transform_to_spherical_harmonics expects the ERIHandle from calculate_two_electron_integrals")
+    ctx = ERI_AO_cart.ctx
+    if cartharm:
+        ctx.set_transform(np.eye(ctx.ncart))
+        if ERI_AO_cart.mode == "stored":
+            ctx.eri_cart_to_sph()
+        return S_cart, T_cart, V_NE_cart, D_cart, Q_cart, ERIHandle(ctx, ctx.ncart, "sph", ERI_AO_cart.mode)
+    timer = _ref_timer()
+    timer("Spherical harmonic transformation", 0)
+    S = U @ S_cart @ U.T
+    T = U @ T_cart @ U.T
+    V_NE = U @ V_NE_cart @ U.T
+    D = np.einsum("mw,awx,nx->amn", U, D_cart, U, optimize=True)
+    Q = np.einsum("mw,awx,nx->amn", U, Q_cart, U, optimize=True)
+    ctx.set_transform(U)
+    if ERI_AO_cart.mode == "stored":
+        ctx.eri_cart_to_sph()
+    handle = ERIHandle(ctx, U.shape[0], "sph", ERI_AO_cart.mode)
+    timer("Spherical harmonic transformation", 1)
+    return S, T, V_NE, D, Q, handle
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tuna_scf level
+# ---------------------------------------------------------------------------------------------------------
+_uploaded = {}     # id(ndarray) -> (weakref, ERIHandle): dense tensors handed in by the caller, uploaded once
+
+
+def _handle_for(ERI_AO):
+    if isinstance(ERI_AO, ERIHandle):
+        return ERI_AO
+    arr = np.asarray(ERI_AO)
+    if arr.ndim != 4:
+        raise _lib.error_class("tuna_b200: ERI_AO must be an ERIHandle or a 4-index array")
+    key = id(ERI_AO)
+    hit = _uploaded.get(key)
+    if hit is not None and hit[0]() is ERI_AO:
+        return hit[1]
+    ctx = _lib.Context(_settings["device"])
+    ctx.eri_upload(arr)
+    h = ERIHandle(ctx, arr.shape[0], "sph", "stored")
+    h._host = arr
+    try:
+        _uploaded[key] = (weakref.ref(ERI_AO, lambda _r, k=key: _uploaded.pop(k, None)), h)
+    except TypeError:
+        pass
+    return h
+
+
+def coulomb_and_exchange(P, ERI_AO, want_j=True, want_k=True):
+    """J and K for one density (n,n) or a stack (nD,n,n) from ONE pass over the integrals."""
+    h = _handle_for(ERI_AO)
+    P = np.asarray(P, dtype=np.float64)
+    if h.mode == "stored":
+        return h.ctx.jk_stored(P, want_j, want_k)
+    sym = np.array_equal(P, np.swapaxes(P, -1, -2))
+    if sym:
+        return h.ctx.jk_direct(P, _settings["tau"], want_j, want_k)
+    # K is not symmetric for a non-symmetric P: K[P] = K[S] + K[A] with K[A] antisymmetric.  The direct kernel
+    # assumes a symmetric density, so a general P needs the stored path.
+    raise _lib.error_class("tuna_b200: direct mode requires symmetric density matrices; use stored mode for a general P")
+
+
+def _cached_jk(P, ERI_AO, which):
+    h = _handle_for(ERI_AO)
+    P = np.asarray(P, dtype=np.float64)
+    for Pc, J, K in h._jk_cache:
+        if Pc.shape == P.shape and np.array_equal(Pc, P):
+            return (J if which == 0 else K).copy()
+    J, K = coulomb_and_exchange(P, h)
+    h._jk_cache.insert(0, (P.copy(), J, K))
+    del h._jk_cache[4:]
+    return (J if which == 0 else K).copy()
+
+
+def calculate_coulomb_matrix(P, ERI_AO):
+    """J_ij = sum_kl (ij|kl) P_kl (tuna_scf.py:55-72).  The fused kernel also produces K for the same P, which the
+    reference always asks for next (tuna_scf.py:520-521, :571-577): it is kept for that call."""
+    return _cached_jk(P, ERI_AO, 0)
+
+
+def calculate_exchange_matrix(P, ERI_AO):
+    """K_ij = sum_kl (il|kj) P_kl (tuna_scf.py:27-44)."""
+    return _cached_jk(P, ERI_AO, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# installation on the reference's modules
+# ---------------------------------------------------------------------------------------------------------
+_timer_fn = None
+
+
+def _ref_timer():
+    return _timer_fn if _timer_fn is not None else (lambda name, flag: None)
+
+
+def install(tuna_integral=None, tuna_kernel=None, tuna_scf=None, tuna_util=None):
+    """Rebind the six hot-path names on the reference's (already imported) modules.  All four are module-global
+    lookups at call time, so no reference source is edited.  Returns a dict of the originals."""
+    import sys
+    global _timer_fn
+    tuna_integral = tuna_integral or sys.modules.get("tuna_integrals.tuna_integral")
+    tuna_kernel = tuna_kernel or sys.modules.get("tuna_kernel")
+    tuna_scf = tuna_scf or sys.modules.get("tuna_scf")
+    tuna_util = tuna_util or sys.modules.get("tuna_util")
+    originals = {}
+    if tuna_util is not None:
+        _lib.error_class = getattr(tuna_util, "TunaError", _lib.error_class)
+        _timer_fn = getattr(tuna_util, "timer", None)
+    for mod, names in ((tuna_integral, ("calculate_electron_repulsion_integrals", "calculate_electron_repulsion_integral")),
+                       (tuna_kernel, ("calculate_two_electron_integrals", "transform_to_spherical_harmonics")),
+                       (tuna_scf, ("calculate_coulomb_matrix", "calculate_exchange_matrix"))):
+        if mod is None:
+            continue
+        for name in names:
+            originals[(mod.__name__, name)] = getattr(mod, name)
+            setattr(mod, name, globals()[name])
+    return originals
+
+
+def uninstall(originals):
+    import sys
+    for (modname, name), fn in originals.items():
+        setattr(sys.modules[modname], name, fn)
