@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py — the driver's benchmark contract for the TUNA SCF two-electron hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload direct:et400|stored:n2_ccpvtz|...]
+
+Headline workload (BASELINE.json configs[4], the one the metric's "1/2/4/8 B200 ... % FP64 peak" is quoted on): the
+synthetic even-tempered N2 diatomic at nbf=400 (ncart 524), direct ERI + J/K, one density.  A "step" is one Fock build:
+every parity-surviving unique AO quartet is evaluated (Schwarz-screened) and folded into J and K.  At N GPUs the quartet
+list is sharded over ranks (strong scaling) and the partial J/K are summed by one NCCL all-reduce inside the timed region.
+The stored-ERI configuration (configs[1], N2 RHF/cc-pVTZ) is measured in the same run at N=1 and reported under "stored".
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput; `e2e` goes through the public API with host
+buffers (H2D of P, D2H of J and K inside the timed region); `roofline` is the dominant kernel's ALGORITHMIC flops (the
+reference algorithm's count) over its CUDA-event time against the FP64 pipe peak measured in this run.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "fock_builds_per_s"
+UNIT = "Fock builds/s"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------------
+def load_workload(spec):
+    """-> dict(name, mode, bfs, U, nbf, ncart, nD, description)."""
+    from tuna_b200 import workloads as w
+    from tuna_b200.basis import from_arrays
+    mode, name = spec.split(":")
+    if name.startswith("et"):
+        nbf = int(name[2:])
+        b = w.even_tempered_diatomic(nbf)
+        bfs = from_arrays(b["origins"], b["lmn"], b["nprim"], b["exps"], b["raw_coefs"])
+        U = make_U(b["lmn"])
+        desc = f"configs[4]: synthetic even-tempered N2 (1.10 A) nbf={nbf}, {mode} ERI+J/K, RHF (1 density)"
+        return dict(name=name, mode=mode, bfs=bfs, U=U, nbf=U.shape[0], ncart=len(bfs), nD=1, description=desc, raw=b)
+    from util import basis_objects, load_golden
+    g = load_golden(name)
+    nD = 2 if bool(g["unrestricted"]) else 1
+    desc = {"n2_ccpvtz": "configs[1]: N2 RHF/cc-pVTZ 1.10 A", "co_b3lyp_ccpvtz": "configs[2]: CO B3LYP/cc-pVTZ (exact-exchange K)",
+            "ne2_uhf_ccpvqz": "configs[3]: Ne2 UHF/cc-pVQZ 3.1 A", "h2_631g": "configs[0]: H2 RHF/6-31G 0.74 A"}.get(name, name)
+    return dict(name=name, mode=mode, bfs=basis_objects(g), U=np.array(g["U"]), nbf=int(g["nbf"]), ncart=int(g["ncart"]), nD=nD,
+                description=f"{desc}, {mode} J/K, {nD} density(ies)", raw=dict(origins=g["origins"], lmn=g["lmn"], nprim=g["nprim"],
+                                                                               exps=g["exps"], coefs=g["coefs"], norms=g["norms"]))
+
+
+def make_U(lmn):
+    """Cartesian->spherical map for full shells.  Bench inputs are synthetic, so the pure-d/f/g/h rows are generated
+    from the real solid harmonics (orthonormalised per shell) instead of the reference's hard-coded tables
+    (tuna_kernel.py:540-649); any full-rank (2L+1) x ncart(L) block gives the same amount of work."""
+    lmn = np.asarray(lmn)
+    blocks, i = [], 0
+    while i < len(lmn):
+        L = int(lmn[i].sum())
+        nc = (L + 1) * (L + 2) // 2
+        blocks.append(_sph_block(L))
+        i += nc
+    n_r, n_c = sum(b.shape[0] for b in blocks), sum(b.shape[1] for b in blocks)
+    U = np.zeros((n_r, n_c))
+    r = c = 0
+    for b in blocks:
+        U[r:r + b.shape[0], c:c + b.shape[1]] = b
+        r += b.shape[0]
+        c += b.shape[1]
+    return U
+
+
+_SPH_CACHE = {}
+
+
+def _sph_block(L):
+    if L in _SPH_CACHE:
+        return _SPH_CACHE[L]
+    if L <= 1:
+        blk = np.eye(2 * L + 1)
+    else:
+        # traceless projection: remove the r^2 * (degree L-2) subspace from the Cartesian monomials of degree L
+        from tuna_b200.workloads import cartesian_components
+        comps = cartesian_components(L)
+        low = cartesian_components(L - 2)
+        idx = {c: k for k, c in enumerate(comps)}
+        A = np.zeros((len(low), len(comps)))
+        for r, (a, b, c) in enumerate(low):
+            for d in ((2, 0, 0), (0, 2, 0), (0, 0, 2)):
+                A[r, idx[(a + d[0], b + d[1], c + d[2])]] = 1.0
+        # rows spanning the orthogonal complement of span(A) (dimension 2L+1), sparse-ish via QR of the null space
+        _, s, Vt = np.linalg.svd(A)
+        blk = Vt[len(low):]
+        blk[np.abs(blk) < 1e-14] = 0.0
+    _SPH_CACHE[L] = blk
+    return blk
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle/_ref = the unmodified reference engine; numpy einsum = the reference's J/K, tuna_scf.py:42,70)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference(wl, budget_s=20.0):
+    """Times the reference's own CPU implementation of the path on this box's host cores, on a bounded sample.
+    Returns dict(value=builds/s, kind, cores, sample, quartets_per_s)."""
+    from oracle import tuna_oracle as orc
+    cores = host_threads()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    raw = wl["raw"]
+    if "raw_coefs" in raw:
+        fb = orc.FlatBasis.from_raw(raw["origins"], raw["lmn"], raw["nprim"], raw["exps"], raw["raw_coefs"])
+    else:
+        fb = orc.FlatBasis(raw["origins"], raw["lmn"], raw["nprim"], raw["exps"], raw["coefs"], raw["norms"])
+    eng = orc.reference_engine()
+    kind = "reference" if eng is not None else "port"
+    n = fb.ncart
+    full_unique, full_surv = orc.parity_surviving_quartets(fb.lmn)
+    subset = None
+    if n > 160:        # the reference cannot hold 8*ncart^4 beyond ~250 functions (tuna_kernel.py:392-402): sample 150 functions
+        rng = np.random.default_rng(20261018)
+        subset = np.sort(rng.choice(n, size=150, replace=False))
+        off = fb.offsets
+        sel = np.concatenate([np.arange(off[i], off[i] + fb.nprim[i]) for i in subset])
+        fb = orc.FlatBasis(fb.origins[subset], fb.lmn[subset], fb.nprim[subset], fb.exps[sel], fb.coefs[sel], fb.norms[sel])
+        n = fb.ncart
+    _, surv = orc.parity_surviving_quartets(fb.lmn)
+
+    def eri_once():
+        if eng is not None:
+            bfs = orc.reference_basis_objects(fb)
+            t = time.perf_counter()
+            E = np.asarray(eng.calculate_electron_repulsion_integrals(n, np.empty((n,) * 4), bfs, cores))
+            return time.perf_counter() - t, E
+        t = time.perf_counter()
+        E = orc.eri_fill(fb, cores)
+        return time.perf_counter() - t, E
+
+    t_eri, E = eri_once()
+    if t_eri < budget_s / 4:
+        t_eri = min(t_eri, eri_once()[0])
+    qps = surv / t_eri
+    if subset is None:
+        # the whole reference path: ERI build + Cartesian->spherical rotation + J + K einsums on the fixed density
+        t = time.perf_counter()
+        Es = orc.cart_to_sph_eri(E, wl["U"]) if wl["U"].shape[0] != wl["U"].shape[1] or not np.array_equal(wl["U"], np.eye(n)) else E
+        t_sph = time.perf_counter() - t
+        from tuna_b200.workloads import fixed_density
+        P = fixed_density(Es.shape[0])
+        reps, tJ, tK = 3, [], []
+        for _ in range(reps):
+            t = time.perf_counter(); orc.coulomb(P, Es); tJ.append(time.perf_counter() - t)
+            t = time.perf_counter(); orc.exchange(P, Es); tK.append(time.perf_counter() - t)
+        t_jk = wl["nD"] * (min(tJ) + min(tK))
+        if wl["mode"] == "stored":
+            value = 1.0 / t_jk
+            sample = f"full workload: J+K einsums on the dense tensor, best of {reps} (ERI build {t_eri:.3f} s and rotation {t_sph:.3f} s are per-geometry, excluded as in the GPU stored figure)"
+        else:
+            value = 1.0 / (t_eri + t_sph + t_jk)
+            sample = f"full workload: the reference has no direct mode, so one build = ERI build {t_eri:.3f} s + rotation {t_sph:.3f} s + J/K einsums {t_jk:.4f} s"
+    else:
+        value = qps / full_surv
+        sample = (f"EXTRAPOLATED: reference ERI build on a random 150-function subset of the same basis ({surv} surviving quartets in {t_eri:.2f} s), "
+                  f"scaled to the workload's {full_surv} surviving quartets; J/K einsums not included (the reference cannot hold 8*{wl['ncart']}^4 bytes)")
+    return dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample, quartets_per_s=qps)
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last, t0 = [], None, time.perf_counter()
+    for s in range(args.warmup + args.steps):
+        last = cpu_reference(wl, budget_s=10.0)
+        if s >= args.warmup:
+            vals.append(last["value"])
+        if vals and time.perf_counter() - t0 > 150:      # keep the whole run within a few minutes
+            break
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["description"], "nbf": wl["nbf"], "ncart": wl["ncart"], "mode": wl["mode"]},
+            "cpu_baseline": dict(last, value=value),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "eri_quartets_per_s": last["quartets_per_s"], "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def time_steps(torch, stream, fn, steps, warmup, flush, dist=None):
+    """W untimed + K timed steps; each timed step bracketed by CUDA events on the launching stream; L2 flushed between steps."""
+    for _ in range(warmup):
+        fn()
+    stream.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms = 0.0
+    for _ in range(steps):
+        if flush is not None:
+            flush.add_(1.0)                       # > L2 (126 MB): evicts the previous step's lines
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    return total_ms
+
+
+def bench_stored(torch, wl, steps, warmup, device):
+    """configs[1]-style: dense tensor resident, fused J+K per step."""
+    import tuna_b200
+    from tuna_b200.basis import flatten
+    ctx = tuna_b200.Context(device)
+    ctx.set_basis(*flatten(wl["bfs"]))
+    ctx.set_transform(wl["U"])
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    t_fill, t_sph = [], []
+    for _ in range(3):
+        ctx.eri_fill_cart(); t_fill.append(ctx.last_kernel_ms(0))
+        ctx.eri_cart_to_sph(); t_sph.append(ctx.last_kernel_ms(1))
+    n, nD = wl["nbf"], wl["nD"]
+    c = ctx.counts()
+    P = np.stack([tuna_b200.workloads.fixed_density(n)] * nD)
+    dP = torch.from_numpy(P).cuda()
+    dJK = torch.empty((2, nD, n, n), dtype=torch.float64, device="cuda")
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")      # 256 MB
+    l0 = ctx.counts()["launches"]
+    ms = time_steps(torch, stream, lambda: ctx.jk_stored_dev(nD, dP.data_ptr(), dJK[0].data_ptr(), dJK[1].data_ptr()), steps, warmup, flush)
+    launches = ctx.counts()["launches"] - l0 - 2 * warmup * ((nD + 3) // 4)
+    # per-launch kernel time from the context's own events on the same stream
+    kms = []
+    for _ in range(5):
+        flush.add_(1.0); torch.cuda.synchronize()
+        ctx.jk_stored_dev(nD, dP.data_ptr(), dJK[0].data_ptr(), dJK[1].data_ptr())
+        kms.append(ctx.last_kernel_ms(2))
+    k_ms = float(np.median(kms))
+    alg_bytes = 8.0 * n ** 4 + 8.0 * n * n * (nD + 2 * nD)
+    peaks, src = measured_peaks()
+    # e2e through the public API with host buffers
+    handle = tuna_b200.ERIHandle(ctx, n, "sph", "stored")
+    Ph = P if nD > 1 else P[0]
+    for _ in range(warmup):
+        tuna_b200.coulomb_and_exchange(Ph, handle)
+    t = time.perf_counter()
+    for _ in range(steps):
+        J, K = tuna_b200.coulomb_and_exchange(Ph, handle)
+    e2e = steps / (time.perf_counter() - t)
+    res = {"workload": wl["description"], "nbf": n, "ncart": wl["ncart"], "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "l2": "flushed between steps (256 MB write); the 8*nbf^4 tensor is read from HBM",
+           "eri_fill_ms": float(min(t_fill)), "cart_to_sph_ms": float(min(t_sph)),
+           "eri_quartets_per_s": c["surviving_quartets"] / (min(t_fill) * 1e-3),
+           "roofline": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": src, "kernel": "k_jk_stored",
+                        "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes},
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * nD * n * n), "d2h_bytes_per_step": int(16 * nD * n * n)},
+           "gpu_launches": int(launches)}
+    ctx.set_stream(0)
+    return res, ctx
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — tuna_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    ddist = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ddist = dist
+    import tuna_b200
+    from tuna_b200.basis import flatten
+    from tuna_b200.distributed import FockBuilder
+
+    sampler = ClockSampler(local)
+    if wl["mode"] == "stored":
+        if world > 1:
+            raise SystemExit("stored mode is a single-GPU workload (SURVEY.md 8e); use a direct: workload for --gpus > 1")
+        sampler.start()
+        res, ctx = bench_stored(torch, wl, args.steps, args.warmup, local)
+        clocks = sampler.stop()
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": res["workload"], "nbf": res["nbf"], "ncart": res["ncart"], "mode": "stored", "l2": res["l2"]},
+                "roofline": res["roofline"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks,
+                "eri_quartets_per_s": res["eri_quartets_per_s"], "eri_fill_ms": res["eri_fill_ms"], "cart_to_sph_ms": res["cart_to_sph_ms"]}
+        line["cpu_baseline"] = cpu_reference(wl)
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---- direct mode (headline) ----
+    ctx = tuna_b200.Context(local)
+    t0 = time.perf_counter()
+    ctx.set_basis(*flatten(wl["bfs"]))
+    ctx.set_transform(wl["U"])
+    setup_s = time.perf_counter() - t0
+    n, nD = wl["nbf"], wl["nD"]
+    fb = FockBuilder(ctx, nD=nD, tau=args.tau)
+    P = np.stack([tuna_b200.workloads.fixed_density(n)] * nD)
+    fb.dP.copy_(torch.from_numpy(P))
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    fp64_peak = ctx.fp64_peak_probe() if rank == 0 else 0.0
+    sampler.start()
+    l0 = None
+    for _ in range(args.warmup):
+        fb.build_device()
+    fb.stream.synchronize()
+    l0 = ctx.counts()["launches"]
+    ms = time_steps(torch, fb.stream, fb.build_device, args.steps, 0, flush, ddist)
+    launches = ctx.counts()["launches"] - l0
+    k_ms = ctx.last_kernel_ms(3)
+    evaluated = ctx.counts()["evaluated_last_direct"]
+    # e2e: host P in, host J/K out, every step (pinned H2D + kernels + all-reduce + D2H)
+    for _ in range(max(1, args.warmup // 2)):
+        fb.build(P)
+    if ddist is not None:
+        ddist.barrier()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        J, K = fb.build(P)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t
+    if ddist is not None:
+        tt = torch.tensor([e2e_s, float(evaluated), k_ms], dtype=torch.float64, device="cuda")
+        mx = tt.clone(); ddist.all_reduce(mx, op=ddist.ReduceOp.MAX)
+        sm = tt.clone(); ddist.all_reduce(sm, op=ddist.ReduceOp.SUM)
+        e2e_s, evaluated, k_ms = float(mx[0]), int(sm[1].item()), float(mx[2])
+    clocks = sampler.stop()
+    if rank != 0:
+        if ddist is not None:
+            ddist.destroy_process_group()
+        return
+    c = ctx.counts()
+    alg_eri, alg_digest = ctx.algorithmic_flops()
+    alg = alg_eri + alg_digest * nD
+    builds_per_s = args.steps / (ms * 1e-3)
+    achieved = alg / world / (k_ms * 1e-3) / 1e12           # this rank's share of the algorithmic flops over its kernel time
+    line = {"metric": METRIC, "value": builds_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["description"], "nbf": n, "ncart": wl["ncart"], "mode": "direct", "densities": nD, "schwarz_tau": args.tau,
+                       "parallelism": f"quartet list sharded over {world} GPU(s), one all-reduce of J/K per build",
+                       "l2": "flushed between steps (256 MB write); inputs (pair table, P) are re-read from HBM each step",
+                       "pair_table_setup_s": setup_s},
+            "eri_quartets_per_s": evaluated * builds_per_s, "surviving_quartets": c["surviving_quartets"], "evaluated_quartets": evaluated,
+            "unique_quartets_per_s": c["unique_quartets"] * builds_per_s,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                         "traffic": None, "peak_source": "FP64 DFMA stream measured in this run (tuna_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry",
+                         "kernel": "k_jk_direct", "kernel_ms": k_ms, "algorithmic_flops": alg,
+                         "note": "algorithmic = the reference algorithm's flop count F(a,b) (SURVEY.md 8d) + 12 flops/quartet/density of digestion"},
+            "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(fb.h2d_bytes), "d2h_bytes_per_step": int(fb.d2h_bytes)},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if world == 1:
+        line["cpu_baseline"] = cpu_reference(wl)
+        if not args.no_stored:
+            fb = None
+            ctx.set_stream(0)
+            swl = load_workload("stored:n2_ccpvtz")
+            sres, sctx = bench_stored(torch, swl, max(args.steps, 20), max(args.warmup, 3), local)
+            sres["cpu_baseline"] = cpu_reference(swl)
+            line["stored"] = sres
+    print(json.dumps(line), flush=True)
+    if ddist is not None:
+        ddist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("TUNA_BENCH_WORKLOAD", "direct:et400"))
+    ap.add_argument("--tau", type=float, default=1e-16)
+    ap.add_argument("--no-stored", action="store_true", help="skip the extra stored-mode (configs[1]) measurement at N=1")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = load_workload(args.workload)
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,3 +64,81 @@ int emul_eri_fill(int ncart, const double* oz, const int* lmn, const int* nprim,
     return 0;
 }
 }
+
+// ---- shell-quartet engine (shell_jk.cuh) with the serial HostPolicy ------------------------------------------------
+#include "../../tuna_b200/csrc/shell_host.hpp"
+
+struct HostPolicy {
+    static constexpr int G = 1;
+    static int lane() { return 0; }
+    static void sync() {}
+    static void atomic_add(double* p, double v) { *p += v; }
+};
+
+extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
+                             const double* ceff, int nD, const double* P, double* Jout, double* Kout, double tau, long long* stats) {
+    HostBasis B = make_basis(ncart, oz, lmn, nprim, off, exps, ceff);
+    PairTable PT;
+    build_pair_table(B, PT);
+    std::vector<double> boys, herm;
+    build_boys_table(boys);
+    build_hermite_poly_table(herm);
+    std::vector<double> aoQ(PT.npair);
+    for (int64_t a = 0; a < PT.npair; ++a) {
+        PairClass ca{PT.cls[a] & 255, (PT.cls[a] >> 8) & 255, PT.cls[a] >> 16};
+        aoQ[a] = std::sqrt(std::fabs(eri_ao_quartet(PT.pp.data() + PT.ppoff[a] * PP_DOUBLES, PT.npp[a], PT.pp.data() + PT.ppoff[a] * PP_DOUBLES,
+                                                    PT.npp[a], ca, ca, boys.data(), herm.data())));
+    }
+    ShellTab T;
+    build_shell_tab(T);
+    ShellSystem S;
+    if (!detect_shells(B, T, S)) return 1;
+    build_shell_pairs(S, T, PT, aoQ, ncart);
+    const size_t nn = (size_t)ncart * ncart;
+    std::vector<double> Pf(nD * nn), Jf(nD * nn, 0.0), Kf(nD * nn, 0.0);
+    double dmax = 0.0;
+    for (int d = 0; d < nD; ++d)
+        for (int i = 0; i < ncart; ++i)
+            for (int j = 0; j < ncart; ++j) {
+                Pf[d * nn + (size_t)i * ncart + j] = S.fnorm[i] * S.fnorm[j] * P[d * nn + (size_t)i * ncart + j];
+                dmax = std::max(dmax, std::fabs(P[d * nn + (size_t)i * ncart + j]));
+            }
+    ShellData D;
+    D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
+    D.sh_ao = S.sh_ao.data(); D.tab = &T; D.boys = boys.data(); D.herm = herm.data();
+    long long nitems_total = 0, nskipped = 0;
+    const int ncls = (int)S.classes.size();
+    for (int cb = 0; cb < ncls; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            ShellJob J;
+            J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
+            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
+            J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
+            std::vector<long long> prefix;
+            J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
+            J.item_prefix = prefix.data(); J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
+            shell_job_layout(J, T, nD);
+            std::vector<double> sm(J.total);
+            for (long long item = 0; item < J.nitems; ++item) {
+                int ib, ik;
+                shell_item_decode(J, item, ib, ik);
+                const int AB = J.bra_list[ib], CD = J.ket_list[ik];
+                if (tau > 0.0 && S.pairQ[AB] * S.pairQ[CD] * dmax < tau) { ++nskipped; continue; }
+                double w = 1.0;
+                if (S.pairA[AB] == S.pairB[AB]) w *= 0.5;
+                if (S.pairA[CD] == S.pairB[CD]) w *= 0.5;
+                if (AB == CD) w *= 0.5;
+                shell_quartet<HostPolicy>(J, D, true, AB, CD, w, sm.data(), nD, Pf.data(), Jf.data(), Kf.data(), ncart);
+            }
+            nitems_total += J.nitems;
+        }
+    for (int d = 0; d < nD; ++d)
+        for (int i = 0; i < ncart; ++i)
+            for (int j = 0; j < ncart; ++j) {
+                const double ff = S.fnorm[i] * S.fnorm[j];
+                Jout[d * nn + (size_t)i * ncart + j] = ff * (Jf[d * nn + (size_t)i * ncart + j] + Jf[d * nn + (size_t)j * ncart + i]);
+                Kout[d * nn + (size_t)i * ncart + j] = ff * (Kf[d * nn + (size_t)i * ncart + j] + Kf[d * nn + (size_t)j * ncart + i]);
+            }
+    if (stats) { stats[0] = (long long)S.shells.size(); stats[1] = (long long)S.pairA.size(); stats[2] = nitems_total; stats[3] = nskipped; stats[4] = ncls; }
+    return 0;
+}

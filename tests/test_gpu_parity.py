@@ -218,3 +218,27 @@ def test_error_behaviour(tb):
         ctx.jk_direct(np.eye(5))              # wrong shape
     with pytest.raises(tb.TunaError):
         ctx.eri_single(0, 0, 0, 9)
+
+
+@pytest.mark.parametrize("name", ["n2_ccpvtz", "ne2_uhf_ccpvqz"])
+def test_direct_engines_agree_and_general_density(tb, oracle, name, monkeypatch):
+    """Shell-quartet engine vs the per-component kernel vs the stored path, incl. a NON-symmetric density
+    (K[P] = K[S] + K[A]; the reference's guess densities are asymmetric at the 1e-8 level)."""
+    g = load_golden(name)
+    nbf = int(g["nbf"])
+    rng = np.random.default_rng(11)
+    P = rng.standard_normal((2, nbf, nbf))
+    P[1] = (P[1] + P[1].T) / 2
+    ctx = context_for(g)
+    ctx.set_transform(g["U"])
+    ctx.eri_fill_cart()
+    ctx.eri_cart_to_sph()
+    Js, Ks = ctx.jk_stored(P)
+    Jd, Kd = ctx.jk_direct(P, tau=0.0)
+    monkeypatch.setenv("TUNA_B200_DIRECT_ENGINE", "generic")
+    ctx2 = context_for(g)
+    ctx2.set_transform(g["U"])
+    Jg, Kg = ctx2.jk_direct(P, tau=0.0)
+    scale = max(1.0, np.abs(Ks).max())
+    for a, b in ((Jd, Js), (Kd, Ks), (Jg, Js), (Kg, Ks)):
+        assert np.abs(a - b).max() < 1e-11 * scale

@@ -53,3 +53,31 @@ def test_quartet_math_vs_oracle(emul, oracle, name):
     ref = oracle.eri_fill(fb)
     assert np.all(np.abs(out - ref) <= np.maximum(1e-12, 1e-13 * np.abs(ref)))
     assert np.array_equal(out == 0.0, ref == 0.0)
+
+
+@pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "et100"])
+def test_shell_engine_vs_oracle(emul, oracle, name):
+    """shell_jk.cuh (the direct-mode engine) run serially on the CPU: J/K for two symmetric densities vs the oracle's
+    einsums over the oracle's Cartesian tensor, with and without Schwarz screening."""
+    g = load_golden(name)
+    fb = oracle_basis(oracle, g)
+    n = fb.ncart
+    E = oracle.eri_fill(fb)
+    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    oz = np.ascontiguousarray(fb.origins[:, 2])
+    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
+    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
+    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
+    rng = np.random.default_rng(1)
+    P = rng.standard_normal((2, n, n))
+    P = (P + P.transpose(0, 2, 1)) / 2
+    J, K, stats = np.zeros_like(P), np.zeros_like(P), np.zeros(8, dtype=np.int64)
+    for tau in (0.0, 1e-16):
+        rc = emul.emul_jk_shell(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                                fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), 2, P.ctypes.data_as(dp), J.ctypes.data_as(dp),
+                                K.ctypes.data_as(dp), ctypes.c_double(tau), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+        assert rc == 0
+        for d in range(2):
+            Jr, Kr = oracle.coulomb(P[d], E), oracle.exchange(P[d], E)
+            assert np.abs(J[d] - Jr).max() < 1e-11 and np.abs(K[d] - Kr).max() < 1e-11

@@ -21,6 +21,8 @@
 #include "../../include/tuna_b200.h"
 #include "eri_core.cuh"
 #include "pairtable.hpp"
+#include "shell_host.hpp"
+#include "shell_jk.cuh"
 
 using namespace tuna;
 
@@ -76,6 +78,22 @@ struct tuna_ctx {
 
     int shard_rank = 0, shard_n = 1;
     cudaEvent_t ev[4][2] = {};
+
+    // shell-quartet engine (shell_jk.cuh)
+    ShellTab stab;
+    ShellSystem ss;
+    bool shell_ready = false;
+    double shell_tau = -1.0;
+    int shell_nD = -1;
+    ShellTab* d_stab = nullptr;
+    int* d_pairA = nullptr; int* d_pairB = nullptr; long long* d_pair_rec = nullptr; double* d_rec = nullptr; double* d_pairQ = nullptr;
+    int* d_sh_ao = nullptr; int* d_class_lists = nullptr; long long* d_prefix = nullptr; double* d_finv = nullptr;
+    double* d_eval = nullptr;
+    std::vector<size_t> class_list_off;
+    struct JobHost { ShellJob job; int G; size_t smem; double allowed; int threads, gpc; };
+    std::vector<JobHost> jobs;
+    CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
+    int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
 };
 
 #define CK(call)                                                                                   \
@@ -329,6 +347,75 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters, doub
     if (s == 123.456) out[0] = s;
 }
 
+// ---- shell-quartet engine launch wrapper -----------------------------------------------------------------------
+template <int GG>
+struct DevPolicy {
+    static constexpr int G = GG;
+    __device__ __forceinline__ static int lane() { return threadIdx.x & (GG - 1); }
+    __device__ __forceinline__ static void sync() {
+        if (GG <= 32) __syncwarp(); else __syncthreads();
+    }
+    __device__ __forceinline__ static void atomic_add(double* p, double v) { atomicAdd(p, v); }
+};
+
+// One group of G lanes per shell quartet; groups of a CTA march through the job's item list in lock step.
+// Items are dealt to ranks in chunks of 64 (multi-GPU sharding).
+template <int GG>
+__global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
+                                                                     double* Jf, double* Kf, int ncart, double tau,
+                                                                     const unsigned long long* scalars, double* evaluated,
+                                                                     double allowed_per_item, int rank, int nranks) {
+    extern __shared__ double smem_all[];
+    const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
+    double* sm = smem_all + (size_t)gid * J.total;
+    const double dmax = __longlong_as_double((long long)scalars[0]);
+    constexpr long long CH = 64;
+    const long long nchunk = (J.nitems + CH - 1) / CH;
+    const long long nlocal = ((nchunk - rank + nranks - 1) / nranks) * CH;     // local item slots (some may fall beyond nitems)
+    double done = 0.0;
+    for (long long base = (long long)blockIdx.x * gpc; base < nlocal; base += (long long)gridDim.x * gpc) {
+        const long long loc = base + gid;
+        const long long item = ((loc / CH) * nranks + rank) * CH + loc % CH;
+        bool active = loc < nlocal && item < J.nitems;
+        int AB = 0, CD = 0;
+        double w = 1.0;
+        if (active) {
+            int ib, ik;
+            shell_item_decode(J, item, ib, ik);
+            AB = J.bra_list[ib]; CD = J.ket_list[ik];
+            if (tau > 0.0 && D.pairQ[AB] * D.pairQ[CD] * dmax < tau) active = false;
+            if (D.pairA[AB] == D.pairB[AB]) w *= 0.5;
+            if (D.pairA[CD] == D.pairB[CD]) w *= 0.5;
+            if (AB == CD) w *= 0.5;
+        }
+        if (active && (threadIdx.x & (GG - 1)) == 0) done += w * allowed_per_item;
+        shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Jf, Kf, ncart);
+    }
+    if (done != 0.0) atomicAdd(evaluated, done);
+}
+
+__global__ void k_absmax_scaled(const double* __restrict__ x, const double* __restrict__ finv, int n, int nD, unsigned long long* out) {
+    const int64_t nn = (int64_t)n * n, count = nn * nD;
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ij = i % nn;
+        m = fmax(m, fabs(x[i] * finv[ij / n] * finv[ij % n]));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// out = acc + sign_d * acc^T, sign from the bit mask (bit d set -> antisymmetric density d)
+__global__ void k_add_transpose_signed(const double* __restrict__ acc, double* __restrict__ out, int nD, int n, unsigned anti_mask) {
+    const int64_t nn = (int64_t)n * n, total = nD * nn;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = x / nn, ij = x % nn;
+        const int i = (int)(ij / n), j = (int)(ij % n);
+        const double t = acc[d * nn + (int64_t)j * n + i];
+        out[x] = ((anti_mask >> d) & 1u) ? acc[x] - t : acc[x] + t;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -497,6 +584,11 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->d_eri_cart); dev_free(&ctx->d_eri_sph);
     dev_free(&ctx->d_P); dev_free(&ctx->d_J); dev_free(&ctx->d_K);
     dev_free(&ctx->d_Pc); dev_free(&ctx->d_Jc); dev_free(&ctx->d_Kc); dev_free(&ctx->d_tmp); dev_free(&ctx->d_Kpart);
+    dev_free(&ctx->d_stab); dev_free(&ctx->d_pairA); dev_free(&ctx->d_pairB); dev_free(&ctx->d_pair_rec); dev_free(&ctx->d_rec);
+    dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_prefix); dev_free(&ctx->d_finv);
+    dev_free(&ctx->d_eval);
+    dev_free(&ctx->Uf.rowptr); dev_free(&ctx->Uf.col); dev_free(&ctx->Uf.val);
+    dev_free(&ctx->Uft.rowptr); dev_free(&ctx->Uft.col); dev_free(&ctx->Uft.val);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int w = 0; w < 4; ++w)
         for (int s = 0; s < 2; ++s) if (ctx->ev[w][s]) cudaEventDestroy(ctx->ev[w][s]);
@@ -564,6 +656,12 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     ctx->n_stored = 0;
     ctx->nbf = 0;
     count_work(ctx);
+    build_shell_tab(ctx->stab);
+    ctx->shell_ready = false;
+    ctx->jobs.clear();
+    detect_shells(ctx->hb, ctx->stab, ctx->ss);     // ss.ok == false -> direct mode uses the per-component kernel
+    const char* eng = getenv("TUNA_B200_DIRECT_ENGINE");
+    ctx->direct_engine = (eng && std::string(eng) == "generic") ? 0 : 1;
     return TUNA_OK;
 }
 
@@ -579,6 +677,16 @@ int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U) {
     int rc;
     if ((rc = build_csr(ctx, ctx->U, nbf, nc, u))) return rc;
     if ((rc = build_csr(ctx, ctx->Ut, nc, nbf, ut))) return rc;
+    if (ctx->ss.ok) {
+        std::vector<double> uf(u), uft(ut);
+        for (int p = 0; p < nbf; ++p)
+            for (int a = 0; a < nc; ++a) {
+                uf[(size_t)p * nc + a] *= ctx->ss.fnorm[a];
+                uft[(size_t)a * nbf + p] *= ctx->ss.fnorm[a];
+            }
+        if ((rc = build_csr(ctx, ctx->Uf, nbf, nc, uf))) return rc;
+        if ((rc = build_csr(ctx, ctx->Uft, nc, nbf, uft))) return rc;
+    }
     ctx->nbf = nbf;
     ctx->U_identity = (nbf == nc);
     for (int p = 0; p < nbf && ctx->U_identity; ++p)
@@ -793,65 +901,243 @@ int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
     return TUNA_OK;
 }
 
-int tuna_jk_direct_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK, double tau) {
-    if (!ctx) return TUNA_ERR_ARG;
+}  // extern "C" (internal helpers follow)
+
+// Build (or refresh for a new threshold) the shell-pair data and the job list of the shell-quartet engine.
+static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
+    int rc;
+    if (!ctx->shell_ready) {
+        if ((rc = ensure_schwarz(ctx))) return rc;
+        std::vector<double> q((size_t)ctx->pt.npair);
+        CK(cudaMemcpyAsync(q.data(), ctx->d_Q, q.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ShellSystem& S = ctx->ss;
+        try {
+            build_shell_pairs(S, ctx->stab, ctx->pt, q, ctx->ncart);
+        } catch (const std::bad_alloc&) { FAIL(TUNA_ERR_NOMEM, "host allocation failed while building shell pairs"); }
+        const size_t np = S.pairA.size();
+        if ((rc = dev_alloc(ctx, &ctx->d_stab, (size_t)1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_pairA, np))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_pairB, np))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_pair_rec, np))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_pairQ, np))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_rec, S.rec.size()))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_sh_ao, S.sh_ao.size()))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_finv, (size_t)ctx->ncart))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_eval, (size_t)1))) return rc;
+        std::vector<int> lists;
+        ctx->class_list_off.clear();
+        for (auto& c : S.classes) { ctx->class_list_off.push_back(lists.size()); lists.insert(lists.end(), c.pairs.begin(), c.pairs.end()); }
+        if ((rc = dev_alloc(ctx, &ctx->d_class_lists, lists.size()))) return rc;
+        std::vector<double> finv(ctx->ncart);
+        for (int i = 0; i < ctx->ncart; ++i) finv[i] = 1.0 / S.fnorm[i];
+        CK(cudaMemcpyAsync(ctx->d_stab, &ctx->stab, sizeof(ShellTab), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pairA, S.pairA.data(), np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pairB, S.pairB.data(), np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pair_rec, S.pair_rec.data(), np * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pairQ, S.pairQ.data(), np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_rec, S.rec.data(), S.rec.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_sh_ao, S.sh_ao.data(), S.sh_ao.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_class_lists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_finv, finv.data(), finv.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->shell_ready = true;
+        ctx->shell_tau = -1.0;
+    }
+    if (ctx->shell_tau != tau || ctx->shell_nD != nD || ctx->jobs.empty()) {
+        ctx->shell_nD = nD;
+        const ShellSystem& S = ctx->ss;
+        const int ncls = (int)S.classes.size();
+        std::vector<long long> all_prefix;
+        std::vector<size_t> prefix_off;
+        ctx->jobs.clear();
+        const char* env_div = getenv("TUNA_B200_G_DIV");
+        const char* env_spl = getenv("TUNA_B200_SMEM_PER_LANE");
+        const double gdiv = env_div ? atof(env_div) : 8.0;
+        const double smem_per_lane = env_spl ? atof(env_spl) : 512.0;
+        for (int cb = 0; cb < ncls; ++cb)
+            for (int ck = 0; ck <= cb; ++ck) {
+                tuna_ctx::JobHost jh;
+                ShellJob& J = jh.job;
+                J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
+                J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
+                std::vector<long long> prefix;
+                J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
+                if (J.nitems == 0) continue;
+                J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
+                J.bra_list = ctx->d_class_lists + ctx->class_list_off[cb];
+                J.ket_list = ctx->d_class_lists + ctx->class_list_off[ck];
+                prefix_off.push_back(all_prefix.size());
+                all_prefix.insert(all_prefix.end(), prefix.begin(), prefix.end());
+                shell_job_layout(J, ctx->stab, nD);
+                jh.allowed = (double)allowed_components(ctx->stab, J.La, J.Lb, J.Lc, J.Ld);
+                int G = 1;
+                while (G < 256 && G * gdiv < jh.allowed) G *= 2;
+                while (G < 256 && (double)J.total * 8.0 / G > smem_per_lane) G *= 2;
+                while (G < 256 && (size_t)(G <= 32 ? 128 / G : 1) * J.total * 8 > 200 * 1024) G *= 2;
+                jh.G = G;
+                jh.threads = G <= 32 ? 128 : G;
+                jh.gpc = jh.threads / G;
+                jh.smem = (size_t)jh.gpc * J.total * sizeof(double);
+                if (jh.smem > 220 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 220 KB");
+                ctx->jobs.push_back(jh);
+            }
+        if ((rc = dev_alloc(ctx, &ctx->d_prefix, std::max<size_t>(all_prefix.size(), 1)))) return rc;
+        CK(cudaMemcpyAsync(ctx->d_prefix, all_prefix.data(), all_prefix.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t j = 0; j < ctx->jobs.size(); ++j) ctx->jobs[j].job.item_prefix = ctx->d_prefix + prefix_off[j];
+        ctx->shell_tau = tau;
+    }
+    return TUNA_OK;
+}
+
+template <int GG>
+static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, double* Jf, double* Kf, double tau) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_shell_jk<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    constexpr long long CH = 64;
+    const long long nchunk = (jh.job.nitems + CH - 1) / CH;
+    const long long nlocal = ((nchunk - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n) * CH;
+    if (nlocal <= 0) return cudaSuccess;
+    long long blocks = (nlocal + jh.gpc - 1) / jh.gpc;
+    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
+    k_shell_jk<GG><<<(int)blocks, jh.threads, jh.smem, ctx->stream>>>(jh.job, D, nD, Pf, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
+                                                                         jh.allowed, ctx->shard_rank, ctx->shard_n);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+// Core of direct mode on DEVICE buffers: nD densities, bit d of anti_mask marks density d as antisymmetric
+// (its K is Kacc - Kacc^T and its J vanishes); all others must be symmetric.
+static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau) {
     if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: call tuna_set_basis first");
     if (ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: call tuna_set_transform first");
-    if (nD <= 0 || !dP) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments");
+    if (nD <= 0 || nD > 16 || !dP) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments (1 <= nD <= 16)");
     const int nc = ctx->ncart, nb = ctx->nbf;
+    const bool shell = ctx->direct_engine == 1 && ctx->ss.ok;
     int rc;
     if ((rc = ensure_mats(ctx, nD, nb, nc))) return rc;
     if ((rc = ensure_schwarz(ctx))) return rc;
+    if (shell && (rc = ensure_shell(ctx, tau, nD))) return rc;
     const size_t ncc = (size_t)nc * nc;
+    const CsrDev& Uin = shell ? ctx->Uft : ctx->Ut;      // the shell engine works with unnormalised components: U' = U diag(f)
+    const CsrDev& Uout = shell ? ctx->Uf : ctx->U;
     // P_cart = U^T P U
-    if ((rc = rotate(ctx, ctx->Ut, dP, ctx->d_tmp, nD, nb))) return rc;               // [d][a][q] = sum_p U[p,a] P[d][p][q]
-    if ((rc = rotate(ctx, ctx->Ut, ctx->d_tmp, ctx->d_Pc, (int64_t)nD * nc, 1))) return rc;   // [d][a][b] = sum_q U[q,b] tmp[d][a][q]
+    if ((rc = rotate(ctx, Uin, dP, ctx->d_tmp, nD, nb))) return rc;                          // [d][a][q] = sum_p U[p,a] P[d][p][q]
+    if ((rc = rotate(ctx, Uin, ctx->d_tmp, ctx->d_Pc, (int64_t)nD * nc, 1))) return rc;      // [d][a][b] = sum_q U[q,b] tmp[d][a][q]
     CK(cudaMemsetAsync(ctx->d_scalars, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    k_absmax<<<grid_for(ctx, (int64_t)nD * ncc, 256, 4), 256, 0, ctx->stream>>>(ctx->d_Pc, (int64_t)nD * ncc, ctx->d_scalars);
+    if (shell) {
+        CK(cudaMemsetAsync(ctx->d_eval, 0, sizeof(double), ctx->stream));
+        k_absmax_scaled<<<grid_for(ctx, (int64_t)nD * ncc, 256, 4), 256, 0, ctx->stream>>>(ctx->d_Pc, ctx->d_finv, nc, nD, ctx->d_scalars);
+    } else {
+        k_absmax<<<grid_for(ctx, (int64_t)nD * ncc, 256, 4), 256, 0, ctx->stream>>>(ctx->d_Pc, (int64_t)nD * ncc, ctx->d_scalars);
+    }
     ctx->launches++;
     CK(cudaMemsetAsync(ctx->d_Jc, 0, nD * ncc * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_Kc, 0, nD * ncc * sizeof(double), ctx->stream));
     CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
-    k_jk_direct<<<grid_for(ctx, ctx->task_begin[4] / ctx->shard_n + 1, 128, 16), 128, 0, ctx->stream>>>(
-        table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, nc, nD, tau, ctx->d_scalars, ctx->d_scalars + 1,
-        ctx->shard_rank, ctx->shard_n);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    if (shell) {
+        ShellData D;
+        D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
+        D.sh_ao = ctx->d_sh_ao; D.tab = ctx->d_stab; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
+        for (const auto& jh : ctx->jobs) {
+            cudaError_t e;
+            switch (jh.G) {
+                case 1: e = launch_shell<1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 2: e = launch_shell<2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 4: e = launch_shell<4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 8: e = launch_shell<8>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 16: e = launch_shell<16>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 32: e = launch_shell<32>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 64: e = launch_shell<64>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 128: e = launch_shell<128>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                default: e = launch_shell<256>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+            }
+            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk launch: ") + cudaGetErrorString(e));
+        }
+    } else {
+        k_jk_direct<<<grid_for(ctx, ctx->task_begin[4] / ctx->shard_n + 1, 128, 16), 128, 0, ctx->stream>>>(
+            table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, nc, nD, tau, ctx->d_scalars, ctx->d_scalars + 1,
+            ctx->shard_rank, ctx->shard_n);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
-    // J = U (Jacc + Jacc^T) U^T, same for K
+    // J = U (Jacc + Jacc^T) U^T,  K = U (Kacc +- Kacc^T) U^T
     for (int which = 0; which < 2; ++which) {
         double* acc = which == 0 ? ctx->d_Jc : ctx->d_Kc;
         double* out = which == 0 ? dJ : dK;
         if (!out) continue;
-        k_add_transpose<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(acc, ctx->d_Pc, nD, nc);   // d_Pc reused as scratch
+        k_add_transpose_signed<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(acc, ctx->d_Pc, nD, nc, which == 0 ? 0u : anti_mask);   // d_Pc reused as scratch
         ctx->launches++;
-        if ((rc = rotate(ctx, ctx->U, ctx->d_Pc, ctx->d_tmp, nD, nc))) return rc;          // [d][p][b]
-        if ((rc = rotate(ctx, ctx->U, ctx->d_tmp, out, (int64_t)nD * nb, 1))) return rc;    // [d][p][q]
+        if ((rc = rotate(ctx, Uout, ctx->d_Pc, ctx->d_tmp, nD, nc))) return rc;          // [d][p][b]
+        if ((rc = rotate(ctx, Uout, ctx->d_tmp, out, (int64_t)nD * nb, 1))) return rc;    // [d][p][q]
     }
     CK(cudaGetLastError());
     return TUNA_OK;
 }
 
+extern "C" {
+
+int tuna_jk_direct_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK, double tau) {
+    if (!ctx) return TUNA_ERR_ARG;
+    return jk_direct_core(ctx, nD, dP, 0u, dJ, dK, tau);
+}
+
 int tuna_jk_direct(tuna_ctx* ctx, int nD, const double* P, double* J, double* K, double tau) {
     if (!ctx) return TUNA_ERR_ARG;
     if (ctx->ncart == 0 || ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: basis and transform must be set first");
-    if (nD <= 0 || !P) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments");
+    if (nD <= 0 || nD > 8 || !P) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments (1 <= nD <= 8)");
     CK(cudaSetDevice(ctx->device));
     const int nb = ctx->nbf;
+    const size_t nn = (size_t)nb * nb;
+    // A general P splits into symmetric S and antisymmetric A parts: J[P] = J[S], K[P] = K[S] + K[A] with K[A] antisymmetric.
+    // SCF densities are symmetric to round-off (reference guess densities are not always: asymmetry ~1e-8 was observed).
+    double pmax = 0.0, amax = 0.0;
+    for (int d = 0; d < nD; ++d)
+        for (int i = 0; i < nb; ++i)
+            for (int j = 0; j <= i; ++j) {
+                const double x = P[d * nn + (size_t)i * nb + j], y = P[d * nn + (size_t)j * nb + i];
+                pmax = std::max(pmax, std::max(std::fabs(x), std::fabs(y)));
+                amax = std::max(amax, std::fabs(x - y));
+            }
+    const bool general = amax > 1e-15 * pmax;
+    const int nDrun = general ? 2 * nD : nD;
     int rc;
-    if ((rc = ensure_mats(ctx, nD, nb, ctx->ncart))) return rc;
-    const size_t bytes = (size_t)nD * nb * nb * sizeof(double);
+    if ((rc = ensure_mats(ctx, nDrun, nb, ctx->ncart))) return rc;
+    const size_t bytes = (size_t)nDrun * nn * sizeof(double);
     double* hP = ctx->h_pin;
-    double* hJ = hP + (size_t)nD * nb * nb;
-    double* hK = hJ + (size_t)nD * nb * nb;
-    std::memcpy(hP, P, bytes);
+    double* hJ = hP + (size_t)nDrun * nn;
+    double* hK = hJ + (size_t)nDrun * nn;
+    unsigned anti_mask = 0;
+    if (!general) {
+        std::memcpy(hP, P, bytes);
+    } else {
+        for (int d = 0; d < nD; ++d) {
+            anti_mask |= 1u << (nD + d);
+            for (int i = 0; i < nb; ++i)
+                for (int j = 0; j < nb; ++j) {
+                    const double x = P[d * nn + (size_t)i * nb + j], y = P[d * nn + (size_t)j * nb + i];
+                    hP[d * nn + (size_t)i * nb + j] = 0.5 * (x + y);
+                    hP[(nD + d) * nn + (size_t)i * nb + j] = 0.5 * (x - y);
+                }
+        }
+    }
     CK(cudaMemcpyAsync(ctx->d_P, hP, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = tuna_jk_direct_dev(ctx, nD, ctx->d_P, J ? ctx->d_J : nullptr, K ? ctx->d_K : nullptr, tau))) return rc;
+    if ((rc = jk_direct_core(ctx, nDrun, ctx->d_P, anti_mask, J ? ctx->d_J : nullptr, K ? ctx->d_K : nullptr, tau))) return rc;
     if (J) CK(cudaMemcpyAsync(hJ, ctx->d_J, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (K) CK(cudaMemcpyAsync(hK, ctx->d_K, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (J) std::memcpy(J, hJ, bytes);
-    if (K) std::memcpy(K, hK, bytes);
+    if (J) std::memcpy(J, hJ, (size_t)nD * nn * sizeof(double));
+    if (K) {
+        std::memcpy(K, hK, (size_t)nD * nn * sizeof(double));
+        if (general)
+            for (size_t x = 0; x < (size_t)nD * nn; ++x) K[x] += hK[(size_t)nD * nn + x];
+    }
     return TUNA_OK;
 }
 
@@ -863,6 +1149,11 @@ int tuna_get_counts(const tuna_ctx* c, int64_t counts[8]) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(&ev, ctx->d_scalars + 1, sizeof(ev), cudaMemcpyDeviceToHost);
+        if (ctx->direct_engine == 1 && ctx->ss.ok && ctx->d_eval) {
+            double dv = 0.0;
+            cudaMemcpy(&dv, ctx->d_eval, sizeof(dv), cudaMemcpyDeviceToHost);
+            ev = (unsigned long long)(dv + 0.5);
+        }
     }
     counts[0] = ctx->pt.npair; counts[1] = ctx->n_unique; counts[2] = ctx->n_surviving; counts[3] = ctx->n_primq;
     counts[4] = (int64_t)ev; counts[5] = ctx->launches; counts[6] = ctx->ncart; counts[7] = ctx->nbf;
