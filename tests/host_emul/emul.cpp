@@ -4,6 +4,7 @@
 // eri_core.cuh / pairtable.hpp is compiled here with g++ and checked against the oracle before GPU time
 // is spent.  The package never loads this library; the product path is the CUDA library only.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -105,7 +106,7 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
             }
     ShellData D;
     D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
-    D.sh_ao = S.sh_ao.data(); D.tab = &T; D.boys = boys.data(); D.herm = herm.data();
+    D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data();
     long long nitems_total = 0, nskipped = 0;
     const int ncls = (int)S.classes.size();
     for (int cb = 0; cb < ncls; ++cb)
@@ -117,7 +118,11 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
             std::vector<long long> prefix;
             J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
             J.item_prefix = prefix.data(); J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
-            shell_job_layout(J, T, nD);
+            ClassTablesHost CTH;
+            const char* eb = getenv("TUNA_EMUL_IT_BUDGET");      // small budgets force the multi-chunk path in tests
+            if (eb) build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH, atoi(eb), atoi(eb)); else build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH);
+            J.ct = class_tables_view(CTH, HostPtrOf());
+            shell_job_layout(J, nD);
             std::vector<double> sm(J.total);
             for (long long item = 0; item < J.nitems; ++item) {
                 int ib, ik;

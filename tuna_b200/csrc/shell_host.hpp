@@ -179,14 +179,182 @@ inline long long build_item_prefix(const ShellSystem& S, int cb, int ck, double 
     return prefix.back();
 }
 
-// parity-allowed component combinations of a shell-class quartet (the AO quartets one shell quartet stands for)
-inline long long allowed_components(const ShellTab& T, int La, int Lb, int Lc, int Ld) {
-    long long cnt[4] = {0, 0, 0, 0}, cnt2[4] = {0, 0, 0, 0};
-    for (int a = 0; a < T.nc[La]; ++a)
-        for (int b = 0; b < T.nc[Lb]; ++b) cnt[T.pg[La][a] ^ T.pg[Lb][b]]++;
-    for (int c = 0; c < T.nc[Lc]; ++c)
-        for (int d = 0; d < T.nc[Ld]; ++d) cnt2[T.pg[Lc][c] ^ T.pg[Ld][d]]++;
-    return cnt[0] * cnt2[0] + cnt[1] * cnt2[1] + cnt[2] * cnt2[2] + cnt[3] * cnt2[3];
+// ---------------------------------------------------------------------------------------------------------------
+// Per-class work tables of the shell-quartet engine (see ClassTablesDev in shell_jk.cuh).
+// ---------------------------------------------------------------------------------------------------------------
+struct ClassTablesHost {
+    int La, Lb, Lc, Ld;
+    int nout = 0, nk = 0, itmax = 0, smax_rows = 0, nint = 0;
+    std::vector<int> chunk_bz0, chunk_e0, chunk_s0, bz_list;
+    std::vector<unsigned> p4, p5ptr, p5term, p5off, t_rt, t_xy, t_u, t_s;
+    std::vector<unsigned short> pmap, omap;
+    long long allowed = 0;            // parity-allowed component quartets = integrals per shell quartet
+    double uniq[6] = {0, 0, 0, 0, 0, 0};   // unique AO quartets a shell quartet stands for: [0] generic, [1] A==B, [2] C==D,
+                                           // [3] A==B and C==D, [4] AB==CD (A!=B), [5] all four shells equal
+};
+
+constexpr int SH_IT_BUDGET = 6144;    // doubles of shared memory for the integral buffer of a chunk
+constexpr int SH_S_BUDGET = 6144;     // doubles for the S slice of a chunk
+
+inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld, ClassTablesHost& C, int it_budget = SH_IT_BUDGET,
+                               int s_budget = SH_S_BUDGET) {
+    C = ClassTablesHost();
+    C.La = La; C.Lb = Lb; C.Lc = Lc; C.Ld = Ld;
+    const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = Ltot / 2 + 1, NGZ = (Lc + 1) * (Ld + 1);
+    const int ncA = T.nc[La], ncB = T.nc[Lb], ncC = T.nc[Lc], ncD = T.nc[Ld];
+    // output blocks KAC KAD KBC KBD JAB JCD and staged density blocks PDB PCB PDA PCA PCD(sym) PAB(sym)
+    const int ob[7] = {0, ncA * ncC, ncA * ncC + ncA * ncD, ncA * ncC + ncA * ncD + ncB * ncC, ncA * ncC + ncA * ncD + ncB * ncC + ncB * ncD,
+                       ncA * ncC + ncA * ncD + ncB * ncC + ncB * ncD + ncA * ncB, 0};
+    C.nout = ob[5] + ncC * ncD;
+    C.nk = ob[4];
+    const int pb[6] = {0, ncD * ncB, ncD * ncB + ncC * ncB, ncD * ncB + ncC * ncB + ncD * ncA, ncD * ncB + ncC * ncB + ncD * ncA + ncC * ncA,
+                       ncD * ncB + ncC * ncB + ncD * ncA + ncC * ncA + ncC * ncD};
+    auto rc = [](int rsel, int r, int csel, int c, bool sym) { return (unsigned short)((rsel << 5) | r | ((csel << 5 | c) << 8) | (sym ? 0x8000 : 0)); };
+    C.omap.assign(C.nout, 0); C.pmap.assign(C.nout, 0);
+    for (int a = 0; a < ncA; ++a) for (int c = 0; c < ncC; ++c) C.omap[ob[0] + a * ncC + c] = rc(0, a, 2, c, false);
+    for (int a = 0; a < ncA; ++a) for (int d = 0; d < ncD; ++d) C.omap[ob[1] + a * ncD + d] = rc(0, a, 3, d, false);
+    for (int b = 0; b < ncB; ++b) for (int c = 0; c < ncC; ++c) C.omap[ob[2] + b * ncC + c] = rc(1, b, 2, c, false);
+    for (int b = 0; b < ncB; ++b) for (int d = 0; d < ncD; ++d) C.omap[ob[3] + b * ncD + d] = rc(1, b, 3, d, false);
+    for (int a = 0; a < ncA; ++a) for (int b = 0; b < ncB; ++b) C.omap[ob[4] + a * ncB + b] = rc(0, a, 1, b, false);
+    for (int c = 0; c < ncC; ++c) for (int d = 0; d < ncD; ++d) C.omap[ob[5] + c * ncD + d] = rc(2, c, 3, d, false);
+    for (int d = 0; d < ncD; ++d) for (int b = 0; b < ncB; ++b) C.pmap[pb[0] + d * ncB + b] = rc(3, d, 1, b, false);
+    for (int c = 0; c < ncC; ++c) for (int b = 0; b < ncB; ++b) C.pmap[pb[1] + c * ncB + b] = rc(2, c, 1, b, false);
+    for (int d = 0; d < ncD; ++d) for (int a = 0; a < ncA; ++a) C.pmap[pb[2] + d * ncA + a] = rc(3, d, 0, a, false);
+    for (int c = 0; c < ncC; ++c) for (int a = 0; a < ncA; ++a) C.pmap[pb[3] + c * ncA + a] = rc(2, c, 0, a, false);
+    for (int c = 0; c < ncC; ++c) for (int d = 0; d < ncD; ++d) C.pmap[pb[4] + c * ncD + d] = rc(2, c, 3, d, true);
+    for (int a = 0; a < ncA; ++a) for (int b = 0; b < ncB; ++b) C.pmap[pb[5] + a * ncB + b] = rc(0, a, 1, b, true);
+
+    // phase 1-2 work lists
+    for (int w = 0; w <= Ltot; ++w)
+        for (int n = 0; 2 * n + w <= Ltot; ++n) C.t_rt.push_back((unsigned)(w * NS + n) | (unsigned)w << 16 | (unsigned)n << 24);
+    for (int n12 = 0; n12 <= Lab; ++n12)
+        for (int n34 = n12 & 1; n34 <= Lcd; n34 += 2)
+            for (int m = n12 & 1; 2 * m <= n12 + n34; ++m)
+                C.t_xy.push_back((unsigned)((n12 * (Lcd + 1) + n34) * NS + m) | (unsigned)n12 << 16 | (unsigned)n34 << 20 | (unsigned)m << 24);
+    for (int v = 0; v <= Lab; ++v)
+        for (int cz = 0; cz <= Lc; ++cz)
+            for (int dz = 0; dz <= Ld; ++dz) {
+                const int gz = cz * (Ld + 1) + dz, lz34 = cz + dz;
+                for (int n = 0; 2 * n + v + lz34 <= Ltot; ++n) {
+                    C.t_u.push_back((unsigned)((v * NGZ + gz) * NS + n) | (unsigned)(v * NS + n) << 16);
+                    C.t_u.push_back((unsigned)(gz * (Lcd + 1)) | (unsigned)lz34 << 16);
+                }
+            }
+
+    // bra z-combinations, chunked so that the S slice and the integral buffer fit their budgets
+    struct Quartet { int a, b, c, d; };
+    std::vector<std::vector<Quartet>> per_bz;
+    for (int az = 0; az <= La; ++az)
+        for (int bz = 0; bz <= Lb; ++bz) {
+            C.bz_list.push_back(az | bz << 8);
+            std::vector<Quartet> q;
+            for (int a = 0; a < ncA; ++a) {
+                if (T.lz[La][a] != az) continue;
+                for (int b = 0; b < ncB; ++b) {
+                    if (T.lz[Lb][b] != bz) continue;
+                    for (int c = 0; c < ncC; ++c)
+                        for (int d = 0; d < ncD; ++d)
+                            if ((T.pg[La][a] ^ T.pg[Lb][b] ^ T.pg[Lc][c] ^ T.pg[Ld][d]) == 0) q.push_back({a, b, c, d});
+                }
+            }
+            per_bz.push_back(q);
+        }
+    const int nbz = (int)C.bz_list.size();
+    const int max_rows = std::max(1, std::min(s_budget / (NGZ * NS), 65535 / (NGZ * NS)));
+    C.chunk_bz0.push_back(0); C.chunk_e0.push_back(0); C.chunk_s0.push_back(0);
+    int cur_rows = 0, cur_int = 0;
+    for (int bi = 0; bi < nbz; ++bi) {
+        const int add = (int)per_bz[bi].size();
+        if (cur_rows > 0 && (cur_rows + 1 > max_rows || cur_int + add > it_budget)) {
+            C.chunk_bz0.push_back(bi); C.chunk_e0.push_back(C.nint); C.chunk_s0.push_back((int)C.t_s.size() / 2);
+            cur_rows = 0; cur_int = 0;
+        }
+        const int az = C.bz_list[bi] & 255, bz = C.bz_list[bi] >> 8, lz12 = az + bz;
+        // phase 3 entries of this row
+        for (int cz = 0; cz <= Lc; ++cz)
+            for (int dz = 0; dz <= Ld; ++dz) {
+                const int gz = cz * (Ld + 1) + dz;
+                for (int n = 0; 2 * n + lz12 + cz + dz <= Ltot; ++n) {
+                    C.t_s.push_back((unsigned)((cur_rows * NGZ + gz) * NS + n) | (unsigned)(gz * NS + n) << 16);
+                    C.t_s.push_back((unsigned)((az * (Lb + 1) + bz) * (Lab + 1)) | (unsigned)lz12 << 16);
+                }
+            }
+        // phase 4 entries
+        for (const Quartet& q : per_bz[bi]) {
+            const int nx12 = T.lx[La][q.a] + T.lx[Lb][q.b], nx34 = T.lx[Lc][q.c] + T.lx[Ld][q.d];
+            const int ny12 = T.ly[La][q.a] + T.ly[Lb][q.b], ny34 = T.ly[Lc][q.c] + T.ly[Ld][q.d];
+            const int gz = T.lz[Lc][q.c] * (Ld + 1) + T.lz[Ld][q.d];
+            const unsigned xoff = (nx12 * (Lcd + 1) + nx34) * NS, yoff = (ny12 * (Lcd + 1) + ny34) * NS, soff = (cur_rows * NGZ + gz) * NS;
+            C.p4.push_back(xoff | yoff << 16);
+            C.p4.push_back(soff | (unsigned)(nx12 & 1) << 16 | (unsigned)((nx12 + nx34) >> 1) << 20 | (unsigned)(ny12 & 1) << 24 | (unsigned)((ny12 + ny34) >> 1) << 28);
+        }
+        C.nint += add; cur_int += add; cur_rows += 1;
+        C.itmax = std::max(C.itmax, cur_int);
+        C.smax_rows = std::max(C.smax_rows, cur_rows);
+    }
+    C.chunk_bz0.push_back(nbz); C.chunk_e0.push_back(C.nint); C.chunk_s0.push_back((int)C.t_s.size() / 2);
+    C.allowed = C.nint;
+    {   // unique AO quartets (the reference's pair12 >= pair34 enumeration, pyx:1312-1331) per degeneracy case
+        auto count = [&](bool ab, bool cd, bool diag) {
+            double n = 0;
+            for (int a = 0; a < ncA; ++a) for (int b = 0; b < ncB; ++b) {
+                if (ab && b > a) continue;
+                for (int c = 0; c < ncC; ++c) for (int d = 0; d < ncD; ++d) {
+                    if (cd && d > c) continue;
+                    if ((T.pg[La][a] ^ T.pg[Lb][b] ^ T.pg[Lc][c] ^ T.pg[Ld][d]) != 0) continue;
+                    if (diag && (c * ncD + d) > (a * ncB + b)) continue;
+                    n += 1;
+                }
+            }
+            return n;
+        };
+        C.uniq[0] = count(false, false, false); C.uniq[1] = count(true, false, false); C.uniq[2] = count(false, true, false);
+        C.uniq[3] = count(true, true, false);
+        C.uniq[4] = (La == Lc && Lb == Ld) ? count(false, false, true) : 0;
+        C.uniq[5] = (La == Lb && Lb == Lc && Lc == Ld) ? count(true, true, true) : 0;
+    }
+    // phase 5: CSR over outputs per chunk
+    const int nchunk = (int)C.chunk_bz0.size() - 1;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        std::vector<std::vector<unsigned>> terms(C.nout);
+        int e = 0;
+        for (int bi = C.chunk_bz0[ch]; bi < C.chunk_bz0[ch + 1]; ++bi)
+            for (const Quartet& q : per_bz[bi]) {
+                const unsigned it = (unsigned)e++;
+                terms[ob[0] + q.a * ncC + q.c].push_back(it | (unsigned)(pb[0] + q.d * ncB + q.b) << 16);   // KAC += I P[d][b]
+                terms[ob[1] + q.a * ncD + q.d].push_back(it | (unsigned)(pb[1] + q.c * ncB + q.b) << 16);   // KAD += I P[c][b]
+                terms[ob[2] + q.b * ncC + q.c].push_back(it | (unsigned)(pb[2] + q.d * ncA + q.a) << 16);   // KBC += I P[d][a]
+                terms[ob[3] + q.b * ncD + q.d].push_back(it | (unsigned)(pb[3] + q.c * ncA + q.a) << 16);   // KBD += I P[c][a]
+                terms[ob[4] + q.a * ncB + q.b].push_back(it | (unsigned)(pb[4] + q.c * ncD + q.d) << 16);   // JAB += I (P[c][d]+P[d][c])
+                terms[ob[5] + q.c * ncD + q.d].push_back(it | (unsigned)(pb[5] + q.a * ncB + q.b) << 16);   // JCD += I (P[a][b]+P[b][a])
+            }
+        C.p5off.push_back((unsigned)C.p5term.size());
+        unsigned run = 0;
+        for (int o = 0; o < C.nout; ++o) {
+            C.p5ptr.push_back(run);
+            C.p5term.insert(C.p5term.end(), terms[o].begin(), terms[o].end());
+            run += (unsigned)terms[o].size();
+        }
+        C.p5ptr.push_back(run);
+    }
 }
+
+
+// View of the tables with the given base pointers (host vectors for the CPU test build, device copies for the GPU).
+template <class PtrOf>
+inline ClassTablesDev class_tables_view(const ClassTablesHost& C, PtrOf ptr) {
+    ClassTablesDev V;
+    V.nchunk = (int)C.chunk_bz0.size() - 1; V.nout = C.nout; V.itmax = C.itmax; V.smax_rows = C.smax_rows; V.nk = C.nk;
+    V.chunk_bz0 = ptr(C.chunk_bz0); V.chunk_e0 = ptr(C.chunk_e0); V.chunk_s0 = ptr(C.chunk_s0);
+    V.p4 = ptr(C.p4); V.p5ptr = ptr(C.p5ptr); V.p5term = ptr(C.p5term); V.p5off = ptr(C.p5off);
+    V.pmap = ptr(C.pmap); V.omap = ptr(C.omap);
+    V.n_rt = (int)C.t_rt.size(); V.n_xy = (int)C.t_xy.size(); V.n_u = (int)C.t_u.size() / 2;
+    V.t_rt = ptr(C.t_rt); V.t_xy = ptr(C.t_xy); V.t_u = ptr(C.t_u); V.t_s = ptr(C.t_s);
+    return V;
+}
+
+struct HostPtrOf {
+    template <class V> const typename V::value_type* operator()(const V& v) const { return v.data(); }
+};
 
 }  // namespace tuna

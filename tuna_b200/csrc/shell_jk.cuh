@@ -4,20 +4,23 @@
 // six-deep Hermite loop per component quartet, TUNA/tuna_integrals/tuna_integral.pyx:1142-1253, driver
 // :1312-1342) and has no direct mode.  Here one cooperative GROUP of G lanes owns one SHELL quartet
 // (AB|CD): the Boys values, the z Coulomb-Hermite table and the x/y convolution table are formed once
-// and shared by all ncart(A) ncart(B) ncart(C) ncart(D) components, and the integrals are folded into
-// shared-memory J/K blocks that are flushed with one atomic per block entry per shell quartet (instead
-// of six global atomics per component quartet).  The N^4 tensor is never materialised.
+// and shared by all ncart(A) ncart(B) ncart(C) ncart(D) components; the integrals are folded into
+// shared-memory J/K blocks and flushed with one atomic per block entry per shell quartet (instead of
+// six global atomics per component quartet).  The N^4 tensor is never materialised.
 //
 // Math (all centres on the z axis; unnormalised Cartesian Gaussians, shell-level contraction coefficients;
-// the per-component norms f are folded into the density and the result on the host side of the kernel):
+// the per-component norms f are folded into the density and the result outside the kernel):
 //   (ab|cd) = cc_AB cc_CD 2 pi^(5/2) / (p q sqrt(p+q))
 //             * sum_{m,m'} XY[ax+bx][cx+dx][m] XY[ay+by][cy+dy][m'] S[(az,bz),(cz,dz)][m+m']
 //   XY[n12][n34][m] = (2m-1)!! (-1)^n34 sum_{t+tau=2m} E^{n12}_t(p) E^{n34}_tau(q)       (one-centre x/y Hermite)
 //   S[bz,gz][n]     = sum_{v,phi} Ez_AB[az][bz][v] (-1)^phi Ez_CD[cz][dz][phi] R^n_{v+phi}
 //   R^n_w           = sum_k a(w,k) PQz^(w-2k) B[n+w-k],  B[m] = (-2 rho)^m F_m(rho PQz^2)
 //
-// The body is written against a Policy (lane id, group size, group barrier, atomic add) so that the same
-// source is the sm_100a kernel (DevPolicy<G>) and, with G = 1, a CPU unit-test build (tests/host_emul).
+// All component-index arithmetic is done ONCE per angular class on the host (ClassTables): the integral
+// assembly (phase 4) and the J/K digestion (phase 5) are table-driven loops, so the device code contains no
+// per-integral divisions or parity logic.  The body is written against a Policy (lane id, group size, barrier,
+// atomic add): DevPolicy<G> is the sm_100a kernel, the serial HostPolicy is the CPU unit-test build
+// (tests/host_emul).
 #pragma once
 #include "eri_core.cuh"
 
@@ -31,12 +34,6 @@ struct ShellTab {
     int nc[SH_LMAX + 1];
     int lx[SH_LMAX + 1][SH_NCMAX], ly[SH_LMAX + 1][SH_NCMAX], lz[SH_LMAX + 1][SH_NCMAX];
     int pg[SH_LMAX + 1][SH_NCMAX];            // x/y parity code (lx&1)*2 + (ly&1)
-    int goff[SH_LMAX + 1][5];                 // components sorted by parity code: group offsets
-    int glist[SH_LMAX + 1][SH_NCMAX];         // component ids in group order
-    int gslot[SH_LMAX + 1][SH_NCMAX];         // position of a component inside its group
-    int gmax[SH_LMAX + 1];                    // largest group
-    int zoff[SH_LMAX + 1][SH_LMAX + 2];       // components sorted by lz: offsets
-    int zlist[SH_LMAX + 1][SH_NCMAX];
 };
 
 inline void build_shell_tab(ShellTab& T) {
@@ -48,22 +45,6 @@ inline void build_shell_tab(ShellTab& T) {
                 T.pg[L][c] = (i & 1) * 2 + (j & 1);
             }
         T.nc[L] = c;
-        int pos = 0;
-        T.gmax[L] = 0;
-        for (int g = 0; g < 4; ++g) {
-            T.goff[L][g] = pos;
-            for (int k = 0; k < c; ++k)
-                if (T.pg[L][k] == g) { T.glist[L][pos] = k; T.gslot[L][k] = pos - T.goff[L][g]; ++pos; }
-            if (pos - T.goff[L][g] > T.gmax[L]) T.gmax[L] = pos - T.goff[L][g];
-        }
-        T.goff[L][4] = pos;
-        pos = 0;
-        for (int z = 0; z <= L; ++z) {
-            T.zoff[L][z] = pos;
-            for (int k = 0; k < c; ++k)
-                if (T.lz[L][k] == z) T.zlist[L][pos++] = k;
-        }
-        T.zoff[L][L + 1] = pos;
     }
 }
 
@@ -75,6 +56,36 @@ TUNA_HD int sp_ez_size(int La, int Lb) { return (La + 1) * (Lb + 1) * (La + Lb +
 TUNA_HD int sp_ex_size(int La, int Lb) { return (La + Lb + 1) * ((La + Lb) / 2 + 1); }
 TUNA_HD int sp_rec_size(int La, int Lb) { return SP_HDR + sp_ez_size(La, Lb) + sp_ex_size(La, Lb); }
 
+// Host-built, per angular class (La, Lb, Lc, Ld): everything that depends on component indices only.
+//   Integrals are listed chunk by chunk (a chunk = a run of bra z-combinations (az,bz) whose S slice and integral
+//   buffer fit the shared-memory budget).  Phase-4 entry of integral e (2 words):
+//     w0 = xoff | yoff << 16          offsets of the XY rows of the x and y index pairs
+//     w1 = soff | mx0<<16 | mx1<<20 | my0<<24 | my1<<28   S row offset inside the chunk slice and the m / m' ranges
+//   Phase 5 is a CSR per chunk over the NOUT output entries (six blocks KAC,KAD,KBC,KBD,JAB,JCD, in that order):
+//     term = it_index_in_chunk | pstage_index << 16
+//   The staged density blocks (same sizes/order: P[d][b], P[c][b], P[d][a], P[c][a], P[c][d]+P[d][c], P[a][b]+P[b][a])
+//   and the output blocks are addressed through `pmap` / `omap`: row | col << 8 with row/col = shell_sel << 5 | component.
+struct ClassTablesDev {
+    int nchunk, nout, itmax, smax_rows;     // smax_rows: largest number of (az,bz) rows in a chunk
+    const int* chunk_bz0;                   // [nchunk+1] first bra z-combination index of each chunk
+    const int* chunk_e0;                    // [nchunk+1] first integral of each chunk
+    const unsigned* p4;                     // [2 * nint]
+    const unsigned* p5ptr;                  // [nchunk * (nout + 1)]
+    const unsigned* p5term;                 // concatenated; chunk c starts at p5off[c]
+    const unsigned* p5off;                  // [nchunk]
+    const unsigned short* pmap;             // [nout]  staged density entry -> (row, col), high bit 15 = symmetrise
+    const unsigned short* omap;             // [nout]  output entry -> (row, col); entries < nk are K, the rest J
+    int nk;                                 // number of K outputs (first nk entries of the output list)
+    // phases 1-3 as flat work lists (no per-entry index arithmetic on the device):
+    //   t_rt[i]  = (w * NS + n) | w << 16 | n << 24                                   R^n_w entries with 2n + w <= Ltot
+    //   t_xy[i]  = ((n12 (Lcd+1) + n34) NS + m) | n12 << 16 | n34 << 20 | m << 24     non-zero XY entries
+    //   t_u[2i]  = ((v NGZ + gz) NS + n) | (v NS + n) << 16 ; t_u[2i+1] = gz (Lcd+1) | lz34 << 16
+    //   t_s[2i]  = S offset in the chunk slice | (gz NS + n) << 16 ; t_s[2i+1] = (az (Lb+1) + bz)(Lab+1) | lz12 << 16
+    int n_rt, n_xy, n_u;
+    const unsigned* t_rt; const unsigned* t_xy; const unsigned* t_u; const unsigned* t_s;
+    const int* chunk_s0;                    // [nchunk+1] first t_s entry of each chunk
+};
+
 // One launch = one (bra pair class, ket pair class) job.
 struct ShellJob {
     int La, Lb, Lc, Ld;
@@ -84,8 +95,10 @@ struct ShellJob {
     const long long* item_prefix;   // [nbra + 1]: kets kept per bra (Schwarz cut, and ket_pos <= bra_pos if same class)
     int nbra, same_class;
     long long nitems;
+    double uniq[6];                 // unique AO quartets per shell quartet by degeneracy case (ClassTablesHost::uniq)
+    ClassTablesDev ct;
     // shared-memory layout of one group (offsets in doubles)
-    int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oKAC, oKAD, oKBC, oKBD, oJAB, oJCD, total;
+    int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oAO, total;
 };
 
 struct ShellData {
@@ -94,12 +107,11 @@ struct ShellData {
     const double* rec;
     const double* pairQ;                    // Schwarz factor of the shell pair (max over components, normalised integrals)
     const int* sh_ao;                       // [shell * SH_NCMAX + component] -> AO (Cartesian basis function) index
-    const ShellTab* tab;
     const double* boys;
     const double* herm;
 };
 
-inline void shell_job_layout(ShellJob& J, const ShellTab& T, int nD) {
+inline void shell_job_layout(ShellJob& J, int nD) {
     const int Ltot = J.La + J.Lb + J.Lc + J.Ld, Lab = J.La + J.Lb, Lcd = J.Lc + J.Ld;
     J.NS = Ltot / 2 + 1;
     J.NGZ = (J.Lc + 1) * (J.Ld + 1);
@@ -109,14 +121,11 @@ inline void shell_job_layout(ShellJob& J, const ShellTab& T, int nD) {
     J.oRt = o; o += (Ltot + 1) * J.NS;
     J.oXY = o; o += (Lab + 1) * (Lcd + 1) * J.NS;
     J.oU = o; o += (Lab + 1) * J.NGZ * J.NS;
-    J.oS = o; o += J.NGZ * J.NS;
-    J.oIt = o; o += (J.La + 1) * (J.Lb + 1) * T.nc[J.Lc] * T.gmax[J.Ld];
-    J.oKAC = o; o += nD * T.nc[J.La] * T.nc[J.Lc];
-    J.oKAD = o; o += nD * T.nc[J.La] * T.nc[J.Ld];
-    J.oKBC = o; o += nD * T.nc[J.Lb] * T.nc[J.Lc];
-    J.oKBD = o; o += nD * T.nc[J.Lb] * T.nc[J.Ld];
-    J.oJAB = o; o += nD * T.nc[J.La] * T.nc[J.Lb];
-    J.oJCD = o; o += nD * T.nc[J.Lc] * T.nc[J.Ld];
+    J.oS = o; o += J.ct.smax_rows * J.NGZ * J.NS;
+    J.oIt = o; o += J.ct.itmax;
+    J.oP = o; o += nD * J.ct.nout;
+    J.oOut = o; o += nD * J.ct.nout;
+    J.oAO = o; o += (4 * SH_NCMAX * (int)sizeof(int) + 7) / 8;      // AO indices of the four shells (ints)
     J.total = (o + 1) & ~1;
 }
 
@@ -138,7 +147,8 @@ TUNA_HD double boys_single(const double* __restrict__ tab, int m, double T) {
     }
     double inv2T = 0.5 / T, e = exp(-T);
     double f = 0.88622692545275801365 * sqrt(1.0 / T);
-    for (int k = 0; k < m; ++k) f = ((double)(2 * k + 1) * f - e) * inv2T;
+    double odd = 1.0;
+    for (int k = 0; k < m; ++k) { f = (odd * f - e) * inv2T; odd += 2.0; }
     return f;
 }
 
@@ -150,226 +160,171 @@ TUNA_HD double boys_single(const double* __restrict__ tab, int m, double T) {
 template <class Pol>
 TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, int AB, int CD, double w, double* __restrict__ sm,
                            int nD, const double* __restrict__ Pf, double* Jf, double* Kf, int ncart) {
-    const ShellTab& T = *D.tab;
+    const ClassTablesDev& CT = J.ct;
     const int La = J.La, Lb = J.Lb, Lc = J.Lc, Ld = J.Ld;
     const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = J.NS, NGZ = J.NGZ;
-    const int ncA = T.nc[La], ncB = T.nc[Lb], ncC = T.nc[Lc], ncD = T.nc[Ld], gmaxD = T.gmax[Ld];
-    const int NTA = Lab / 2 + 1, NTC = Lcd / 2 + 1;
+    const int NTA = Lab / 2 + 1, NTC = Lcd / 2 + 1, nout = CT.nout;
     const size_t nn = (size_t)ncart * ncart;
     double* B = sm + J.oB; double* pzt = sm + J.oPz; double* Rt = sm + J.oRt; double* XY = sm + J.oXY;
-    double* U = sm + J.oU; double* S = sm + J.oS; double* It = sm + J.oIt;
-    double* KAC = sm + J.oKAC; double* KAD = sm + J.oKAD; double* KBC = sm + J.oKBC; double* KBD = sm + J.oKBD;
-    double* JAB = sm + J.oJAB; double* JCD = sm + J.oJCD;
+    double* U = sm + J.oU; double* S = sm + J.oS; double* It = sm + J.oIt; double* Pst = sm + J.oP; double* Out = sm + J.oOut;
+    int* ao = reinterpret_cast<int*>(sm + J.oAO);          // [4][SH_NCMAX]
 
-    int shA = 0, shB = 0, shC = 0, shD = 0;
     const double* recA = nullptr; const double* recC = nullptr;
     if (active) {
-        shA = D.pairA[AB]; shB = D.pairB[AB]; shC = D.pairA[CD]; shD = D.pairB[CD];
+        const int sh[4] = {D.pairA[AB], D.pairB[AB], D.pairA[CD], D.pairB[CD]};
         recA = D.rec + D.pair_rec[AB]; recC = D.rec + D.pair_rec[CD];
-        TUNA_LANES(x, J.total - J.oKAC) KAC[x] = 0.0;      // all six accumulator blocks are contiguous
+        TUNA_LANES(x, 4 * SH_NCMAX) ao[x] = D.sh_ao[sh[x / SH_NCMAX] * SH_NCMAX + x % SH_NCMAX];
     }
-    const int* aoA = D.sh_ao + shA * SH_NCMAX; const int* aoB = D.sh_ao + shB * SH_NCMAX;
-    const int* aoC = D.sh_ao + shC * SH_NCMAX; const int* aoD = D.sh_ao + shD * SH_NCMAX;
+    Pol::sync();
+    if (active) {
+        // stage the six density blocks and clear the output blocks
+        for (int dn = 0; dn < nD; ++dn) {
+            const double* P = Pf + dn * nn;
+            TUNA_LANES(x, nout) {
+                const unsigned m = CT.pmap[x];
+                const int r = ao[((m >> 5) & 3) * SH_NCMAX + (m & 31)], c = ao[((m >> 13) & 3) * SH_NCMAX + ((m >> 8) & 31)];
+                double v = P[(size_t)r * ncart + c];
+                if (m & 0x8000u) v += P[(size_t)c * ncart + r];
+                Pst[dn * nout + x] = v;
+                Out[dn * nout + x] = 0.0;
+            }
+        }
+    }
     const int recAsz = sp_rec_size(La, Lb), recCsz = sp_rec_size(Lc, Ld);
     const int oExA = SP_HDR + sp_ez_size(La, Lb), oExC = SP_HDR + sp_ez_size(Lc, Ld);
 
-    for (int ia = 0; ia < J.nppAB; ++ia)
-        for (int ic = 0; ic < J.nppCD; ++ic) {
-            const double* rA = recA + (size_t)ia * recAsz;
-            const double* rC = recC + (size_t)ic * recCsz;
-            double pref = 0.0;
-            // ---- phase 0: Boys values scaled by (-2 rho)^m, powers of PQz -------------------------------------
-            if (active) {
-                const double p = rA[0], q = rC[0], pq = p + q, rho = p * q / pq, PQz = rA[1] - rC[1];
-                const double Targ = rho * PQz * PQz;
-                pref = w * rA[2] * rC[2] * 34.986836655249725 / (p * q * sqrt(pq));
-                TUNA_LANES(m, Ltot + 1) {
-                    double f = boys_single(D.boys, m, Targ), s = 1.0, z = 1.0;
-                    for (int k = 0; k < m; ++k) { s *= -2.0 * rho; z *= PQz; }
-                    B[m] = f * s;
-                    pzt[m] = z;
+    for (int ch = 0; ch < CT.nchunk; ++ch) {
+        const int bz0 = CT.chunk_bz0[ch], bz1 = CT.chunk_bz0[ch + 1];
+        const int e0 = CT.chunk_e0[ch], ne = CT.chunk_e0[ch + 1] - e0;
+        if (active) { TUNA_LANES(x, ne) It[x] = 0.0; }
+        for (int ia = 0; ia < J.nppAB; ++ia)
+            for (int ic = 0; ic < J.nppCD; ++ic) {
+                const double* rA = recA + (size_t)ia * recAsz;
+                const double* rC = recC + (size_t)ic * recCsz;
+                double pref = 0.0;
+                // ---- phase 0: Boys values scaled by (-2 rho)^m, powers of PQz ---------------------------------
+                if (active) {
+                    const double p = rA[0], q = rC[0], pq = p + q, rho = p * q / pq, PQz = rA[1] - rC[1];
+                    const double Targ = rho * PQz * PQz;
+                    pref = w * rA[2] * rC[2] * 34.986836655249725 / (p * q * sqrt(pq));
+                    TUNA_LANES(m, Ltot + 1) {
+                        double f = boys_single(D.boys, m, Targ), s = 1.0, z = 1.0;
+                        for (int k = 0; k < m; ++k) { s *= -2.0 * rho; z *= PQz; }
+                        B[m] = f * s;
+                        pzt[m] = z;
+                    }
                 }
-            }
-            Pol::sync();
-            // ---- phase 1: R^n_w (closed form) and the x/y convolution table --------------------------------------
-            if (active) {
-                TUNA_LANES(x, (Ltot + 1) * NS) {
-                    const int wv = x / NS, n = x % NS;
-                    if (2 * n + wv > Ltot) continue;
-                    double r = 0.0;
-                    for (int k = 0; 2 * k <= wv; ++k) r = fma(D.herm[wv * HERM_STRIDE + k] * pzt[wv - 2 * k], B[n + wv - k], r);
-                    Rt[x] = r;
-                }
-                const double* ExA = rA + oExA; const double* ExC = rC + oExC;
-                TUNA_LANES(x, (Lab + 1) * (Lcd + 1) * NS) {
-                    const int m = x % NS, n34 = (x / NS) % (Lcd + 1), n12 = x / (NS * (Lcd + 1));
-                    const int px = n12 & 1;
-                    double v = 0.0;
-                    if (((n12 ^ n34) & 1) == 0 && m >= px && 2 * m <= n12 + n34) {
-                        // t = px + 2 t', tau = 2m - t = px + 2 tau'
+                Pol::sync();
+                // ---- phase 1: R^n_w (closed form) and the x/y convolution table ----------------------------------
+                if (active) {
+                    TUNA_LANES(i, CT.n_rt) {
+                        const unsigned e = CT.t_rt[i];
+                        const int wv = (e >> 16) & 255, n = e >> 24;
+                        double r = 0.0;
+                        for (int k = 0; 2 * k <= wv; ++k) r = fma(D.herm[wv * HERM_STRIDE + k] * pzt[wv - 2 * k], B[n + wv - k], r);
+                        Rt[e & 0xffffu] = r;
+                    }
+                    const double* ExA = rA + oExA; const double* ExC = rC + oExC;
+                    TUNA_LANES(i, CT.n_xy) {
+                        const unsigned e = CT.t_xy[i];
+                        const int n12 = (e >> 16) & 15, n34 = (e >> 20) & 15, m = e >> 24, px = n12 & 1;
                         const int tlo = (2 * m - n34 > px) ? 2 * m - n34 : px;
                         const int thi = (2 * m - px < n12) ? 2 * m - px : n12;
+                        double v = 0.0;
                         for (int t = tlo; t <= thi; t += 2) v = fma(ExA[n12 * NTA + (t >> 1)], ExC[n34 * NTC + ((2 * m - t) >> 1)], v);
                         v *= odd_dfact(m);
-                        if (n34 & 1) v = -v;
+                        XY[e & 0xffffu] = (n34 & 1) ? -v : v;
                     }
-                    XY[x] = v;
+                }
+                Pol::sync();
+                // ---- phase 2: U[v][gz][n] = sum_phi (-1)^phi Ez_CD[gz][phi] R^n_{v+phi} ---------------------------
+                if (active) {
+                    const double* EzC = rC + SP_HDR;
+                    TUNA_LANES(i, CT.n_u) {
+                        const unsigned e0w = CT.t_u[2 * i], e1w = CT.t_u[2 * i + 1];
+                        const double* e = EzC + (e1w & 0xffffu);
+                        const double* r = Rt + (e0w >> 16);
+                        const int lz34 = e1w >> 16;
+                        double u = 0.0;
+                        for (int phi = 0; phi <= lz34; phi += 2) u = fma(e[phi], r[phi * NS], u);
+                        for (int phi = 1; phi <= lz34; phi += 2) u = fma(-e[phi], r[phi * NS], u);
+                        U[e0w & 0xffffu] = u;
+                    }
+                }
+                Pol::sync();
+                // ---- phase 3: S[row][gz][n] = sum_v Ez_AB[az][bz][v] U[v][gz][n] for the chunk's bra z rows ----------
+                if (active) {
+                    const double* EzA = rA + SP_HDR;
+                    const int ustride = NGZ * NS;
+                    for (int i = CT.chunk_s0[ch] + Pol::lane(); i < CT.chunk_s0[ch + 1]; i += Pol::G) {
+                        const unsigned e0w = CT.t_s[2 * i], e1w = CT.t_s[2 * i + 1];
+                        const double* e = EzA + (e1w & 0xffffu);
+                        const double* u = U + (e0w >> 16);
+                        const int lz12 = e1w >> 16;
+                        double sacc = 0.0;
+                        for (int v = 0; v <= lz12; ++v) sacc = fma(e[v], u[v * ustride], sacc);
+                        S[e0w & 0xffffu] = sacc;
+                    }
+                }
+                Pol::sync();
+                // ---- phase 4: table-driven integral assembly, accumulated over primitive quartets ----------------
+                if (active) {
+                    const unsigned* p4 = CT.p4 + 2 * (size_t)e0;
+                    TUNA_LANES(e, ne) {
+                        const unsigned w0 = p4[2 * e], w1 = p4[2 * e + 1];
+                        const double* xr = XY + (w0 & 0xffffu);
+                        const double* yr = XY + (w0 >> 16);
+                        const double* sr = S + (w1 & 0xffffu);
+                        const int mx0 = (w1 >> 16) & 15, mx1 = (w1 >> 20) & 15, my0 = (w1 >> 24) & 15, my1 = (w1 >> 28) & 15;
+                        double val = 0.0;
+                        for (int m = mx0; m <= mx1; ++m) {
+                            double t = 0.0;
+                            for (int mp = my0; mp <= my1; ++mp) t = fma(yr[mp], sr[m + mp], t);
+                            val = fma(xr[m], t, val);
+                        }
+                        It[e] = fma(pref, val, It[e]);
+                    }
                 }
             }
-            Pol::sync();
-            // ---- phase 2: U[v][gz][n] = sum_phi (-1)^phi Ez_CD[gz][phi] R^n_{v+phi} -------------------------------
-            if (active) {
-                const double* EzC = rC + SP_HDR;
-                TUNA_LANES(x, (Lab + 1) * NGZ * NS) {
-                    const int n = x % NS, gz = (x / NS) % NGZ, v = x / (NS * NGZ);
-                    const int lz34 = gz / (Ld + 1) + gz % (Ld + 1);
-                    if (2 * n + v + lz34 > Ltot) continue;
-                    const double* e = EzC + gz * (Lcd + 1);
-                    double u = 0.0;
-                    for (int phi = 0; phi <= lz34; ++phi) {
-                        const double t = e[phi] * Rt[(v + phi) * NS + n];
-                        u = (phi & 1) ? u - t : u + t;
+        Pol::sync();
+        // ---- phase 5: table-driven digestion of the chunk: every output entry is owned by one lane ---------------
+        if (active) {
+            const unsigned* ptr = CT.p5ptr + (size_t)ch * (nout + 1);
+            const unsigned* term = CT.p5term + CT.p5off[ch];
+            if (nD == 1) {
+                TUNA_LANES(o, nout) {
+                    double s = 0.0;
+                    for (unsigned t = ptr[o]; t < ptr[o + 1]; ++t) {
+                        const unsigned tt = term[t];
+                        s = fma(It[tt & 0xffffu], Pst[tt >> 16], s);
                     }
-                    U[x] = u;
+                    Out[o] += s;
+                }
+            } else {
+                TUNA_LANES(o, nout) {
+                    for (int dn = 0; dn < nD; ++dn) {
+                        double s = 0.0;
+                        const double* Pd = Pst + dn * nout;
+                        for (unsigned t = ptr[o]; t < ptr[o + 1]; ++t) {
+                            const unsigned tt = term[t];
+                            s = fma(It[tt & 0xffffu], Pd[tt >> 16], s);
+                        }
+                        Out[dn * nout + o] += s;
+                    }
                 }
             }
-            Pol::sync();
-            // ---- loop over bra z-combinations --------------------------------------------------------------------
-            for (int az = 0; az <= La; ++az)
-                for (int bz = 0; bz <= Lb; ++bz) {
-                    const int lz12 = az + bz;
-                    const int nA = La - az + 1, nB = Lb - bz + 1;          // components of A with lz = az, of B with lz = bz
-                    const int* zA = T.zlist[La] + T.zoff[La][az];
-                    const int* zB = T.zlist[Lb] + T.zoff[Lb][bz];
-                    // phase 3: S[gz][n] = sum_v Ez_AB[az][bz][v] U[v][gz][n]
-                    if (active) {
-                        const double* e = rA + SP_HDR + (az * (Lb + 1) + bz) * (Lab + 1);
-                        TUNA_LANES(x, NGZ * NS) {
-                            const int n = x % NS, gz = x / NS;
-                            const int lz34 = gz / (Ld + 1) + gz % (Ld + 1);
-                            if (2 * n + lz12 + lz34 > Ltot) continue;
-                            double s = 0.0;
-                            for (int v = 0; v <= lz12; ++v) s = fma(e[v], U[(v * NGZ + gz) * NS + n], s);
-                            S[x] = s;
-                        }
-                    }
-                    Pol::sync();
-                    // phase 4: the integrals of this slice, It[a'][b'][c][slot of d in its parity group]
-                    if (active) {
-                        TUNA_LANES(x, nA * nB * ncC * gmaxD) {
-                            const int slot = x % gmaxD, c = (x / gmaxD) % ncC, bp = (x / (gmaxD * ncC)) % nB, ap = x / (gmaxD * ncC * nB);
-                            const int a = zA[ap], b = zB[bp];
-                            const int g = T.pg[La][a] ^ T.pg[Lb][b] ^ T.pg[Lc][c];
-                            if (slot >= T.goff[Ld][g + 1] - T.goff[Ld][g]) continue;
-                            const int d = T.glist[Ld][T.goff[Ld][g] + slot];
-                            const int nx12 = T.lx[La][a] + T.lx[Lb][b], nx34 = T.lx[Lc][c] + T.lx[Ld][d];
-                            const int ny12 = T.ly[La][a] + T.ly[Lb][b], ny34 = T.ly[Lc][c] + T.ly[Ld][d];
-                            const int gz = T.lz[Lc][c] * (Ld + 1) + T.lz[Ld][d];
-                            const double* xr = XY + (nx12 * (Lcd + 1) + nx34) * NS;
-                            const double* yr = XY + (ny12 * (Lcd + 1) + ny34) * NS;
-                            const double* sr = S + gz * NS;
-                            double val = 0.0;
-                            for (int m = nx12 & 1; 2 * m <= nx12 + nx34; ++m) {
-                                double t = 0.0;
-                                for (int mp = ny12 & 1; 2 * mp <= ny12 + ny34; ++mp) t = fma(yr[mp], sr[m + mp], t);
-                                val = fma(xr[m], t, val);
-                            }
-                            It[((ap * (Lb + 1) + bp) * ncC + c) * gmaxD + slot] = pref * val;
-                        }
-                    }
-                    Pol::sync();
-                    // phase 5: digestion.  Each output entry is owned by one lane; the six blocks are disjoint.
-                    if (active) {
-                        for (int dn = 0; dn < nD; ++dn) {
-                            const double* P = Pf + dn * nn;
-                            // KAC[a][c] += sum_{b,d} I P[d][b]      KBC[b][c] += sum_{a,d} I P[d][a]
-                            TUNA_LANES(x, (nA + nB) * ncC) {
-                                const int c = x % ncC, r = x / ncC;
-                                const bool isA = r < nA;
-                                const int ap0 = isA ? r : 0, ap1 = isA ? r + 1 : nA, bp0 = isA ? 0 : r - nA, bp1 = isA ? nB : r - nA + 1;
-                                double s = 0.0;
-                                for (int ap = ap0; ap < ap1; ++ap)
-                                    for (int bp = bp0; bp < bp1; ++bp) {
-                                        const int a = zA[ap], b = zB[bp];
-                                        const int g = T.pg[La][a] ^ T.pg[Lb][b] ^ T.pg[Lc][c];
-                                        const int g0 = T.goff[Ld][g], gn = T.goff[Ld][g + 1] - g0;
-                                        const double* it = It + ((ap * (Lb + 1) + bp) * ncC + c) * gmaxD;
-                                        const int col = isA ? aoB[b] : aoA[a];
-                                        for (int sl = 0; sl < gn; ++sl) s = fma(it[sl], P[(size_t)aoD[T.glist[Ld][g0 + sl]] * ncart + col], s);
-                                    }
-                                if (isA) KAC[(dn * ncA + zA[r]) * ncC + c] += s;
-                                else KBC[(dn * ncB + zB[r - nA]) * ncC + c] += s;
-                            }
-                            // KAD[a][d] += sum_{b,c} I P[c][b]      KBD[b][d] += sum_{a,c} I P[c][a]
-                            TUNA_LANES(x, (nA + nB) * ncD) {
-                                const int d = x % ncD, r = x / ncD;
-                                const bool isA = r < nA;
-                                const int ap0 = isA ? r : 0, ap1 = isA ? r + 1 : nA, bp0 = isA ? 0 : r - nA, bp1 = isA ? nB : r - nA + 1;
-                                const int sl = T.gslot[Ld][d];
-                                double s = 0.0;
-                                for (int ap = ap0; ap < ap1; ++ap)
-                                    for (int bp = bp0; bp < bp1; ++bp) {
-                                        const int a = zA[ap], b = zB[bp];
-                                        const int g = T.pg[La][a] ^ T.pg[Lb][b] ^ T.pg[Ld][d];       // parity group of c
-                                        const int g0 = T.goff[Lc][g], g1 = T.goff[Lc][g + 1];
-                                        const double* it = It + ((ap * (Lb + 1) + bp) * ncC) * gmaxD + sl;
-                                        const int col = isA ? aoB[b] : aoA[a];
-                                        for (int k = g0; k < g1; ++k) {
-                                            const int c = T.glist[Lc][k];
-                                            s = fma(it[c * gmaxD], P[(size_t)aoC[c] * ncart + col], s);
-                                        }
-                                    }
-                                if (isA) KAD[(dn * ncA + zA[r]) * ncD + d] += s;
-                                else KBD[(dn * ncB + zB[r - nA]) * ncD + d] += s;
-                            }
-                            // JCD[c][d] += sum_{a,b} I (P[a][b] + P[b][a])
-                            TUNA_LANES(x, ncC * ncD) {
-                                const int d = x % ncD, c = x / ncD;
-                                const int gcd = T.pg[Lc][c] ^ T.pg[Ld][d], sl = T.gslot[Ld][d];
-                                double s = 0.0;
-                                for (int ap = 0; ap < nA; ++ap)
-                                    for (int bp = 0; bp < nB; ++bp) {
-                                        const int a = zA[ap], b = zB[bp];
-                                        if ((T.pg[La][a] ^ T.pg[Lb][b]) != gcd) continue;
-                                        const double pab = P[(size_t)aoA[a] * ncart + aoB[b]] + P[(size_t)aoB[b] * ncart + aoA[a]];
-                                        s = fma(It[((ap * (Lb + 1) + bp) * ncC + c) * gmaxD + sl], pab, s);
-                                    }
-                                JCD[(dn * ncC + c) * ncD + d] += s;
-                            }
-                            // JAB[a][b] += sum_{c,d} I (P[c][d] + P[d][c])
-                            TUNA_LANES(x, nA * nB) {
-                                const int bp = x % nB, ap = x / nB;
-                                const int a = zA[ap], b = zB[bp];
-                                const int gab = T.pg[La][a] ^ T.pg[Lb][b];
-                                const double* it = It + ((ap * (Lb + 1) + bp) * ncC) * gmaxD;
-                                double s = 0.0;
-                                for (int c = 0; c < ncC; ++c) {
-                                    const int g = gab ^ T.pg[Lc][c];
-                                    const int g0 = T.goff[Ld][g], gn = T.goff[Ld][g + 1] - g0;
-                                    for (int sl = 0; sl < gn; ++sl) {
-                                        const int d = T.glist[Ld][g0 + sl];
-                                        const double pcd = P[(size_t)aoC[c] * ncart + aoD[d]] + P[(size_t)aoD[d] * ncart + aoC[c]];
-                                        s = fma(it[c * gmaxD + sl], pcd, s);
-                                    }
-                                }
-                                JAB[(dn * ncA + a) * ncB + b] += s;
-                            }
-                        }
-                    }
-                    Pol::sync();
-                }
         }
-    // ---- flush the shell blocks: one atomic per block entry per shell quartet ------------------------------------
+        Pol::sync();
+    }
+    // ---- flush the shell blocks: one atomic per block entry per shell quartet ---------------------------------------
     if (active) {
         for (int dn = 0; dn < nD; ++dn) {
-            double* Jd = Jf + dn * nn;
-            double* Kd = Kf + dn * nn;
-            TUNA_LANES(x, ncA * ncC) Pol::atomic_add(Kd + (size_t)aoA[x / ncC] * ncart + aoC[x % ncC], KAC[dn * ncA * ncC + x]);
-            TUNA_LANES(x, ncA * ncD) Pol::atomic_add(Kd + (size_t)aoA[x / ncD] * ncart + aoD[x % ncD], KAD[dn * ncA * ncD + x]);
-            TUNA_LANES(x, ncB * ncC) Pol::atomic_add(Kd + (size_t)aoB[x / ncC] * ncart + aoC[x % ncC], KBC[dn * ncB * ncC + x]);
-            TUNA_LANES(x, ncB * ncD) Pol::atomic_add(Kd + (size_t)aoB[x / ncD] * ncart + aoD[x % ncD], KBD[dn * ncB * ncD + x]);
-            TUNA_LANES(x, ncA * ncB) Pol::atomic_add(Jd + (size_t)aoA[x / ncB] * ncart + aoB[x % ncB], JAB[dn * ncA * ncB + x]);
-            TUNA_LANES(x, ncC * ncD) Pol::atomic_add(Jd + (size_t)aoC[x / ncD] * ncart + aoD[x % ncD], JCD[dn * ncC * ncD + x]);
+            TUNA_LANES(x, nout) {
+                const unsigned m = CT.omap[x];
+                const int r = ao[((m >> 5) & 3) * SH_NCMAX + (m & 31)], c = ao[((m >> 13) & 3) * SH_NCMAX + ((m >> 8) & 31)];
+                double* dst = (x < CT.nk ? Kf : Jf) + dn * nn + (size_t)r * ncart + c;
+                Pol::atomic_add(dst, Out[dn * nout + x]);
+            }
         }
     }
     Pol::sync();

@@ -85,12 +85,13 @@ struct tuna_ctx {
     bool shell_ready = false;
     double shell_tau = -1.0;
     int shell_nD = -1;
-    ShellTab* d_stab = nullptr;
     int* d_pairA = nullptr; int* d_pairB = nullptr; long long* d_pair_rec = nullptr; double* d_rec = nullptr; double* d_pairQ = nullptr;
     int* d_sh_ao = nullptr; int* d_class_lists = nullptr; long long* d_prefix = nullptr; double* d_finv = nullptr;
     double* d_eval = nullptr;
     std::vector<size_t> class_list_off;
     struct JobHost { ShellJob job; int G; size_t smem; double allowed; int threads, gpc; };
+    struct ClassTabDev { ClassTablesHost host; ClassTablesDev view; unsigned char* blob = nullptr; };
+    std::map<int, ClassTabDev> class_tabs;      // key La | Lb<<4 | Lc<<8 | Ld<<12
     std::vector<JobHost> jobs;
     CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
     int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
@@ -384,11 +385,12 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(ShellJob J, 
             shell_item_decode(J, item, ib, ik);
             AB = J.bra_list[ib]; CD = J.ket_list[ik];
             if (tau > 0.0 && D.pairQ[AB] * D.pairQ[CD] * dmax < tau) active = false;
-            if (D.pairA[AB] == D.pairB[AB]) w *= 0.5;
-            if (D.pairA[CD] == D.pairB[CD]) w *= 0.5;
-            if (AB == CD) w *= 0.5;
+            const bool ab = D.pairA[AB] == D.pairB[AB], cd = D.pairA[CD] == D.pairB[CD], dg = AB == CD;
+            if (ab) w *= 0.5;
+            if (cd) w *= 0.5;
+            if (dg) w *= 0.5;
+            if (active && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
         }
-        if (active && (threadIdx.x & (GG - 1)) == 0) done += w * allowed_per_item;
         shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Jf, Kf, ncart);
     }
     if (done != 0.0) atomicAdd(evaluated, done);
@@ -584,7 +586,8 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->d_eri_cart); dev_free(&ctx->d_eri_sph);
     dev_free(&ctx->d_P); dev_free(&ctx->d_J); dev_free(&ctx->d_K);
     dev_free(&ctx->d_Pc); dev_free(&ctx->d_Jc); dev_free(&ctx->d_Kc); dev_free(&ctx->d_tmp); dev_free(&ctx->d_Kpart);
-    dev_free(&ctx->d_stab); dev_free(&ctx->d_pairA); dev_free(&ctx->d_pairB); dev_free(&ctx->d_pair_rec); dev_free(&ctx->d_rec);
+    for (auto& kv : ctx->class_tabs) dev_free(&kv.second.blob);
+    dev_free(&ctx->d_pairA); dev_free(&ctx->d_pairB); dev_free(&ctx->d_pair_rec); dev_free(&ctx->d_rec);
     dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_prefix); dev_free(&ctx->d_finv);
     dev_free(&ctx->d_eval);
     dev_free(&ctx->Uf.rowptr); dev_free(&ctx->Uf.col); dev_free(&ctx->Uf.val);
@@ -903,6 +906,43 @@ int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
 
 }  // extern "C" (internal helpers follow)
 
+// Per-class work tables: built on the host once per angular class and kept on the device in one blob.
+static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, tuna_ctx::ClassTabDev** out) {
+    const int key = La | Lb << 4 | Lc << 8 | Ld << 12;
+    auto it = ctx->class_tabs.find(key);
+    if (it != ctx->class_tabs.end()) { *out = &it->second; return TUNA_OK; }
+    tuna_ctx::ClassTabDev& E = ctx->class_tabs[key];
+    build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host);
+    const ClassTablesHost& C = E.host;
+    size_t total = 0;
+    auto reserve = [&](size_t bytes) { size_t o = total; total += (bytes + 15) & ~(size_t)15; return o; };
+    struct Piece { const void* src; size_t bytes, off; };
+    std::vector<Piece> pieces;
+    auto add = [&](const void* src, size_t bytes) { pieces.push_back({src, bytes, reserve(bytes)}); return pieces.back().off; };
+    const size_t o_bz0 = add(C.chunk_bz0.data(), C.chunk_bz0.size() * 4), o_e0 = add(C.chunk_e0.data(), C.chunk_e0.size() * 4);
+    const size_t o_s0 = add(C.chunk_s0.data(), C.chunk_s0.size() * 4), o_p4 = add(C.p4.data(), C.p4.size() * 4);
+    const size_t o_ptr = add(C.p5ptr.data(), C.p5ptr.size() * 4), o_term = add(C.p5term.data(), C.p5term.size() * 4);
+    const size_t o_off = add(C.p5off.data(), C.p5off.size() * 4), o_pmap = add(C.pmap.data(), C.pmap.size() * 2);
+    const size_t o_omap = add(C.omap.data(), C.omap.size() * 2), o_rt = add(C.t_rt.data(), C.t_rt.size() * 4);
+    const size_t o_xy = add(C.t_xy.data(), C.t_xy.size() * 4), o_u = add(C.t_u.data(), C.t_u.size() * 4), o_s = add(C.t_s.data(), C.t_s.size() * 4);
+    std::vector<unsigned char> host(total, 0);
+    for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
+    int rc;
+    if ((rc = dev_alloc(ctx, &E.blob, total))) return rc;
+    CK(cudaMemcpyAsync(E.blob, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ClassTablesDev& V = E.view;
+    V.nchunk = (int)C.chunk_bz0.size() - 1; V.nout = C.nout; V.itmax = C.itmax; V.smax_rows = C.smax_rows; V.nk = C.nk;
+    V.n_rt = (int)C.t_rt.size(); V.n_xy = (int)C.t_xy.size(); V.n_u = (int)C.t_u.size() / 2;
+    V.chunk_bz0 = (const int*)(E.blob + o_bz0); V.chunk_e0 = (const int*)(E.blob + o_e0); V.chunk_s0 = (const int*)(E.blob + o_s0);
+    V.p4 = (const unsigned*)(E.blob + o_p4); V.p5ptr = (const unsigned*)(E.blob + o_ptr); V.p5term = (const unsigned*)(E.blob + o_term);
+    V.p5off = (const unsigned*)(E.blob + o_off); V.pmap = (const unsigned short*)(E.blob + o_pmap); V.omap = (const unsigned short*)(E.blob + o_omap);
+    V.t_rt = (const unsigned*)(E.blob + o_rt); V.t_xy = (const unsigned*)(E.blob + o_xy); V.t_u = (const unsigned*)(E.blob + o_u);
+    V.t_s = (const unsigned*)(E.blob + o_s);
+    *out = &E;
+    return TUNA_OK;
+}
+
 // Build (or refresh for a new threshold) the shell-pair data and the job list of the shell-quartet engine.
 static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
     int rc;
@@ -916,7 +956,6 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
             build_shell_pairs(S, ctx->stab, ctx->pt, q, ctx->ncart);
         } catch (const std::bad_alloc&) { FAIL(TUNA_ERR_NOMEM, "host allocation failed while building shell pairs"); }
         const size_t np = S.pairA.size();
-        if ((rc = dev_alloc(ctx, &ctx->d_stab, (size_t)1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_pairA, np))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_pairB, np))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_pair_rec, np))) return rc;
@@ -931,7 +970,6 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
         if ((rc = dev_alloc(ctx, &ctx->d_class_lists, lists.size()))) return rc;
         std::vector<double> finv(ctx->ncart);
         for (int i = 0; i < ctx->ncart; ++i) finv[i] = 1.0 / S.fnorm[i];
-        CK(cudaMemcpyAsync(ctx->d_stab, &ctx->stab, sizeof(ShellTab), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_pairA, S.pairA.data(), np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_pairB, S.pairB.data(), np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_pair_rec, S.pair_rec.data(), np * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -969,8 +1007,12 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 J.ket_list = ctx->d_class_lists + ctx->class_list_off[ck];
                 prefix_off.push_back(all_prefix.size());
                 all_prefix.insert(all_prefix.end(), prefix.begin(), prefix.end());
-                shell_job_layout(J, ctx->stab, nD);
-                jh.allowed = (double)allowed_components(ctx->stab, J.La, J.Lb, J.Lc, J.Ld);
+                tuna_ctx::ClassTabDev* ctd = nullptr;
+                if ((rc = get_class_tables(ctx, J.La, J.Lb, J.Lc, J.Ld, &ctd))) return rc;
+                J.ct = ctd->view;
+                shell_job_layout(J, nD);
+                jh.allowed = (double)ctd->host.allowed;
+                for (int u = 0; u < 6; ++u) J.uniq[u] = ctd->host.uniq[u];
                 int G = 1;
                 while (G < 256 && G * gdiv < jh.allowed) G *= 2;
                 while (G < 256 && (double)J.total * 8.0 / G > smem_per_lane) G *= 2;
@@ -1043,7 +1085,7 @@ static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     if (shell) {
         ShellData D;
         D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
-        D.sh_ao = ctx->d_sh_ao; D.tab = ctx->d_stab; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
+        D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
         for (const auto& jh : ctx->jobs) {
             cudaError_t e;
             switch (jh.G) {
