@@ -104,6 +104,10 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
                 Pf[d * nn + (size_t)i * ncart + j] = S.fnorm[i] * S.fnorm[j] * P[d * nn + (size_t)i * ncart + j];
                 dmax = std::max(dmax, std::fabs(P[d * nn + (size_t)i * ncart + j]));
             }
+    std::vector<double> Psym(nD * nn);
+    for (int d = 0; d < nD; ++d)
+        for (int i = 0; i < ncart; ++i)
+            for (int j = 0; j < ncart; ++j) Psym[d * nn + (size_t)i * ncart + j] = Pf[d * nn + (size_t)i * ncart + j] + Pf[d * nn + (size_t)j * ncart + i];
     ShellData D;
     D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
     D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data();
@@ -133,7 +137,7 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
                 if (S.pairA[AB] == S.pairB[AB]) w *= 0.5;
                 if (S.pairA[CD] == S.pairB[CD]) w *= 0.5;
                 if (AB == CD) w *= 0.5;
-                shell_quartet<HostPolicy>(J, D, true, AB, CD, w, sm.data(), nD, Pf.data(), Jf.data(), Kf.data(), ncart);
+                shell_quartet<HostPolicy>(J, D, true, AB, CD, w, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
             }
             nitems_total += J.nitems;
         }

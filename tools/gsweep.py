@@ -17,8 +17,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps({"ms": ctx.last_kernel_ms(3), "launches": ctx.counts()["launches"]}))
 else:
     for nbf in (200, 400):
-        for gdiv in (2, 8):
-            for spl in (32, 64, 128, 256):
+        for gdiv in (8,):
+            for spl in (128, 256):
                 env = dict(os.environ, TUNA_B200_G_DIV=str(gdiv), TUNA_B200_SMEM_PER_LANE=str(spl))
                 r = subprocess.run([sys.executable, __file__, "child", str(nbf)], env=env, capture_output=True, text=True)
                 print(nbf, gdiv, spl, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:], flush=True)

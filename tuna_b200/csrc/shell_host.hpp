@@ -328,12 +328,13 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
                 terms[ob[4] + q.a * ncB + q.b].push_back(it | (unsigned)(pb[4] + q.c * ncD + q.d) << 16);   // JAB += I (P[c][d]+P[d][c])
                 terms[ob[5] + q.c * ncD + q.d].push_back(it | (unsigned)(pb[5] + q.a * ncB + q.b) << 16);   // JCD += I (P[a][b]+P[b][a])
             }
-        C.p5off.push_back((unsigned)C.p5term.size());
-        unsigned run = 0;
+        C.p5off.push_back((unsigned)C.p5term.size());       // multiple of 4: 16-byte aligned uint4 loads
+        unsigned run = 0;                                   // in units of four terms
         for (int o = 0; o < C.nout; ++o) {
             C.p5ptr.push_back(run);
+            while (terms[o].size() % 4) terms[o].push_back((unsigned)C.itmax);      // dummy: zero slot It[itmax], P stage entry 0
             C.p5term.insert(C.p5term.end(), terms[o].begin(), terms[o].end());
-            run += (unsigned)terms[o].size();
+            run += (unsigned)terms[o].size() / 4;
         }
         C.p5ptr.push_back(run);
     }

@@ -24,6 +24,10 @@
 #pragma once
 #include "eri_core.cuh"
 
+#if !defined(__CUDACC__)
+struct uint4 { unsigned x, y, z, w; };
+#endif
+
 namespace tuna {
 
 constexpr int SH_LMAX = 5;
@@ -98,7 +102,7 @@ struct ShellJob {
     double uniq[6];                 // unique AO quartets per shell quartet by degeneracy case (ClassTablesHost::uniq)
     ClassTablesDev ct;
     // shared-memory layout of one group (offsets in doubles)
-    int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oAO, total;
+    int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oAO, aostride, total;
 };
 
 struct ShellData {
@@ -122,10 +126,14 @@ inline void shell_job_layout(ShellJob& J, int nD) {
     J.oXY = o; o += (Lab + 1) * (Lcd + 1) * J.NS;
     J.oU = o; o += (Lab + 1) * J.NGZ * J.NS;
     J.oS = o; o += J.ct.smax_rows * J.NGZ * J.NS;
-    J.oIt = o; o += J.ct.itmax;
+    J.oIt = o; o += J.ct.itmax + 1;       // + the zero slot read by padding terms
     J.oP = o; o += nD * J.ct.nout;
     J.oOut = o; o += nD * J.ct.nout;
-    J.oAO = o; o += (4 * SH_NCMAX * (int)sizeof(int) + 7) / 8;      // AO indices of the four shells (ints)
+    int lmax = J.La > J.Lc ? J.La : J.Lc;            // La >= Lb, Lc >= Ld by construction
+    if (J.Lb > lmax) lmax = J.Lb;
+    if (J.Ld > lmax) lmax = J.Ld;
+    J.aostride = (lmax + 1) * (lmax + 2) / 2;
+    J.oAO = o; o += (4 * J.aostride * (int)sizeof(int) + 7) / 8;      // AO indices of the four shells (ints)
     J.total = (o + 1) & ~1;
 }
 
@@ -159,7 +167,7 @@ TUNA_HD double boys_single(const double* __restrict__ tab, int m, double T) {
 // `active` = false groups only take part in the barriers.
 template <class Pol>
 TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, int AB, int CD, double w, double* __restrict__ sm,
-                           int nD, const double* __restrict__ Pf, double* Jf, double* Kf, int ncart) {
+                           int nD, const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf, double* Kf, int ncart) {
     const ClassTablesDev& CT = J.ct;
     const int La = J.La, Lb = J.Lb, Lc = J.Lc, Ld = J.Ld;
     const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = J.NS, NGZ = J.NGZ;
@@ -167,13 +175,14 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
     const size_t nn = (size_t)ncart * ncart;
     double* B = sm + J.oB; double* pzt = sm + J.oPz; double* Rt = sm + J.oRt; double* XY = sm + J.oXY;
     double* U = sm + J.oU; double* S = sm + J.oS; double* It = sm + J.oIt; double* Pst = sm + J.oP; double* Out = sm + J.oOut;
-    int* ao = reinterpret_cast<int*>(sm + J.oAO);          // [4][SH_NCMAX]
+    int* ao = reinterpret_cast<int*>(sm + J.oAO);          // [4][aostride]
+    const int aos = J.aostride;
 
     const double* recA = nullptr; const double* recC = nullptr;
     if (active) {
         const int sh[4] = {D.pairA[AB], D.pairB[AB], D.pairA[CD], D.pairB[CD]};
         recA = D.rec + D.pair_rec[AB]; recC = D.rec + D.pair_rec[CD];
-        TUNA_LANES(x, 4 * SH_NCMAX) ao[x] = D.sh_ao[sh[x / SH_NCMAX] * SH_NCMAX + x % SH_NCMAX];
+        TUNA_LANES(x, 4 * aos) ao[x] = D.sh_ao[sh[x / aos] * SH_NCMAX + x % aos];
     }
     Pol::sync();
     if (active) {
@@ -182,10 +191,8 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
             const double* P = Pf + dn * nn;
             TUNA_LANES(x, nout) {
                 const unsigned m = CT.pmap[x];
-                const int r = ao[((m >> 5) & 3) * SH_NCMAX + (m & 31)], c = ao[((m >> 13) & 3) * SH_NCMAX + ((m >> 8) & 31)];
-                double v = P[(size_t)r * ncart + c];
-                if (m & 0x8000u) v += P[(size_t)c * ncart + r];
-                Pst[dn * nout + x] = v;
+                const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
+                Pst[dn * nout + x] = ((m & 0x8000u) ? Psym + dn * nn : P)[(size_t)r * ncart + c];
                 Out[dn * nout + x] = 0.0;
             }
         }
@@ -196,7 +203,10 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
     for (int ch = 0; ch < CT.nchunk; ++ch) {
         const int bz0 = CT.chunk_bz0[ch], bz1 = CT.chunk_bz0[ch + 1];
         const int e0 = CT.chunk_e0[ch], ne = CT.chunk_e0[ch + 1] - e0;
-        if (active) { TUNA_LANES(x, ne) It[x] = 0.0; }
+        if (active) {
+            TUNA_LANES(x, ne) It[x] = 0.0;
+            if (Pol::lane() == 0) It[CT.itmax] = 0.0;
+        }
         for (int ia = 0; ia < J.nppAB; ++ia)
             for (int ic = 0; ic < J.nppCD; ++ic) {
                 const double* rA = recA + (size_t)ia * recAsz;
@@ -287,30 +297,24 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
                 }
             }
         Pol::sync();
-        // ---- phase 5: table-driven digestion of the chunk: every output entry is owned by one lane ---------------
+        // ---- phase 5: table-driven digestion of the chunk: every output entry is owned by one lane.  Term lists are padded
+        // to a multiple of four (dummy terms read the zero slot It[itmax]) so that one 16-byte load brings four terms.
         if (active) {
             const unsigned* ptr = CT.p5ptr + (size_t)ch * (nout + 1);
-            const unsigned* term = CT.p5term + CT.p5off[ch];
-            if (nD == 1) {
-                TUNA_LANES(o, nout) {
-                    double s = 0.0;
-                    for (unsigned t = ptr[o]; t < ptr[o + 1]; ++t) {
-                        const unsigned tt = term[t];
-                        s = fma(It[tt & 0xffffu], Pst[tt >> 16], s);
+            const uint4* term = reinterpret_cast<const uint4*>(CT.p5term + CT.p5off[ch]);
+            TUNA_LANES(o, nout) {
+                const unsigned t0 = ptr[o], t1 = ptr[o + 1];        // in units of four terms
+                for (int dn = 0; dn < nD; ++dn) {
+                    const double* Pd = Pst + dn * nout;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    for (unsigned t = t0; t < t1; ++t) {
+                        const uint4 q = term[t];
+                        s0 = fma(It[q.x & 0xffffu], Pd[q.x >> 16], s0);
+                        s1 = fma(It[q.y & 0xffffu], Pd[q.y >> 16], s1);
+                        s2 = fma(It[q.z & 0xffffu], Pd[q.z >> 16], s2);
+                        s3 = fma(It[q.w & 0xffffu], Pd[q.w >> 16], s3);
                     }
-                    Out[o] += s;
-                }
-            } else {
-                TUNA_LANES(o, nout) {
-                    for (int dn = 0; dn < nD; ++dn) {
-                        double s = 0.0;
-                        const double* Pd = Pst + dn * nout;
-                        for (unsigned t = ptr[o]; t < ptr[o + 1]; ++t) {
-                            const unsigned tt = term[t];
-                            s = fma(It[tt & 0xffffu], Pd[tt >> 16], s);
-                        }
-                        Out[dn * nout + o] += s;
-                    }
+                    Out[dn * nout + o] += (s0 + s1) + (s2 + s3);
                 }
             }
         }
@@ -321,7 +325,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
         for (int dn = 0; dn < nD; ++dn) {
             TUNA_LANES(x, nout) {
                 const unsigned m = CT.omap[x];
-                const int r = ao[((m >> 5) & 3) * SH_NCMAX + (m & 31)], c = ao[((m >> 13) & 3) * SH_NCMAX + ((m >> 8) & 31)];
+                const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
                 double* dst = (x < CT.nk ? Kf : Jf) + dn * nn + (size_t)r * ncart + c;
                 Pol::atomic_add(dst, Out[dn * nout + x]);
             }

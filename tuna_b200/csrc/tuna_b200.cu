@@ -363,7 +363,7 @@ struct DevPolicy {
 // Items are dealt to ranks in chunks of 64 (multi-GPU sharding).
 template <int GG>
 __global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
-                                                                     double* Jf, double* Kf, int ncart, double tau,
+                                                                     const double* __restrict__ Psym, double* Jf, double* Kf, int ncart, double tau,
                                                                      const unsigned long long* scalars, double* evaluated,
                                                                      double allowed_per_item, int rank, int nranks) {
     extern __shared__ double smem_all[];
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(ShellJob J, 
             if (dg) w *= 0.5;
             if (active && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
         }
-        shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Jf, Kf, ncart);
+        shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
     }
     if (done != 0.0) atomicAdd(evaluated, done);
 }
@@ -992,7 +992,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
         const char* env_div = getenv("TUNA_B200_G_DIV");
         const char* env_spl = getenv("TUNA_B200_SMEM_PER_LANE");
         const double gdiv = env_div ? atof(env_div) : 8.0;
-        const double smem_per_lane = env_spl ? atof(env_spl) : 512.0;
+        const double smem_per_lane = env_spl ? atof(env_spl) : 256.0;
         for (int cb = 0; cb < ncls; ++cb)
             for (int ck = 0; ck <= cb; ++ck) {
                 tuna_ctx::JobHost jh;
@@ -1034,7 +1034,8 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
 }
 
 template <int GG>
-static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, double* Jf, double* Kf, double tau) {
+static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
+                                double* Jf, double* Kf, double tau) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_shell_jk<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1047,7 +1048,7 @@ static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, cons
     if (nlocal <= 0) return cudaSuccess;
     long long blocks = (nlocal + jh.gpc - 1) / jh.gpc;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
-    k_shell_jk<GG><<<(int)blocks, jh.threads, jh.smem, ctx->stream>>>(jh.job, D, nD, Pf, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
+    k_shell_jk<GG><<<(int)blocks, jh.threads, jh.smem, ctx->stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
                                                                          jh.allowed, ctx->shard_rank, ctx->shard_n);
     ctx->launches++;
     return cudaGetLastError();
@@ -1083,21 +1084,23 @@ static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     CK(cudaMemsetAsync(ctx->d_Kc, 0, nD * ncc * sizeof(double), ctx->stream));
     CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
     if (shell) {
+        k_add_transpose_signed<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_Pc, ctx->d_tmp, nD, nc, 0u);   // Psym = P + P^T
+        ctx->launches++;
         ShellData D;
         D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
         D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
         for (const auto& jh : ctx->jobs) {
             cudaError_t e;
             switch (jh.G) {
-                case 1: e = launch_shell<1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 2: e = launch_shell<2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 4: e = launch_shell<4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 8: e = launch_shell<8>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 16: e = launch_shell<16>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 32: e = launch_shell<32>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 64: e = launch_shell<64>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 128: e = launch_shell<128>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
-                default: e = launch_shell<256>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 1: e = launch_shell<1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 2: e = launch_shell<2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 4: e = launch_shell<4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 8: e = launch_shell<8>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 16: e = launch_shell<16>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 32: e = launch_shell<32>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 64: e = launch_shell<64>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 128: e = launch_shell<128>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                default: e = launch_shell<256>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
             }
             if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk launch: ") + cudaGetErrorString(e));
         }
