@@ -423,7 +423,7 @@ def run_ours(args, wl):
             "unique_quartets_per_s": c["unique_quartets"] * builds_per_s,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "traffic": None, "peak_source": "FP64 DFMA stream measured in this run (tuna_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry",
-                         "kernel": "k_jk_direct", "kernel_ms": k_ms, "algorithmic_flops": alg,
+                         "kernel": "k_shell_jk (all class jobs of one build)", "kernel_ms": k_ms, "algorithmic_flops": alg,
                          "note": "algorithmic = the reference algorithm's flop count F(a,b) (SURVEY.md 8d) + 12 flops/quartet/density of digestion"},
             "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(fb.h2d_bytes), "d2h_bytes_per_step": int(fb.d2h_bytes)},
             "gpu_launches": int(launches), "clocks": clocks}
