@@ -66,5 +66,5 @@ def test_shard_chunks_partition():
     from tuna_b200.distributed import shard_chunks
     for n in (0, 1, 63, 64, 65, 1000, 4097):
         for world in (1, 2, 4, 8):
-            seen = sorted(c for r in range(world) for c in shard_chunks(n, r, world, 64))
-            assert seen == list(range((n + 63) // 64))
+            seen = sorted(c for r in range(world) for c in shard_chunks(n, r, world))
+            assert seen == list(range((n + 127) // 128))

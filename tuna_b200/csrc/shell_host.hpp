@@ -263,9 +263,22 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
     const int max_rows = std::max(1, std::min(s_budget / (NGZ * NS), 65535 / (NGZ * NS)));
     C.chunk_bz0.push_back(0); C.chunk_e0.push_back(0); C.chunk_s0.push_back(0);
     int cur_rows = 0, cur_int = 0;
+    auto pf_key = [&](int bi, const Quartet& q) {
+        const int nx12 = T.lx[La][q.a] + T.lx[Lb][q.b], nx34 = T.lx[Lc][q.c] + T.lx[Ld][q.d];
+        const int ny12 = T.ly[La][q.a] + T.ly[Lb][q.b], ny34 = T.ly[Lc][q.c] + T.ly[Ld][q.d];
+        const int gz = T.lz[Lc][q.c] * (Ld + 1) + T.lz[Ld][q.d];
+        return ((((long long)bi * 16 + nx12) * 16 + ny12) * 16 + nx34) * 16 * 64 + ny34 * 64 + gz;
+    };
+    std::map<long long, int> slot_of;     // pair-function quartet -> It slot inside its chunk
     for (int bi = 0; bi < nbz; ++bi) {
-        const int add = (int)per_bz[bi].size();
-        if (cur_rows > 0 && (cur_rows + 1 > max_rows || cur_int + add > it_budget)) {
+        int distinct = 0;
+        {
+            std::map<long long, int> seen;
+            for (const Quartet& q : per_bz[bi]) seen[pf_key(bi, q)] = 1;
+            distinct = (int)seen.size();
+        }
+        const size_t slots_before = slot_of.size();
+        if (cur_rows > 0 && (cur_rows + 1 > max_rows || cur_int + distinct > it_budget)) {
             C.chunk_bz0.push_back(bi); C.chunk_e0.push_back(C.nint); C.chunk_s0.push_back((int)C.t_s.size() / 2);
             cur_rows = 0; cur_int = 0;
         }
@@ -279,21 +292,27 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
                     C.t_s.push_back((unsigned)((az * (Lb + 1) + bz) * (Lab + 1)) | (unsigned)lz12 << 16);
                 }
             }
-        // phase 4 entries
+        // phase 4 entries: one per DISTINCT pair-function quartet.  Component quartets with equal (ax+bx, ay+by, az, bz |
+        // cx+dx, cy+dy, cz, dz) have identical (unnormalised) integrals, so they share one It slot (1.8x-3.2x fewer).
         for (const Quartet& q : per_bz[bi]) {
             const int nx12 = T.lx[La][q.a] + T.lx[Lb][q.b], nx34 = T.lx[Lc][q.c] + T.lx[Ld][q.d];
             const int ny12 = T.ly[La][q.a] + T.ly[Lb][q.b], ny34 = T.ly[Lc][q.c] + T.ly[Ld][q.d];
             const int gz = T.lz[Lc][q.c] * (Ld + 1) + T.lz[Ld][q.d];
+            const long long key = ((((long long)bi * 16 + nx12) * 16 + ny12) * 16 + nx34) * 16 * 64 + ny34 * 64 + gz;
+            if (slot_of.count(key)) continue;
+            slot_of[key] = cur_int + (int)(slot_of.size() - slots_before);
             const unsigned xoff = (nx12 * (Lcd + 1) + nx34) * NS, yoff = (ny12 * (Lcd + 1) + ny34) * NS, soff = (cur_rows * NGZ + gz) * NS;
             C.p4.push_back(xoff | yoff << 16);
             C.p4.push_back(soff | (unsigned)(nx12 & 1) << 16 | (unsigned)((nx12 + nx34) >> 1) << 20 | (unsigned)(ny12 & 1) << 24 | (unsigned)((ny12 + ny34) >> 1) << 28);
         }
+        const int add = (int)(slot_of.size() - slots_before);
         C.nint += add; cur_int += add; cur_rows += 1;
         C.itmax = std::max(C.itmax, cur_int);
         C.smax_rows = std::max(C.smax_rows, cur_rows);
     }
     C.chunk_bz0.push_back(nbz); C.chunk_e0.push_back(C.nint); C.chunk_s0.push_back((int)C.t_s.size() / 2);
-    C.allowed = C.nint;
+    C.allowed = 0;
+    for (const auto& v : per_bz) C.allowed += (long long)v.size();
     {   // unique AO quartets (the reference's pair12 >= pair34 enumeration, pyx:1312-1331) per degeneracy case
         auto count = [&](bool ab, bool cd, bool diag) {
             double n = 0;
@@ -317,10 +336,9 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
     const int nchunk = (int)C.chunk_bz0.size() - 1;
     for (int ch = 0; ch < nchunk; ++ch) {
         std::vector<std::vector<unsigned>> terms(C.nout);
-        int e = 0;
         for (int bi = C.chunk_bz0[ch]; bi < C.chunk_bz0[ch + 1]; ++bi)
             for (const Quartet& q : per_bz[bi]) {
-                const unsigned it = (unsigned)e++;
+                const unsigned it = (unsigned)slot_of[pf_key(bi, q)];
                 terms[ob[0] + q.a * ncC + q.c].push_back(it | (unsigned)(pb[0] + q.d * ncB + q.b) << 16);   // KAC += I P[d][b]
                 terms[ob[1] + q.a * ncD + q.d].push_back(it | (unsigned)(pb[1] + q.c * ncB + q.b) << 16);   // KAD += I P[c][b]
                 terms[ob[2] + q.b * ncC + q.c].push_back(it | (unsigned)(pb[2] + q.d * ncA + q.a) << 16);   // KBC += I P[d][a]

@@ -98,7 +98,9 @@ struct ShellJob {
     const int* ket_list;
     const long long* item_prefix;   // [nbra + 1]: kets kept per bra (Schwarz cut, and ket_pos <= bra_pos if same class)
     int nbra, same_class;
+    int chunk;                      // consecutive items per CTA work unit / sharding unit
     long long nitems;
+    int dbg_skip;                   // development aid: bit k set -> phase k is skipped (timing experiments only; 0 in production)
     double uniq[6];                 // unique AO quartets per shell quartet by degeneracy case (ClassTablesHost::uniq)
     ClassTablesDev ct;
     // shared-memory layout of one group (offsets in doubles)
@@ -185,7 +187,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
         TUNA_LANES(x, 4 * aos) ao[x] = D.sh_ao[sh[x / aos] * SH_NCMAX + x % aos];
     }
     Pol::sync();
-    if (active) {
+    if (active && !(J.dbg_skip & 64)) {
         // stage the six density blocks and clear the output blocks
         for (int dn = 0; dn < nD; ++dn) {
             const double* P = Pf + dn * nn;
@@ -213,7 +215,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
                 const double* rC = recC + (size_t)ic * recCsz;
                 double pref = 0.0;
                 // ---- phase 0: Boys values scaled by (-2 rho)^m, powers of PQz ---------------------------------
-                if (active) {
+                if (active && !(J.dbg_skip & 1)) {
                     const double p = rA[0], q = rC[0], pq = p + q, rho = p * q / pq, PQz = rA[1] - rC[1];
                     const double Targ = rho * PQz * PQz;
                     pref = w * rA[2] * rC[2] * 34.986836655249725 / (p * q * sqrt(pq));
@@ -226,7 +228,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
                 }
                 Pol::sync();
                 // ---- phase 1: R^n_w (closed form) and the x/y convolution table ----------------------------------
-                if (active) {
+                if (active && !(J.dbg_skip & 2)) {
                     TUNA_LANES(i, CT.n_rt) {
                         const unsigned e = CT.t_rt[i];
                         const int wv = (e >> 16) & 255, n = e >> 24;
@@ -248,7 +250,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
                 }
                 Pol::sync();
                 // ---- phase 2: U[v][gz][n] = sum_phi (-1)^phi Ez_CD[gz][phi] R^n_{v+phi} ---------------------------
-                if (active) {
+                if (active && !(J.dbg_skip & 4)) {
                     const double* EzC = rC + SP_HDR;
                     TUNA_LANES(i, CT.n_u) {
                         const unsigned e0w = CT.t_u[2 * i], e1w = CT.t_u[2 * i + 1];
@@ -263,7 +265,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
                 }
                 Pol::sync();
                 // ---- phase 3: S[row][gz][n] = sum_v Ez_AB[az][bz][v] U[v][gz][n] for the chunk's bra z rows ----------
-                if (active) {
+                if (active && !(J.dbg_skip & 8)) {
                     const double* EzA = rA + SP_HDR;
                     const int ustride = NGZ * NS;
                     for (int i = CT.chunk_s0[ch] + Pol::lane(); i < CT.chunk_s0[ch + 1]; i += Pol::G) {
@@ -278,7 +280,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
                 }
                 Pol::sync();
                 // ---- phase 4: table-driven integral assembly, accumulated over primitive quartets ----------------
-                if (active) {
+                if (active && !(J.dbg_skip & 16)) {
                     const unsigned* p4 = CT.p4 + 2 * (size_t)e0;
                     TUNA_LANES(e, ne) {
                         const unsigned w0 = p4[2 * e], w1 = p4[2 * e + 1];
@@ -299,7 +301,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
         Pol::sync();
         // ---- phase 5: table-driven digestion of the chunk: every output entry is owned by one lane.  Term lists are padded
         // to a multiple of four (dummy terms read the zero slot It[itmax]) so that one 16-byte load brings four terms.
-        if (active) {
+        if (active && !(J.dbg_skip & 32)) {
             const unsigned* ptr = CT.p5ptr + (size_t)ch * (nout + 1);
             const uint4* term = reinterpret_cast<const uint4*>(CT.p5term + CT.p5off[ch]);
             TUNA_LANES(o, nout) {
@@ -321,7 +323,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
         Pol::sync();
     }
     // ---- flush the shell blocks: one atomic per block entry per shell quartet ---------------------------------------
-    if (active) {
+    if (active && !(J.dbg_skip & 128)) {
         for (int dn = 0; dn < nD; ++dn) {
             TUNA_LANES(x, nout) {
                 const unsigned m = CT.omap[x];

@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters, doub
 }
 
 // ---- shell-quartet engine launch wrapper -----------------------------------------------------------------------
+constexpr int SHELL_ITEMS_PER_GROUP = 4;   // a CTA work unit (= multi-GPU sharding unit) is 4 consecutive shell quartets per group
+
 template <int GG>
 struct DevPolicy {
     static constexpr int G = GG;
@@ -360,7 +362,7 @@ struct DevPolicy {
 };
 
 // One group of G lanes per shell quartet; groups of a CTA march through the job's item list in lock step.
-// Items are dealt to ranks in chunks of 64 (multi-GPU sharding).
+// Items are dealt to ranks in chunks of J.chunk consecutive shell quartets (multi-GPU sharding).
 template <int GG>
 __global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
                                                                      const double* __restrict__ Psym, double* Jf, double* Kf, int ncart, double tau,
@@ -368,30 +370,42 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(ShellJob J, 
                                                                      double allowed_per_item, int rank, int nranks) {
     extern __shared__ double smem_all[];
     const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
+    int& s_ib0 = *reinterpret_cast<int*>(smem_all + (size_t)gpc * J.total);      // one extra slot behind the group slices
     double* sm = smem_all + (size_t)gid * J.total;
     const double dmax = __longlong_as_double((long long)scalars[0]);
-    constexpr long long CH = 64;
+    const long long CH = J.chunk;
     const long long nchunk = (J.nitems + CH - 1) / CH;
-    const long long nlocal = ((nchunk - rank + nranks - 1) / nranks) * CH;     // local item slots (some may fall beyond nitems)
     double done = 0.0;
-    for (long long base = (long long)blockIdx.x * gpc; base < nlocal; base += (long long)gridDim.x * gpc) {
-        const long long loc = base + gid;
-        const long long item = ((loc / CH) * nranks + rank) * CH + loc % CH;
-        bool active = loc < nlocal && item < J.nitems;
-        int AB = 0, CD = 0;
-        double w = 1.0;
-        if (active) {
+    // chunk-major: a CTA owns CH consecutive items of the job; the bra position of the chunk's first item is found once
+    // by binary search, the others by walking the per-bra prefix (consecutive items share or neighbour the bra).
+    for (long long gc = (long long)blockIdx.x * nranks + rank; gc < nchunk; gc += (long long)gridDim.x * nranks) {
+        const long long first = gc * CH;
+        if (threadIdx.x == 0) {
             int ib, ik;
-            shell_item_decode(J, item, ib, ik);
-            AB = J.bra_list[ib]; CD = J.ket_list[ik];
-            if (tau > 0.0 && D.pairQ[AB] * D.pairQ[CD] * dmax < tau) active = false;
-            const bool ab = D.pairA[AB] == D.pairB[AB], cd = D.pairA[CD] == D.pairB[CD], dg = AB == CD;
-            if (ab) w *= 0.5;
-            if (cd) w *= 0.5;
-            if (dg) w *= 0.5;
-            if (active && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+            shell_item_decode(J, first, ib, ik);
+            s_ib0 = ib;
         }
-        shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
+        __syncthreads();
+        const int ib0 = s_ib0;
+        __syncthreads();
+        for (int k0 = 0; k0 < (int)CH; k0 += gpc) {
+            const long long item = first + k0 + gid;
+            bool active = (k0 + gid) < (int)CH && item < J.nitems;
+            int AB = 0, CD = 0;
+            double w = 1.0;
+            if (active) {
+                int ib = ib0;
+                while (J.item_prefix[ib + 1] <= item) ++ib;
+                AB = J.bra_list[ib]; CD = J.ket_list[(int)(item - J.item_prefix[ib])];
+                if (tau > 0.0 && D.pairQ[AB] * D.pairQ[CD] * dmax < tau) active = false;
+                const bool ab = D.pairA[AB] == D.pairB[AB], cd = D.pairA[CD] == D.pairB[CD], dg = AB == CD;
+                if (ab) w *= 0.5;
+                if (cd) w *= 0.5;
+                if (dg) w *= 0.5;
+                if (active && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+            }
+            shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
+        }
     }
     if (done != 0.0) atomicAdd(evaluated, done);
 }
@@ -912,7 +926,11 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, tuna_
     auto it = ctx->class_tabs.find(key);
     if (it != ctx->class_tabs.end()) { *out = &it->second; return TUNA_OK; }
     tuna_ctx::ClassTabDev& E = ctx->class_tabs[key];
-    build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host);
+    {
+        const char* eb = getenv("TUNA_B200_IT_BUDGET");
+        const char* es = getenv("TUNA_B200_S_BUDGET");
+        build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host, eb ? atoi(eb) : SH_IT_BUDGET, es ? atoi(es) : SH_S_BUDGET);
+    }
     const ClassTablesHost& C = E.host;
     size_t total = 0;
     auto reserve = [&](size_t bytes) { size_t o = total; total += (bytes + 15) & ~(size_t)15; return o; };
@@ -999,6 +1017,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 ShellJob& J = jh.job;
                 J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
                 J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
+                { const char* dbg = getenv("TUNA_B200_DBG_SKIP"); J.dbg_skip = dbg ? atoi(dbg) : 0; }
                 std::vector<long long> prefix;
                 J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
                 if (J.nitems == 0) continue;
@@ -1020,7 +1039,8 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 jh.G = G;
                 jh.threads = G <= 32 ? 128 : G;
                 jh.gpc = jh.threads / G;
-                jh.smem = (size_t)jh.gpc * J.total * sizeof(double);
+                J.chunk = jh.gpc * SHELL_ITEMS_PER_GROUP;
+                jh.smem = ((size_t)jh.gpc * J.total + 2) * sizeof(double);
                 if (jh.smem > 220 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 220 KB");
                 ctx->jobs.push_back(jh);
             }
@@ -1042,11 +1062,9 @@ static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, cons
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    constexpr long long CH = 64;
-    const long long nchunk = (jh.job.nitems + CH - 1) / CH;
-    const long long nlocal = ((nchunk - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n) * CH;
-    if (nlocal <= 0) return cudaSuccess;
-    long long blocks = (nlocal + jh.gpc - 1) / jh.gpc;
+    const long long nchunk = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
+    long long blocks = (nchunk - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // chunks owned by this rank
+    if (blocks <= 0) return cudaSuccess;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
     k_shell_jk<GG><<<(int)blocks, jh.threads, jh.smem, ctx->stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
                                                                          jh.allowed, ctx->shard_rank, ctx->shard_n);
