@@ -68,6 +68,24 @@ def make(name):
             seq[f"seq{it}_{c_i}_{kind}_P"] = P
             seq[f"seq{it}_{c_i}_{kind}_out"] = M
 
+    # inputs of the main SCF loop (for oracle/scf_oracle.py): guess densities = the densities of the first recorded calls
+    first = main_calls[:per_iter]
+    if per_iter == 4:      # UHF call order: J(Pa), J(Pb), K(Pa), K(Pb)  (tuna_scf.py:571-577)
+        Pg_a, Pg_b = first[0][2], first[1][2]
+        Pg = Pg_a + Pg_b
+    else:
+        Pg = first[0][2]
+        Pg_a = Pg_b = Pg / 2
+    ns0 = rh.load_reference()
+    V_NN = float(ns0.kern.calculate_nuclear_repulsion_energy(molecule.charges, molecule.coordinates, calc, True)) if calc.diatomic else 0.0
+    scf_inputs = dict(P_guess=Pg, P_guess_alpha=Pg_a, P_guess_beta=Pg_b, E_guess=float(rec.E_guess) if rec.E_guess is not None else 0.0, V_NN=V_NN,
+                      n_alpha=int(molecule.n_alpha), n_beta=int(molecule.n_beta), n_doubly_occ=int(molecule.n_doubly_occ),
+                      partition_ranges=np.array(molecule.partition_ranges, dtype=np.int64), damping=bool(calc.damping),
+                      damping_factor=float("nan") if calc.damping_factor is None else float(calc.damping_factor),
+                      max_damping=float(calc.max_damping), DIIS=bool(calc.DIIS), max_DIIS_matrices=int(calc.max_DIIS_matrices),
+                      conv_delta_E=calc.SCF_conv["delta_E"], conv_max_DP=calc.SCF_conv["max_DP"], conv_RMS_DP=calc.SCF_conv["RMS_DP"],
+                      conv_commutator=calc.SCF_conv["commutator"], is_dft=bool(calc.DFT_calculation))
+
     rng = np.random.default_rng(12345)
     idx_c = rng.integers(0, ncart, size=(N_SAMPLES, 4))
     idx_s = rng.integers(0, nbf, size=(N_SAMPLES, 4))
@@ -91,7 +109,7 @@ def make(name):
         P_alpha_final=np.array(out.P_alpha), P_beta_final=np.array(out.P_beta),
         coulomb_energy=float(out.coulomb_energy), exchange_energy=float(out.exchange_energy),
         HFX_prop=float(calc.HFX_prop), unrestricted=unrestricted,
-        **seq)
+        **scf_inputs, **seq)
     print(f"{name}: ncart={ncart} nbf={nbf} E={float(energy):.12f} iterations={n_iter} calls/iter={per_iter} "
           f"sum_cart={eri_cart.sum():.9f} fro_sph={np.linalg.norm(eri_sph):.9f}")
 

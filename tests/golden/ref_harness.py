@@ -107,6 +107,7 @@ class Recorder:
         self.eri_sph = {}        # nbf -> tensor
         self.bases = {}          # ncart -> list[Basis]
         self.U = {}
+        self.E_guess = None      # E handed to the main SCF loop (guess_objects[3], tuna_scf.py:1334)
 
     def __enter__(self):
         ns = self.ns
@@ -136,6 +137,13 @@ class Recorder:
             self.U[out[5].shape[0]] = np.array(molecule.spherical_harmonic_transformation_matrix)
             return out
 
+        self._loop = ns.scf.run_self_consistent_field_cycle
+
+        def loop(molecule, calculation, integrals, V_NN, X, guess_objects, grid_container, silent):
+            self.E_guess = guess_objects[3]      # the last (= main) SCF loop wins
+            return self._loop(molecule, calculation, integrals, V_NN, X, guess_objects, grid_container, silent)
+
+        ns.scf.run_self_consistent_field_cycle = loop
         ns.scf.calculate_coulomb_matrix, ns.scf.calculate_exchange_matrix = J, K
         ns.kern.calculate_two_electron_integrals, ns.kern.transform_to_spherical_harmonics = two, sph
         return self
@@ -143,6 +151,7 @@ class Recorder:
     def __exit__(self, *exc):
         ns = self.ns
         ns.scf.calculate_coulomb_matrix, ns.scf.calculate_exchange_matrix = self._J, self._K
+        ns.scf.run_self_consistent_field_cycle = self._loop
         ns.kern.calculate_two_electron_integrals, ns.kern.transform_to_spherical_harmonics = self._two, self._sph
         return False
 
