@@ -262,6 +262,162 @@ __global__ void __launch_bounds__(1024) k_jk_stored(const double* __restrict__ E
         }
 }
 
+
+// ---- stored-mode J/K, TMA-streamed variant ------------------------------------------------------------------------
+// The dense tensor is a pure HBM stream (each element is used once per density), so the B200-native shape is a
+// persistent CTA per SM that pulls contiguous row tiles of E[i,l,:,:] into a shared-memory ring with 1-D bulk TMA
+// copies (cp.async.bulk + mbarrier complete_tx) while the previous tiles are being contracted.  Each CTA owns a
+// contiguous range of (i,l) slabs: J[i,l] is written once by its owner, K[i,:] is accumulated in registers and flushed
+// to a per-CTA partial row whenever i changes (k_kslot_reduce sums the partial rows in a fixed order) — no atomics.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+}
+
+constexpr int JK_MAX_STAGES = 4;
+
+template <int ND>
+__global__ void __launch_bounds__(1024) k_jk_stored_tma(const double* __restrict__ E, const double* __restrict__ P, double* __restrict__ J,
+                                                           double* __restrict__ Kslot, int* __restrict__ Krow, int n, int r, int R, int q,
+                                                           int nstage, int kslots) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const size_t tile_doubles = (size_t)R * n;
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    double* sJ = ring + (size_t)nstage * tile_doubles;                 // [2][nwarp][ND]
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sK = sJ + 2 * nwarp * ND;                                   // [ND][r][n]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sK + (size_t)ND * r * n);
+    const int tid = threadIdx.x, j = tid % n, rt = tid / n;
+    const bool active = tid < n * r;
+    const size_t nn = (size_t)n * n;
+    // slab range of this CTA (32-bit, incremental indices: no divisions in the tile loop)
+    const int total = n * n;
+    const int s0 = (int)((long long)total * blockIdx.x / gridDim.x), s1 = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+    const int ntile = (s1 - s0) * q;
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // producer state (thread 0): next tile to issue
+    int p_slab = s0, p_part = 0, p_stage = 0, p_issued = 0;
+    auto issue = [&]() {
+        const int row0 = p_part * R, rows = min(R, n - row0);
+        const uint32_t bytes = (uint32_t)(rows * n * (int)sizeof(double));
+        mbar_expect_tx(&bars[p_stage], bytes);
+        tma_bulk_load(ring + (size_t)p_stage * tile_doubles, E + ((size_t)p_slab * n + row0) * n, bytes, &bars[p_stage]);
+        if (++p_part == q) { p_part = 0; ++p_slab; }
+        if (++p_stage == nstage) p_stage = 0;
+        ++p_issued;
+    };
+    if (tid == 0)
+        while (p_issued < nstage && p_issued < ntile) issue();
+    double accK[ND], accJ[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { accK[d] = 0.0; accJ[d] = 0.0; }
+    int cur_i = s0 / n, flushes = 0, jbuf = 0;
+    auto flushK = [&]() {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (active) sK[((size_t)d * r + rt) * n + j] = accK[d];
+        __syncthreads();
+        const int slot = blockIdx.x * kslots + flushes;
+        for (int x = tid; x < ND * n; x += blockDim.x) {
+            const int d = x / n, jj = x % n;
+            double v = 0.0;
+            for (int qq = 0; qq < r; ++qq) v += sK[((size_t)d * r + qq) * n + jj];
+            Kslot[((size_t)slot * ND + d) * n + jj] = v;
+        }
+        if (tid == 0) Krow[slot] = cur_i;
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < ND; ++d) accK[d] = 0.0;
+        ++flushes;
+    };
+    int i = cur_i, l = s0 - cur_i * n, part = 0, st = 0;
+    uint32_t parity = 0;
+    for (int t = 0; t < ntile; ++t) {
+        const int row0 = part * R, rows = min(R, n - row0);
+        if (i != cur_i) { flushK(); cur_i = i; }
+        mbar_wait(&bars[st], parity);
+        const double* tile = ring + (size_t)st * tile_doubles;
+        if (active) {
+            const double* Pj = P + (size_t)row0 * n + j;       // P[k][j], k = row0 + row
+            const double* Pl = P + (size_t)row0 * n + l;       // P[k][l]
+#pragma unroll 4
+            for (int row = rt; row < rows; row += r) {
+                const double e = tile[row * n + j];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    accJ[d] = fma(e, __ldg(Pj + d * nn + (size_t)row * n), accJ[d]);
+                    accK[d] = fma(e, __ldg(Pl + d * nn + (size_t)row * n), accK[d]);
+                }
+            }
+        }
+        const bool slab_done = part == q - 1;
+        if (slab_done) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                double v = accJ[d];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if (lane == 0) sJ[(jbuf * nwarp + warp) * ND + d] = v;
+                accJ[d] = 0.0;
+            }
+        }
+        __syncthreads();                         // every thread is done with this stage (and sJ[jbuf] is complete)
+        if (tid == 0 && p_issued < ntile) issue();
+        if (slab_done) {
+            if (warp == 1 % nwarp && lane < ND && J) {        // a warp other than the producer's sums the per-warp partials
+                double v = 0.0;
+                for (int w = 0; w < nwarp; ++w) v += sJ[(jbuf * nwarp + w) * ND + lane];
+                J[lane * nn + (size_t)i * n + l] = v;
+            }
+            jbuf ^= 1;
+        }
+        if (++part == q) { part = 0; if (++l == n) { l = 0; ++i; } }
+        if (++st == nstage) { st = 0; parity ^= 1; }
+    }
+    if (ntile > 0) flushK();
+}
+
+// K[d][i][j] = sum of the partial rows of the CTAs whose slab range touches row i, in CTA order (deterministic, atomic-free).
+// CTA c owns slabs [total*c/G, total*(c+1)/G); its flush number for row i is i - first_row(c).
+__global__ void k_kslot_reduce(const double* __restrict__ Kslot, const int* __restrict__ Krow, double* __restrict__ K, int nD, int n, int grid, int kslots) {
+    const int64_t total = (int64_t)nD * n * n;
+    const long long slabs = (long long)n * n;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        const int jj = (int)(x % n), i = (int)((x / n) % n), d = (int)(x / ((int64_t)n * n));
+        // CTAs c with [s0(c), s1(c)) intersecting [i n, (i+1) n)
+        int c_lo = (int)(((long long)i * n * grid) / slabs);
+        while (c_lo > 0 && slabs * c_lo / grid > (long long)i * n) --c_lo;
+        double v = 0.0;
+        for (int c = c_lo; c < grid; ++c) {
+            const long long s0 = slabs * c / grid, s1 = slabs * (c + 1) / grid;
+            if (s0 >= (long long)(i + 1) * n) break;
+            if (s1 <= (long long)i * n || s1 == s0) continue;
+            const int slot = c * kslots + (i - (int)(s0 / n));
+            if (Krow[slot] == i) v += Kslot[((size_t)slot * nD + d) * n + jj];
+        }
+        K[x] = v;
+    }
+}
+
 __global__ void k_kpart_reduce(const double* __restrict__ Kpart, double* __restrict__ K, int nD, int n, int nchunk) {
     const int64_t total = (int64_t)nD * n * n;
     for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
@@ -844,25 +1000,97 @@ int tuna_schwarz(tuna_ctx* ctx, double* host_out) {
     return TUNA_OK;
 }
 
-int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK) {
+}  // extern "C"
+
+template <int ND>
+static cudaError_t launch_jk_tma(tuna_ctx* ctx, const double* P, double* J, double* Kslot, int* Krow, int n, int r, int R, int q, int nstage,
+                                 int kslots, int grid, int threads, size_t smem) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_jk_stored_tma<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_jk_stored_tma<ND><<<grid, threads, smem, ctx->stream>>>(ctx->d_eri_sph, P, J, Kslot, Krow, n, r, R, q, nstage, kslots);
+    return cudaGetLastError();
+}
+
+extern "C" int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK) {
     if (!ctx) return TUNA_ERR_ARG;
     if (!ctx->d_eri_sph || ctx->n_stored == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_stored: no stored tensor resident");
     if (nD <= 0 || !dP) FAIL(TUNA_ERR_ARG, "tuna_jk_stored: bad arguments");
     const int n = ctx->n_stored;
     if (n > 1024) FAIL(TUNA_ERR_ARG, "tuna_jk_stored: stored mode supports n <= 1024");
+    int rc;
+    const size_t nn = (size_t)n * n;
+    const char* env_k = getenv("TUNA_B200_STORED_KERNEL");
+    const bool want_tma = !(env_k && std::string(env_k) == "simple");
+    if (want_tma && (n % 2 == 0) && (n > 64 || (env_k && std::string(env_k) == "tma"))) {
+        // ---- TMA-streamed persistent kernel (16-byte alignment of every row tile needs an even n) ----
+        const int r = std::max(1, 512 / n);
+        const int threads = (n * r + 31) / 32 * 32;
+        const int nwarp = threads / 32;
+        const char* env_tile = getenv("TUNA_B200_JK_TILE_KB");
+        const char* env_st = getenv("TUNA_B200_JK_STAGES");
+        const char* env_cps = getenv("TUNA_B200_JK_CTAS_PER_SM");
+        const size_t tile_budget = (env_tile ? atoi(env_tile) : 24) * 1024;
+        int q = (int)((nn * sizeof(double) + tile_budget - 1) / tile_budget);
+        int R = (n + q - 1) / q;
+        R = (R + r - 1) / r * r;                       // whole row groups per tile
+        q = (n + R - 1) / R;
+        const int nstage = env_st ? std::min(atoi(env_st), JK_MAX_STAGES) : 3;
+        const long long total = (long long)n * n;
+        const int grid = (int)std::min<long long>((long long)ctx->sm_count * (env_cps ? atoi(env_cps) : 2), total);
+        const int kslots = (int)((total / grid + 1 + n - 1) / n) + 2;
+        const int nslots = grid * kslots;
+        const size_t need_kpart = (size_t)nslots * 4 * n + (size_t)(nslots + 1) / 2 + 8;       // doubles: partial rows + row tags
+        if (dK && need_kpart > ctx->cap_kpart) {
+            if ((rc = dev_alloc(ctx, &ctx->d_Kpart, need_kpart))) return rc;
+            ctx->cap_kpart = need_kpart;
+        }
+        CK(cudaEventRecord(ctx->ev[2][0], ctx->stream));
+        for (int d0 = 0; d0 < nD; d0 += 4) {
+            const int nd = std::min(4, nD - d0);
+            if (!dK && need_kpart > ctx->cap_kpart) {      // K not requested: the kernel still needs scratch rows
+                if ((rc = dev_alloc(ctx, &ctx->d_Kpart, need_kpart))) return rc;
+                ctx->cap_kpart = need_kpart;
+            }
+            double* Kslot = ctx->d_Kpart;
+            int* Krow = reinterpret_cast<int*>(ctx->d_Kpart + (size_t)nslots * 4 * n);
+            CK(cudaMemsetAsync(Krow, 0xFF, (size_t)nslots * sizeof(int), ctx->stream));
+            const size_t smem = ((size_t)nstage * R * n + 2 * (size_t)nwarp * nd + (size_t)nd * r * n) * sizeof(double) + JK_MAX_STAGES * sizeof(uint64_t) + 16;
+            const double* P = dP + d0 * nn;
+            double* J = dJ ? dJ + d0 * nn : nullptr;
+            cudaError_t e;
+            switch (nd) {
+                case 1: e = launch_jk_tma<1>(ctx, P, J, Kslot, Krow, n, r, R, q, nstage, kslots, grid, threads, smem); break;
+                case 2: e = launch_jk_tma<2>(ctx, P, J, Kslot, Krow, n, r, R, q, nstage, kslots, grid, threads, smem); break;
+                case 3: e = launch_jk_tma<3>(ctx, P, J, Kslot, Krow, n, r, R, q, nstage, kslots, grid, threads, smem); break;
+                default: e = launch_jk_tma<4>(ctx, P, J, Kslot, Krow, n, r, R, q, nstage, kslots, grid, threads, smem); break;
+            }
+            ctx->launches++;
+            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_jk_stored_tma launch: ") + cudaGetErrorString(e));
+            if (dK) {
+                k_kslot_reduce<<<grid_for(ctx, (int64_t)nd * nn, 256, 8), 256, 0, ctx->stream>>>(Kslot, Krow, dK + d0 * nn, nd, n, grid, kslots);
+                ctx->launches++;
+                CK(cudaGetLastError());
+            }
+        }
+        CK(cudaEventRecord(ctx->ev[2][1], ctx->stream));
+        return TUNA_OK;
+    }
+    // ---- simple variant (any n) ----
     const int r = std::max(1, 256 / n);
     const int threads = (n * r + 31) / 32 * 32;
     const int lch = 4;
     const int nchunk = (n + lch - 1) / lch;
     const int nwarp = (threads + 31) / 32;
-    int rc;
     const size_t need_kpart = (size_t)std::min(nD, 4) * n * nchunk * n;
     if (dK && need_kpart > ctx->cap_kpart) {
         if ((rc = dev_alloc(ctx, &ctx->d_Kpart, need_kpart))) return rc;
         ctx->cap_kpart = need_kpart;
     }
     CK(cudaEventRecord(ctx->ev[2][0], ctx->stream));
-    const size_t nn = (size_t)n * n;
     for (int d0 = 0; d0 < nD; d0 += 4) {
         const int nd = std::min(4, nD - d0);
         const size_t smem = ((size_t)nd * lch * nwarp + (size_t)nd * r * n) * sizeof(double);
@@ -887,6 +1115,8 @@ int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, doub
     CK(cudaEventRecord(ctx->ev[2][1], ctx->stream));
     return TUNA_OK;
 }
+
+extern "C" {
 
 int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K) {
     if (!ctx) return TUNA_ERR_ARG;
