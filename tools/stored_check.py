@@ -28,7 +28,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
                       "GBps": 8.0 * n ** 4 / (np.median(ts) * 1e-3) / 1e9}))
 else:
     cfgs = [("simple", {}), ("tma", {})]
-    for tile in (24, 40):
+    for tile in ():
         for st in (3, 4):
             for cps in (1, 2):
                 cfgs.append(("tma", dict(TUNA_B200_JK_TILE_KB=str(tile), TUNA_B200_JK_STAGES=str(st), TUNA_B200_JK_CTAS_PER_SM=str(cps))))

@@ -166,4 +166,19 @@ TUNA_HD double eri_ao_quartet(const double* __restrict__ ppA, int nA, const doub
     return s;
 }
 
+// The same sum restricted to primitive quartets pq = start, start + stride, ... (pq = i * nB + j): lets the lanes of a
+// warp share one heavily contracted AO quartet (e.g. (ss|ss) of cc-pVTZ: 64 x 64 primitive quartets).
+TUNA_HD double eri_ao_quartet_strided(const double* __restrict__ ppA, int nA, const double* __restrict__ ppB, int nB, PairClass ca, PairClass cb,
+                                      const double* __restrict__ boys_tab, const double* __restrict__ herm, int start, int stride) {
+    double s = 0.0;
+    const int total = nA * nB;
+    int i = start / nB, j = start % nB;
+    for (int pq = start; pq < total; pq += stride) {
+        s += eri_prim_quartet(ppA + (size_t)i * PP_DOUBLES, ppB + (size_t)j * PP_DOUBLES, ca, cb, boys_tab, herm);
+        j += stride;
+        while (j >= nB) { j -= nB; ++i; }
+    }
+    return s;
+}
+
 }  // namespace tuna

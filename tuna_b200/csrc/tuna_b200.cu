@@ -158,19 +158,42 @@ __device__ __forceinline__ double quartet_value(const PairTableDev& T, int64_t a
 // kernels
 // ------------------------------------------------------------------------------------------------
 // Dense fill: one thread per unique parity-surviving AO quartet; parity-forbidden entries stay zero from the memset.
+// Heavily contracted quartets (more than 32 primitive quartets) are shared by the 32 lanes of the warp, so the few
+// (ss|ss)-type quartets of a contracted basis no longer serialise thousands of primitive quartets in one thread.
 __global__ void __launch_bounds__(128) k_eri_fill(PairTableDev T, const double* __restrict__ boys, const double* __restrict__ herm,
                                                   double* __restrict__ out, int n) {
     const int64_t ntask = T.tbeg[4];
     const int64_t n1 = n, n2 = n1 * n1, n3 = n2 * n1;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntask; t += (int64_t)gridDim.x * blockDim.x) {
-        int64_t a, b;
-        decode_task(T, t, a, b);
-        const double v = quartet_value(T, a, b, boys, herm);
-        const int64_t i = T.pi[a], j = T.pj[a], k = T.pi[b], l = T.pj[b];
-        out[i * n3 + j * n2 + k * n1 + l] = v; out[k * n3 + l * n2 + i * n1 + j] = v;
-        out[j * n3 + i * n2 + l * n1 + k] = v; out[l * n3 + k * n2 + j * n1 + i] = v;
-        out[j * n3 + i * n2 + k * n1 + l] = v; out[l * n3 + k * n2 + i * n1 + j] = v;
-        out[i * n3 + j * n2 + l * n1 + k] = v; out[k * n3 + l * n2 + j * n1 + i] = v;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp0 * 32; base < ntask; base += nwarps * 32) {
+        const int64_t t = base + lane;
+        const bool valid = t < ntask;
+        int64_t a = 0, b = 0;
+        int nq = 0;
+        if (valid) {
+            decode_task(T, t, a, b);
+            nq = T.npp[a] * T.npp[b];
+        }
+        const bool heavy = nq > 32;
+        double v = (valid && !heavy) ? quartet_value(T, a, b, boys, herm) : 0.0;
+        unsigned mask = __ballot_sync(0xffffffffu, heavy);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int64_t as = __shfl_sync(0xffffffffu, a, src), bs = __shfl_sync(0xffffffffu, b, src);
+            double part = eri_ao_quartet_strided(T.pp + T.ppoff[as] * PP_DOUBLES, T.npp[as], T.pp + T.ppoff[bs] * PP_DOUBLES, T.npp[bs],
+                                                 unpack_cls(T.cls[as]), unpack_cls(T.cls[bs]), boys, herm, lane, 32);
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == src) v = part;
+        }
+        if (valid) {
+            const int64_t i = T.pi[a], j = T.pj[a], k = T.pi[b], l = T.pj[b];
+            out[i * n3 + j * n2 + k * n1 + l] = v; out[k * n3 + l * n2 + i * n1 + j] = v;
+            out[j * n3 + i * n2 + l * n1 + k] = v; out[l * n3 + k * n2 + j * n1 + i] = v;
+            out[j * n3 + i * n2 + k * n1 + l] = v; out[l * n3 + k * n2 + i * n1 + j] = v;
+            out[i * n3 + j * n2 + l * n1 + k] = v; out[k * n3 + l * n2 + j * n1 + i] = v;
+        }
     }
 }
 
@@ -1025,7 +1048,7 @@ extern "C" int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, doubl
     const size_t nn = (size_t)n * n;
     const char* env_k = getenv("TUNA_B200_STORED_KERNEL");
     const bool want_tma = !(env_k && std::string(env_k) == "simple");
-    if (want_tma && (n % 2 == 0) && (n > 64 || (env_k && std::string(env_k) == "tma"))) {
+    if (want_tma && (n % 2 == 0) && n >= 8) {
         // ---- TMA-streamed persistent kernel (16-byte alignment of every row tile needs an even n) ----
         const int r = std::max(1, 512 / n);
         const int threads = (n * r + 31) / 32 * 32;
