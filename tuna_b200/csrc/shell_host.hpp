@@ -241,6 +241,16 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
                 }
             }
 
+    // divergence control: lanes of a warp take consecutive entries, so order every work list by inner-loop length
+    auto sort_pairs = [](std::vector<unsigned>& v, size_t lo, size_t hi, auto keyfn) {      // v holds 2-word entries in [lo, hi)
+        std::vector<std::pair<unsigned, unsigned>> tmp;
+        for (size_t i = lo; i < hi; i += 2) tmp.push_back({v[i], v[i + 1]});
+        std::stable_sort(tmp.begin(), tmp.end(), [&](const auto& x, const auto& y) { return keyfn(x) > keyfn(y); });
+        for (size_t i = 0; i < tmp.size(); ++i) { v[lo + 2 * i] = tmp[i].first; v[lo + 2 * i + 1] = tmp[i].second; }
+    };
+    std::stable_sort(C.t_rt.begin(), C.t_rt.end(), [](unsigned x, unsigned y) { return ((x >> 16) & 255) > ((y >> 16) & 255); });
+    sort_pairs(C.t_u, 0, C.t_u.size(), [](const std::pair<unsigned, unsigned>& e) { return e.second >> 16; });
+
     // bra z-combinations, chunked so that the S slice and the integral buffer fit their budgets
     struct Quartet { int a, b, c, d; };
     std::vector<std::vector<Quartet>> per_bz;
@@ -332,19 +342,56 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
         C.uniq[4] = (La == Lc && Lb == Ld) ? count(false, false, true) : 0;
         C.uniq[5] = (La == Lb && Lb == Lc && Lc == Ld) ? count(true, true, true) : 0;
     }
-    // phase 5: CSR over outputs per chunk
     const int nchunk = (int)C.chunk_bz0.size() - 1;
+    for (int ch = 0; ch < nchunk; ++ch)
+        sort_pairs(C.t_s, 2 * (size_t)C.chunk_s0[ch], 2 * (size_t)C.chunk_s0[ch + 1], [](const std::pair<unsigned, unsigned>& e) { return e.second >> 16; });
+    // integral slots of a chunk re-ordered by descending number of (m, m') terms
+    std::vector<int> slot_perm(C.nint);       // old global slot (chunk_e0 + slot) -> new slot inside its chunk
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int e0 = C.chunk_e0[ch], ne = C.chunk_e0[ch + 1] - e0;
+        std::vector<int> order(ne);
+        for (int i = 0; i < ne; ++i) order[i] = i;
+        auto nterm = [&](int i) {
+            const unsigned w1 = C.p4[2 * (size_t)(e0 + i) + 1];
+            const int mx = (int)((w1 >> 20) & 15) - (int)((w1 >> 16) & 15) + 1, my = (int)((w1 >> 28) & 15) - (int)((w1 >> 24) & 15) + 1;
+            return mx * my;
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return nterm(x) > nterm(y); });
+        std::vector<unsigned> np4(2 * (size_t)ne);
+        for (int k = 0; k < ne; ++k) {
+            np4[2 * k] = C.p4[2 * (size_t)(e0 + order[k])];
+            np4[2 * k + 1] = C.p4[2 * (size_t)(e0 + order[k]) + 1];
+            slot_perm[e0 + order[k]] = k;
+        }
+        std::copy(np4.begin(), np4.end(), C.p4.begin() + 2 * (size_t)e0);
+    }
+    // phase 5: CSR over outputs per chunk; outputs ordered by descending total number of terms (same order in every chunk)
+    std::vector<long long> tot_terms(C.nout, 0);
+    for (const auto& v : per_bz)
+        for (const Quartet& q : v) {
+            ++tot_terms[ob[0] + q.a * ncC + q.c]; ++tot_terms[ob[1] + q.a * ncD + q.d]; ++tot_terms[ob[2] + q.b * ncC + q.c];
+            ++tot_terms[ob[3] + q.b * ncD + q.d]; ++tot_terms[ob[4] + q.a * ncB + q.b]; ++tot_terms[ob[5] + q.c * ncD + q.d];
+        }
+    std::vector<int> oorder(C.nout), opos(C.nout);       // new position -> old output id, and the inverse
+    for (int o = 0; o < C.nout; ++o) oorder[o] = o;
+    std::stable_sort(oorder.begin(), oorder.end(), [&](int x, int y) { return tot_terms[x] > tot_terms[y]; });
+    for (int k = 0; k < C.nout; ++k) opos[oorder[k]] = k;
+    {
+        std::vector<unsigned short> nomap(C.nout);
+        for (int k = 0; k < C.nout; ++k) nomap[k] = (unsigned short)(C.omap[oorder[k]] | (oorder[k] >= C.nk ? 0x8000 : 0));    // bit 15: J entry
+        C.omap.swap(nomap);
+    }
     for (int ch = 0; ch < nchunk; ++ch) {
         std::vector<std::vector<unsigned>> terms(C.nout);
         for (int bi = C.chunk_bz0[ch]; bi < C.chunk_bz0[ch + 1]; ++bi)
             for (const Quartet& q : per_bz[bi]) {
-                const unsigned it = (unsigned)slot_of[pf_key(bi, q)];
-                terms[ob[0] + q.a * ncC + q.c].push_back(it | (unsigned)(pb[0] + q.d * ncB + q.b) << 16);   // KAC += I P[d][b]
-                terms[ob[1] + q.a * ncD + q.d].push_back(it | (unsigned)(pb[1] + q.c * ncB + q.b) << 16);   // KAD += I P[c][b]
-                terms[ob[2] + q.b * ncC + q.c].push_back(it | (unsigned)(pb[2] + q.d * ncA + q.a) << 16);   // KBC += I P[d][a]
-                terms[ob[3] + q.b * ncD + q.d].push_back(it | (unsigned)(pb[3] + q.c * ncA + q.a) << 16);   // KBD += I P[c][a]
-                terms[ob[4] + q.a * ncB + q.b].push_back(it | (unsigned)(pb[4] + q.c * ncD + q.d) << 16);   // JAB += I (P[c][d]+P[d][c])
-                terms[ob[5] + q.c * ncD + q.d].push_back(it | (unsigned)(pb[5] + q.a * ncB + q.b) << 16);   // JCD += I (P[a][b]+P[b][a])
+                const unsigned it = (unsigned)slot_perm[C.chunk_e0[ch] + slot_of[pf_key(bi, q)]];
+                terms[opos[ob[0] + q.a * ncC + q.c]].push_back(it | (unsigned)(pb[0] + q.d * ncB + q.b) << 16);   // KAC += I P[d][b]
+                terms[opos[ob[1] + q.a * ncD + q.d]].push_back(it | (unsigned)(pb[1] + q.c * ncB + q.b) << 16);   // KAD += I P[c][b]
+                terms[opos[ob[2] + q.b * ncC + q.c]].push_back(it | (unsigned)(pb[2] + q.d * ncA + q.a) << 16);   // KBC += I P[d][a]
+                terms[opos[ob[3] + q.b * ncD + q.d]].push_back(it | (unsigned)(pb[3] + q.c * ncA + q.a) << 16);   // KBD += I P[c][a]
+                terms[opos[ob[4] + q.a * ncB + q.b]].push_back(it | (unsigned)(pb[4] + q.c * ncD + q.d) << 16);   // JAB += I (P[c][d]+P[d][c])
+                terms[opos[ob[5] + q.c * ncD + q.d]].push_back(it | (unsigned)(pb[5] + q.a * ncB + q.b) << 16);   // JCD += I (P[a][b]+P[b][a])
             }
         C.p5off.push_back((unsigned)C.p5term.size());       // multiple of 4: 16-byte aligned uint4 loads
         unsigned run = 0;                                   // in units of four terms
@@ -357,7 +404,6 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
         C.p5ptr.push_back(run);
     }
 }
-
 
 // View of the tables with the given base pointers (host vectors for the CPU test build, device copies for the GPU).
 template <class PtrOf>

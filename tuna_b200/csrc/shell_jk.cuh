@@ -78,7 +78,7 @@ struct ClassTablesDev {
     const unsigned* p5term;                 // concatenated; chunk c starts at p5off[c]
     const unsigned* p5off;                  // [nchunk]
     const unsigned short* pmap;             // [nout]  staged density entry -> (row, col), high bit 15 = symmetrise
-    const unsigned short* omap;             // [nout]  output entry -> (row, col); entries < nk are K, the rest J
+    const unsigned short* omap;             // [nout]  output entry -> (row, col); bit 15 set = J entry, else K (outputs sorted by work)
     int nk;                                 // number of K outputs (first nk entries of the output list)
     // phases 1-3 as flat work lists (no per-entry index arithmetic on the device):
     //   t_rt[i]  = (w * NS + n) | w << 16 | n << 24                                   R^n_w entries with 2n + w <= Ltot
@@ -328,7 +328,7 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
             TUNA_LANES(x, nout) {
                 const unsigned m = CT.omap[x];
                 const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
-                double* dst = (x < CT.nk ? Kf : Jf) + dn * nn + (size_t)r * ncart + c;
+                double* dst = ((m & 0x8000u) ? Jf : Kf) + dn * nn + (size_t)r * ncart + c;
                 Pol::atomic_add(dst, Out[dn * nout + x]);
             }
         }
