@@ -93,6 +93,9 @@ struct tuna_ctx {
     struct ClassTabDev { ClassTablesHost host; ClassTablesDev view; unsigned char* blob = nullptr; };
     std::map<int, ClassTabDev> class_tabs;      // key La | Lb<<4 | Lc<<8 | Ld<<12
     std::vector<JobHost> jobs;
+    static constexpr int NAUX = 4;
+    cudaStream_t aux[NAUX] = {};     // class jobs of one build are independent (atomic accumulation): run them on 4 streams
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
     int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
 };
@@ -754,6 +757,11 @@ int tuna_ctx_create(int device, tuna_ctx** out) {
     ctx->stream = ctx->own_stream;
     for (int w = 0; w < 4; ++w)
         for (int s = 0; s < 2; ++s) CK(cudaEventCreate(&ctx->ev[w][s]));
+    for (int a = 0; a < tuna_ctx::NAUX; ++a) {
+        CK(cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     std::vector<double> boys, herm;
     build_boys_table(boys);
     build_hermite_poly_table(herm);
@@ -788,6 +796,11 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int w = 0; w < 4; ++w)
         for (int s = 0; s < 2; ++s) if (ctx->ev[w][s]) cudaEventDestroy(ctx->ev[w][s]);
+    for (int a = 0; a < tuna_ctx::NAUX; ++a) {
+        if (ctx->aux[a]) { cudaStreamSynchronize(ctx->aux[a]); cudaStreamDestroy(ctx->aux[a]); }
+        if (ctx->ev_join[a]) cudaEventDestroy(ctx->ev_join[a]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return TUNA_OK;
@@ -1298,9 +1311,14 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 ctx->jobs.push_back(jh);
             }
         if ((rc = dev_alloc(ctx, &ctx->d_prefix, std::max<size_t>(all_prefix.size(), 1)))) return rc;
+        for (size_t j = 0; j < ctx->jobs.size(); ++j) ctx->jobs[j].job.item_prefix = reinterpret_cast<const long long*>(prefix_off[j]);   // offset, fixed up below
         CK(cudaMemcpyAsync(ctx->d_prefix, all_prefix.data(), all_prefix.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        for (size_t j = 0; j < ctx->jobs.size(); ++j) ctx->jobs[j].job.item_prefix = ctx->d_prefix + prefix_off[j];
+        for (auto& jh : ctx->jobs) jh.job.item_prefix = ctx->d_prefix + reinterpret_cast<size_t>(jh.job.item_prefix);
+        // heaviest class jobs first: better packing of the tails across the auxiliary streams
+        std::stable_sort(ctx->jobs.begin(), ctx->jobs.end(), [](const tuna_ctx::JobHost& x, const tuna_ctx::JobHost& y) {
+            return x.allowed * (double)x.job.nitems > y.allowed * (double)y.job.nitems;
+        });
         ctx->shell_tau = tau;
     }
     return TUNA_OK;
@@ -1308,7 +1326,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
 
 template <int GG>
 static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
-                                double* Jf, double* Kf, double tau) {
+                                double* Jf, double* Kf, double tau, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_shell_jk<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1319,7 +1337,7 @@ static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, cons
     long long blocks = (nchunk - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // chunks owned by this rank
     if (blocks <= 0) return cudaSuccess;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
-    k_shell_jk<GG><<<(int)blocks, jh.threads, jh.smem, ctx->stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
+    k_shell_jk<GG><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
                                                                          jh.allowed, ctx->shard_rank, ctx->shard_n);
     ctx->launches++;
     return cudaGetLastError();
@@ -1360,20 +1378,28 @@ static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
         ShellData D;
         D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
         D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
+        int jn = 0;
         for (const auto& jh : ctx->jobs) {
+            cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
             cudaError_t e;
             switch (jh.G) {
-                case 1: e = launch_shell<1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 2: e = launch_shell<2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 4: e = launch_shell<4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 8: e = launch_shell<8>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 16: e = launch_shell<16>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 32: e = launch_shell<32>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 64: e = launch_shell<64>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
-                case 128: e = launch_shell<128>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
-                default: e = launch_shell<256>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau); break;
+                case 1: e = launch_shell<1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 2: e = launch_shell<2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 4: e = launch_shell<4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 8: e = launch_shell<8>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 16: e = launch_shell<16>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 32: e = launch_shell<32>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 64: e = launch_shell<64>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 128: e = launch_shell<128>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                default: e = launch_shell<256>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
             }
             if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk launch: ") + cudaGetErrorString(e));
+        }
+        for (int a = 0; a < tuna_ctx::NAUX; ++a) {
+            CK(cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[a], 0));
         }
     } else {
         k_jk_direct<<<grid_for(ctx, ctx->task_begin[4] / ctx->shard_n + 1, 128, 16), 128, 0, ctx->stream>>>(
