@@ -89,12 +89,15 @@ struct tuna_ctx {
     int* d_sh_ao = nullptr; int* d_class_lists = nullptr; long long* d_prefix = nullptr; double* d_finv = nullptr;
     double* d_eval = nullptr;
     std::vector<size_t> class_list_off;
-    struct JobHost { ShellJob job; int G; size_t smem; double allowed; int threads, gpc; };
+    struct JobHost { ShellJob job; int G; size_t smem; double allowed; int threads, gpc; bool own_launch = false; };
     struct ClassTabDev { ClassTablesHost host; ClassTablesDev view; unsigned char* blob = nullptr; };
     std::map<int, ClassTabDev> class_tabs;      // key La | Lb<<4 | Lc<<8 | Ld<<12
     std::vector<JobHost> jobs;
-    static constexpr int NAUX = 4;
-    cudaStream_t aux[NAUX] = {};     // class jobs of one build are independent (atomic accumulation): run them on 4 streams
+    struct LaunchGroup { int G = 1, threads = 128, njobs = 0, ctas_per_sm = 1; long long nunits = 0; size_t smem = 0, job_slot_off = 0;
+                         ShellJob* d_jobs = nullptr; long long* d_unit_prefix = nullptr; };
+    std::vector<LaunchGroup> groups;      // one launch per group size G covers all class jobs with that G
+    static constexpr int NAUX = 6;
+    cudaStream_t aux[NAUX] = {};     // class jobs of one build are independent (atomic accumulation): one launch per group size, each on its own stream
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
     int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
@@ -543,23 +546,84 @@ struct DevPolicy {
     __device__ __forceinline__ static void atomic_add(double* p, double v) { atomicAdd(p, v); }
 };
 
-// One group of G lanes per shell quartet; groups of a CTA march through the job's item list in lock step.
-// Items are dealt to ranks in chunks of J.chunk consecutive shell quartets (multi-GPU sharding).
+// One group of G lanes per shell quartet.  A launch covers ALL class jobs that use this group size: the work units
+// (job, chunk of J.chunk consecutive shell quartets) of those jobs form one flat list (heaviest jobs first) that the CTAs
+// walk with a grid stride; units are dealt round-robin to ranks (multi-GPU sharding).  The job descriptor of
+// the current unit is copied into shared memory; the bra position of the unit's first item is found once by binary search,
+// the others by walking the per-bra prefix.
 template <int GG>
-__global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
-                                                                     const double* __restrict__ Psym, double* Jf, double* Kf, int ncart, double tau,
-                                                                     const unsigned long long* scalars, double* evaluated,
-                                                                     double allowed_per_item, int rank, int nranks) {
+__global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(const ShellJob* __restrict__ jobs, const long long* __restrict__ unit_prefix,
+                                                                     int njobs, ShellData D, int nD, const double* __restrict__ Pf,
+                                                                     const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
+                                                                     double tau, const unsigned long long* scalars, double* evaluated,
+                                                                     int rank, int nranks, size_t job_slot_off) {
+    extern __shared__ double smem_all[];
+    ShellJob& J = *reinterpret_cast<ShellJob*>(smem_all + job_slot_off);          // behind the group slices
+    int& s_ib0 = *reinterpret_cast<int*>(smem_all + job_slot_off + (sizeof(ShellJob) + 7) / 8);
+    const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
+    const double dmax = __longlong_as_double((long long)scalars[0]);
+    const long long nunits = unit_prefix[njobs];
+    double done = 0.0;
+    for (long long u = (long long)blockIdx.x * nranks + rank; u < nunits; u += (long long)gridDim.x * nranks) {
+        int lo = 0, hi = njobs;                         // job of this unit (uniform in the CTA)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (unit_prefix[mid] <= u) lo = mid; else hi = mid;
+        }
+        __syncthreads();                                // previous unit is done with J / s_ib0
+        {
+            const int* src = reinterpret_cast<const int*>(jobs + lo);
+            int* dst = reinterpret_cast<int*>(&J);
+            for (int x = threadIdx.x; x < (int)(sizeof(ShellJob) / sizeof(int)); x += blockDim.x) dst[x] = src[x];
+        }
+        __syncthreads();
+        const long long CH = J.chunk;
+        const long long first = (u - unit_prefix[lo]) * CH;
+        if (threadIdx.x == 0) {
+            int ib, ik;
+            shell_item_decode(J, first, ib, ik);
+            s_ib0 = ib;
+        }
+        __syncthreads();
+        const int ib0 = s_ib0;
+        double* sm = smem_all + (size_t)gid * J.total;
+        for (int k0 = 0; k0 < (int)CH; k0 += gpc) {
+            const long long item = first + k0 + gid;
+            bool active = (k0 + gid) < (int)CH && item < J.nitems;
+            int AB = 0, CD = 0;
+            double w = 1.0;
+            if (active) {
+                int ib = ib0;
+                while (J.item_prefix[ib + 1] <= item) ++ib;
+                AB = J.bra_list[ib]; CD = J.ket_list[(int)(item - J.item_prefix[ib])];
+                if (tau > 0.0 && D.pairQ[AB] * D.pairQ[CD] * dmax < tau) active = false;
+                const bool ab = D.pairA[AB] == D.pairB[AB], cd = D.pairA[CD] == D.pairB[CD], dg = AB == CD;
+                if (ab) w *= 0.5;
+                if (cd) w *= 0.5;
+                if (dg) w *= 0.5;
+                if (active && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+            }
+            shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
+        }
+    }
+    if (done != 0.0) atomicAdd(evaluated, done);
+}
+
+// Single-job variant: the job descriptor travels as a kernel parameter (constant bank / uniform registers instead of shared
+// memory), which is ~25 % faster per quartet; used for class jobs large enough to fill the GPU on their own.
+template <int GG>
+__global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk_one(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
+                                                                         const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
+                                                                         double tau, const unsigned long long* scalars, double* evaluated,
+                                                                         int rank, int nranks) {
     extern __shared__ double smem_all[];
     const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
-    int& s_ib0 = *reinterpret_cast<int*>(smem_all + (size_t)gpc * J.total);      // one extra slot behind the group slices
+    int& s_ib0 = *reinterpret_cast<int*>(smem_all + (size_t)gpc * J.total);
     double* sm = smem_all + (size_t)gid * J.total;
     const double dmax = __longlong_as_double((long long)scalars[0]);
     const long long CH = J.chunk;
     const long long nchunk = (J.nitems + CH - 1) / CH;
     double done = 0.0;
-    // chunk-major: a CTA owns CH consecutive items of the job; the bra position of the chunk's first item is found once
-    // by binary search, the others by walking the per-bra prefix (consecutive items share or neighbour the bra).
     for (long long gc = (long long)blockIdx.x * nranks + rank; gc < nchunk; gc += (long long)gridDim.x * nranks) {
         const long long first = gc * CH;
         if (threadIdx.x == 0) {
@@ -788,6 +852,7 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->d_P); dev_free(&ctx->d_J); dev_free(&ctx->d_K);
     dev_free(&ctx->d_Pc); dev_free(&ctx->d_Jc); dev_free(&ctx->d_Kc); dev_free(&ctx->d_tmp); dev_free(&ctx->d_Kpart);
     for (auto& kv : ctx->class_tabs) dev_free(&kv.second.blob);
+    for (auto& g : ctx->groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
     dev_free(&ctx->d_pairA); dev_free(&ctx->d_pairB); dev_free(&ctx->d_pair_rec); dev_free(&ctx->d_rec);
     dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_prefix); dev_free(&ctx->d_finv);
     dev_free(&ctx->d_eval);
@@ -1180,6 +1245,7 @@ int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K)
 int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
     if (!ctx) return TUNA_ERR_ARG;
     if (nranks < 1 || rank < 0 || rank >= nranks) FAIL(TUNA_ERR_ARG, "tuna_set_shard: bad rank / nranks");
+    if (ctx->shard_n != nranks) ctx->shell_tau = -1.0;      // the big/small job split depends on the rank count
     ctx->shard_rank = rank; ctx->shard_n = nranks;
     return TUNA_OK;
 }
@@ -1319,13 +1385,53 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
         std::stable_sort(ctx->jobs.begin(), ctx->jobs.end(), [](const tuna_ctx::JobHost& x, const tuna_ctx::JobHost& y) {
             return x.allowed * (double)x.job.nitems > y.allowed * (double)y.job.nitems;
         });
+        // large class jobs get their own launch (descriptor as kernel parameter); the many small ones are grouped by group size
+        // and shared-memory footprint into persistent launches that walk a flat (job, chunk) unit list
+        {
+            const char* et = getenv("TUNA_B200_OWN_LAUNCH_MIN");
+            const double thr = (et ? atof(et) : 5.0e5) * ctx->shard_n;
+            for (auto& jh : ctx->jobs) jh.own_launch = jh.allowed * (double)jh.job.nitems >= thr;
+        }
+        for (auto& g : ctx->groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
+        ctx->groups.clear();
+        for (int G = 256; G >= 1; G >>= 1)
+            for (int bucket = 40; bucket >= 0; --bucket) {       // jobs of similar shared-memory footprint share a launch (occupancy)
+                std::vector<ShellJob> js;
+                std::vector<long long> up(1, 0);
+                size_t max_slices = 0;
+                int threads = 128;
+                for (const auto& jh : ctx->jobs) {
+                    if (jh.G != G || jh.own_launch) continue;
+                    const size_t slices = (size_t)jh.gpc * jh.job.total;
+                    int b = 0;
+                    while (((size_t)1 << b) < slices) ++b;
+                    b = 2 * b + (slices > ((size_t)3 << (b - 2)) ? 1 : 0);       // half-octave buckets
+                    if (b != bucket) continue;
+                    js.push_back(jh.job);
+                    up.push_back(up.back() + (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk);
+                    max_slices = std::max(max_slices, slices);
+                    threads = jh.threads;
+                }
+                if (js.empty()) continue;
+                tuna_ctx::LaunchGroup lg;
+                lg.G = G; lg.threads = threads; lg.njobs = (int)js.size(); lg.nunits = up.back();
+                lg.job_slot_off = (max_slices + 1) & ~(size_t)1;
+                lg.smem = (lg.job_slot_off + (sizeof(ShellJob) + 7) / 8 + 2) * sizeof(double);
+                lg.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / lg.smem));
+                if ((rc = dev_alloc(ctx, &lg.d_jobs, js.size()))) return rc;
+                if ((rc = dev_alloc(ctx, &lg.d_unit_prefix, up.size()))) return rc;
+                CK(cudaMemcpyAsync(lg.d_jobs, js.data(), js.size() * sizeof(ShellJob), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(lg.d_unit_prefix, up.data(), up.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                ctx->groups.push_back(lg);
+            }
         ctx->shell_tau = tau;
     }
     return TUNA_OK;
 }
 
 template <int GG>
-static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
+static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::LaunchGroup& lg, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                 double* Jf, double* Kf, double tau, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -1333,12 +1439,30 @@ static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, cons
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    long long blocks = (lg.nunits - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // units owned by this rank
+    if (blocks <= 0) return cudaSuccess;
+    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * lg.ctas_per_sm);
+    k_shell_jk<GG><<<(int)blocks, lg.threads, lg.smem, stream>>>(lg.d_jobs, lg.d_unit_prefix, lg.njobs, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau,
+                                                                 ctx->d_scalars, ctx->d_eval, ctx->shard_rank, ctx->shard_n, lg.job_slot_off);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+template <int GG>
+static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
+                                    double* Jf, double* Kf, double tau, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_shell_jk_one<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     const long long nchunk = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
     long long blocks = (nchunk - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // chunks owned by this rank
     if (blocks <= 0) return cudaSuccess;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
-    k_shell_jk<GG><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
-                                                                         jh.allowed, ctx->shard_rank, ctx->shard_n);
+    k_shell_jk_one<GG><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
+                                                                     ctx->shard_rank, ctx->shard_n);
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -1382,18 +1506,35 @@ static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
         for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
         int jn = 0;
         for (const auto& jh : ctx->jobs) {
+            if (!jh.own_launch) continue;
             cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
             cudaError_t e;
             switch (jh.G) {
-                case 1: e = launch_shell<1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 2: e = launch_shell<2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 4: e = launch_shell<4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 8: e = launch_shell<8>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 16: e = launch_shell<16>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 32: e = launch_shell<32>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 64: e = launch_shell<64>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 128: e = launch_shell<128>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                default: e = launch_shell<256>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 1: e = launch_shell_one<1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 2: e = launch_shell_one<2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 4: e = launch_shell_one<4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 8: e = launch_shell_one<8>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 16: e = launch_shell_one<16>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 32: e = launch_shell_one<32>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 64: e = launch_shell_one<64>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 128: e = launch_shell_one<128>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                default: e = launch_shell_one<256>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+            }
+            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk_one launch: ") + cudaGetErrorString(e));
+        }
+        for (const auto& lg : ctx->groups) {
+            cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
+            cudaError_t e;
+            switch (lg.G) {
+                case 1: e = launch_shell<1>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 2: e = launch_shell<2>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 4: e = launch_shell<4>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 8: e = launch_shell<8>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 16: e = launch_shell<16>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 32: e = launch_shell<32>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 64: e = launch_shell<64>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 128: e = launch_shell<128>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                default: e = launch_shell<256>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
             }
             if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk launch: ") + cudaGetErrorString(e));
         }
