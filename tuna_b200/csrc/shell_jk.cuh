@@ -203,7 +203,6 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
     const int oExA = SP_HDR + sp_ez_size(La, Lb), oExC = SP_HDR + sp_ez_size(Lc, Ld);
 
     for (int ch = 0; ch < CT.nchunk; ++ch) {
-        const int bz0 = CT.chunk_bz0[ch], bz1 = CT.chunk_bz0[ch + 1];
         const int e0 = CT.chunk_e0[ch], ne = CT.chunk_e0[ch + 1] - e0;
         if (active) {
             TUNA_LANES(x, ne) It[x] = 0.0;
