@@ -242,3 +242,33 @@ def test_direct_engines_agree_and_general_density(tb, oracle, name, monkeypatch)
     scale = max(1.0, np.abs(Ks).max())
     for a, b in ((Jd, Js), (Kd, Ks), (Jg, Js), (Kg, Ks)):
         assert np.abs(a - b).max() < 1e-11 * scale
+
+
+def test_high_angular_momentum_h_shells(tb, oracle):
+    """A synthetic two-centre basis with every shell type up to H (L = 5, the reference's maximum, tuna_molecule.py:612-618):
+    full Cartesian tensor vs the oracle, and the shell-quartet engine (multi-chunk (hh|hh) class tables) vs the stored path."""
+    from tuna_b200 import workloads as w
+    from tuna_b200.basis import flatten, from_arrays
+    shells_a = [(0, [1.3], [1.0]), (1, [0.9], [1.0]), (5, [1.1], [1.0])]
+    shells_b = [(2, [0.8], [1.0]), (4, [1.2], [1.0]), (5, [0.7], [1.0]), (3, [1.0, 0.4], [0.6, 0.5])]
+    b = w.shells_to_components([shells_a, shells_b], [0.0, 1.9])
+    bfs = from_arrays(b["origins"], b["lmn"], b["nprim"], b["exps"], b["raw_coefs"])
+    n = len(bfs)
+    fb = oracle.FlatBasis.from_reference_objects(bfs)
+    ref = oracle.eri_fill(fb)
+    ctx = tb.Context(0)
+    ctx.set_basis(*flatten(bfs))
+    ctx.set_transform(np.eye(n))
+    ctx.eri_fill_cart()
+    E = ctx.eri_download(0)
+    _check_eri(E, ref)
+    ctx.eri_cart_to_sph()
+    rng = np.random.default_rng(3)
+    P = rng.standard_normal((2, n, n))
+    P = (P + P.transpose(0, 2, 1)) / 2
+    Js, Ks = ctx.jk_stored(P)
+    Jd, Kd = ctx.jk_direct(P, tau=0.0)
+    scale = max(1.0, np.abs(Ks).max())
+    assert np.abs(Jd - Js).max() < 1e-11 * scale and np.abs(Kd - Ks).max() < 1e-11 * scale
+    assert np.abs(Js[0] - oracle.coulomb(P[0], ref)).max() < 1e-11 * scale
+    assert ctx.counts()["evaluated_last_direct"] == ctx.counts()["surviving_quartets"]

@@ -81,3 +81,29 @@ def test_shell_engine_vs_oracle(emul, oracle, name):
         for d in range(2):
             Jr, Kr = oracle.coulomb(P[d], E), oracle.exchange(P[d], E)
             assert np.abs(J[d] - Jr).max() < 1e-11 and np.abs(K[d] - Kr).max() < 1e-11
+
+
+def test_shell_engine_h_shells(emul, oracle):
+    """All shell types up to H, including the multi-chunk (hh|hh) class tables, on a synthetic two-centre basis."""
+    from tuna_b200 import workloads as w
+    from tuna_b200.basis import from_arrays
+    shells_a = [(0, [1.3], [1.0]), (1, [0.9], [1.0]), (5, [1.1], [1.0])]
+    shells_b = [(2, [0.8], [1.0]), (4, [1.2], [1.0]), (5, [0.7], [1.0]), (3, [1.0, 0.4], [0.6, 0.5])]
+    b = w.shells_to_components([shells_a, shells_b], [0.0, 1.9])
+    fb = oracle.FlatBasis.from_reference_objects(from_arrays(b["origins"], b["lmn"], b["nprim"], b["exps"], b["raw_coefs"]))
+    n = fb.ncart
+    E = oracle.eri_fill(fb)
+    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    oz = np.ascontiguousarray(fb.origins[:, 2])
+    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
+    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
+    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
+    P = np.random.default_rng(1).standard_normal((1, n, n))
+    P = (P + P.transpose(0, 2, 1)) / 2
+    J, K, stats = np.zeros_like(P), np.zeros_like(P), np.zeros(8, dtype=np.int64)
+    rc = emul.emul_jk_shell(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                            fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), 1, P.ctypes.data_as(dp), J.ctypes.data_as(dp),
+                            K.ctypes.data_as(dp), ctypes.c_double(0.0), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    assert rc == 0 and stats[0] == 7
+    assert np.abs(J[0] - oracle.coulomb(P[0], E)).max() < 1e-11 and np.abs(K[0] - oracle.exchange(P[0], E)).max() < 1e-11

@@ -1253,15 +1253,26 @@ int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
 }  // extern "C" (internal helpers follow)
 
 // Per-class work tables: built on the host once per angular class and kept on the device in one blob.
-static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, tuna_ctx::ClassTabDev** out) {
-    const int key = La | Lb << 4 | Lc << 8 | Ld << 12;
+// Shared-memory doubles of one group that do not depend on the chunking (everything except the S slice and the It buffer).
+static int shell_fixed_doubles(const ShellTab& T, int La, int Lb, int Lc, int Ld, int nD) {
+    const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = Ltot / 2 + 1, NGZ = (Lc + 1) * (Ld + 1);
+    const int nout = T.nc[La] * T.nc[Lc] + T.nc[La] * T.nc[Ld] + T.nc[Lb] * T.nc[Lc] + T.nc[Lb] * T.nc[Ld] + T.nc[La] * T.nc[Lb] + T.nc[Lc] * T.nc[Ld];
+    return 2 * (Ltot + 1) + (Ltot + 1) * NS + (Lab + 1) * (Lcd + 1) * NS + (Lab + 1) * NGZ * NS + 2 * nD * nout + 64;
+}
+constexpr int SHELL_SMEM_DOUBLES = 26500;      // 207 KB of the 227 KB a CTA may use
+
+static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int nD, tuna_ctx::ClassTabDev** out) {
+    const int key = La | Lb << 4 | Lc << 8 | Ld << 12 | nD << 16;
     auto it = ctx->class_tabs.find(key);
     if (it != ctx->class_tabs.end()) { *out = &it->second; return TUNA_OK; }
     tuna_ctx::ClassTabDev& E = ctx->class_tabs[key];
     {
         const char* eb = getenv("TUNA_B200_IT_BUDGET");
         const char* es = getenv("TUNA_B200_S_BUDGET");
-        build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host, eb ? atoi(eb) : SH_IT_BUDGET, es ? atoi(es) : SH_S_BUDGET);
+        int itb = eb ? atoi(eb) : SH_IT_BUDGET, sb = es ? atoi(es) : SH_S_BUDGET;
+        const int avail = SHELL_SMEM_DOUBLES - shell_fixed_doubles(ctx->stab, La, Lb, Lc, Ld, nD);     // shrink the chunks for big classes
+        if (itb + sb + 2 > avail) { itb = std::max(64, (avail - 2) / 2); sb = std::max(64, avail - 2 - itb); }
+        build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb);
     }
     const ClassTablesHost& C = E.host;
     size_t total = 0;
@@ -1359,7 +1370,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 prefix_off.push_back(all_prefix.size());
                 all_prefix.insert(all_prefix.end(), prefix.begin(), prefix.end());
                 tuna_ctx::ClassTabDev* ctd = nullptr;
-                if ((rc = get_class_tables(ctx, J.La, J.Lb, J.Lc, J.Ld, &ctd))) return rc;
+                if ((rc = get_class_tables(ctx, J.La, J.Lb, J.Lc, J.Ld, nD, &ctd))) return rc;
                 J.ct = ctd->view;
                 shell_job_layout(J, nD);
                 jh.allowed = (double)ctd->host.allowed;
@@ -1469,7 +1480,30 @@ static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, 
 
 // Core of direct mode on DEVICE buffers: nD densities, bit d of anti_mask marks density d as antisymmetric
 // (its K is Kacc - Kacc^T and its J vanishes); all others must be symmetric.
+static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau);
+
+// Densities are processed in passes small enough for the largest class of the basis to fit its J/K blocks in shared memory.
 static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau) {
+    if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: call tuna_set_basis first");
+    if (ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: call tuna_set_transform first");
+    if (nD <= 0 || nD > 16 || !dP) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments (1 <= nD <= 16)");
+    int nd_max = 4;
+    if (ctx->direct_engine == 1 && ctx->ss.ok) {
+        int Lmax = 0;
+        for (const auto& sh : ctx->ss.shells) Lmax = std::max(Lmax, sh.L);
+        while (nd_max > 1 && shell_fixed_doubles(ctx->stab, Lmax, Lmax, Lmax, Lmax, nd_max) + 1024 > SHELL_SMEM_DOUBLES) --nd_max;
+    }
+    const int npass = (nD + nd_max - 1) / nd_max, per = (nD + npass - 1) / npass;
+    const size_t nn = (size_t)ctx->nbf * ctx->nbf;
+    for (int d0 = 0; d0 < nD; d0 += per) {
+        const int nd = std::min(per, nD - d0);
+        int rc = jk_direct_pass(ctx, nd, dP + d0 * nn, (anti_mask >> d0) & ((1u << nd) - 1u), dJ ? dJ + d0 * nn : nullptr, dK ? dK + d0 * nn : nullptr, tau);
+        if (rc) return rc;
+    }
+    return TUNA_OK;
+}
+
+static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau) {
     if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: call tuna_set_basis first");
     if (ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: call tuna_set_transform first");
     if (nD <= 0 || nD > 16 || !dP) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments (1 <= nD <= 16)");
