@@ -272,3 +272,61 @@ def test_high_angular_momentum_h_shells(tb, oracle):
     assert np.abs(Jd - Js).max() < 1e-11 * scale and np.abs(Kd - Ks).max() < 1e-11 * scale
     assert np.abs(Js[0] - oracle.coulomb(P[0], ref)).max() < 1e-11 * scale
     assert ctx.counts()["evaluated_last_direct"] == ctx.counts()["surviving_quartets"]
+
+
+def test_permuted_and_incomplete_shell_lists(tb, oracle):
+    """The provider receives a flat list of per-component Basis objects.  (i) Components of a shell need not be contiguous
+    (DECONTRACT emits component-major order, tuna_molecule.py:557-565): a random permutation of the list must give the
+    permuted J/K.  (ii) A list that is NOT a union of complete shells (one d component removed) cannot use the shell engine
+    and must fall back to the per-component direct kernel — same answers as the stored path."""
+    g = load_golden("n2_ccpvtz")
+    bfs = basis_objects(g)
+    n = len(bfs)
+    rng = np.random.default_rng(21)
+    P = rng.standard_normal((n, n))
+    P = (P + P.T) / 2
+    ctx = tb.Context(0)
+    from tuna_b200.basis import flatten
+    ctx.set_basis(*flatten(bfs))
+    ctx.set_transform(np.eye(n))
+    J0, K0 = ctx.jk_direct(P, tau=0.0)
+    perm = rng.permutation(n)
+    ctx2 = tb.Context(0)
+    ctx2.set_basis(*flatten([bfs[i] for i in perm]))
+    ctx2.set_transform(np.eye(n))
+    J1, K1 = ctx2.jk_direct(P[np.ix_(perm, perm)], tau=0.0)
+    assert np.abs(J1 - J0[np.ix_(perm, perm)]).max() < 1e-11 and np.abs(K1 - K0[np.ix_(perm, perm)]).max() < 1e-11
+    # (ii) drop the first d_xx component
+    drop = next(i for i, b in enumerate(bfs) if tuple(int(x) for x in b.shell) == (2, 0, 0))
+    keep = [i for i in range(n) if i != drop]
+    ctx3 = tb.Context(0)
+    ctx3.set_basis(*flatten([bfs[i] for i in keep]))
+    ctx3.set_transform(np.eye(n - 1))
+    Pk = P[np.ix_(keep, keep)]
+    J2, K2 = ctx3.jk_direct(Pk, tau=0.0)
+    ctx3.eri_fill_cart()
+    ctx3.eri_cart_to_sph()
+    Js, Ks = ctx3.jk_stored(Pk)                      # n - 1 = 69 is odd: also covers the non-TMA stored kernel
+    assert np.abs(J2 - Js).max() < 1e-11 and np.abs(K2 - Ks).max() < 1e-11
+    E = ctx3.eri_download(1)
+    assert np.abs(Js - oracle.coulomb(Pk, E)).max() < 1e-11
+
+
+def test_many_densities(tb, oracle):
+    """More densities than one pass handles (stored: 4 per launch; direct: limited by the shared-memory J/K blocks)."""
+    g = load_golden("et100")
+    ctx = context_for(g)
+    ctx.set_transform(g["U"])
+    ctx.eri_fill_cart()
+    ctx.eri_cart_to_sph()
+    nbf = int(g["nbf"])
+    rng = np.random.default_rng(8)
+    P = rng.standard_normal((6, nbf, nbf))
+    P = (P + P.transpose(0, 2, 1)) / 2
+    Js, Ks = ctx.jk_stored(P)
+    Jd, Kd = ctx.jk_direct(P, tau=0.0)
+    E = ctx.eri_download(1)
+    for d in (0, 3, 5):
+        assert np.abs(Js[d] - oracle.coulomb(P[d], E)).max() < 1e-10 and np.abs(Ks[d] - oracle.exchange(P[d], E)).max() < 1e-10
+    scale = max(1.0, np.abs(Ks).max())
+    assert np.abs(Jd - Js).max() < 1e-11 * scale and np.abs(Kd - Ks).max() < 1e-11 * scale

@@ -22,7 +22,8 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or needs_build():
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+        extra = os.environ.get("TUNA_B200_NVCC_EXTRA", "").split()
+        cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
         subprocess.run(cmd, check=True)
     return OUT
 

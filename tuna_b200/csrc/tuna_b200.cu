@@ -534,6 +534,10 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters, doub
 }
 
 // ---- shell-quartet engine launch wrapper -----------------------------------------------------------------------
+#ifndef TUNA_SHELL_REGS
+#define TUNA_SHELL_REGS 64
+#endif
+#define TUNA_SHELL_MINB(threads) (65536 / ((threads) * TUNA_SHELL_REGS))
 constexpr int SHELL_ITEMS_PER_GROUP = 4;   // a CTA work unit (= multi-GPU sharding unit) is 4 consecutive shell quartets per group
 
 template <int GG>
@@ -552,7 +556,7 @@ struct DevPolicy {
 // the current unit is copied into shared memory; the bra position of the unit's first item is found once by binary search,
 // the others by walking the per-bra prefix.
 template <int GG>
-__global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(const ShellJob* __restrict__ jobs, const long long* __restrict__ unit_prefix,
+__global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 128) ? GG : 128)) k_shell_jk(const ShellJob* __restrict__ jobs, const long long* __restrict__ unit_prefix,
                                                                      int njobs, ShellData D, int nD, const double* __restrict__ Pf,
                                                                      const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
                                                                      double tau, const unsigned long long* scalars, double* evaluated,
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk(const ShellJ
 // Single-job variant: the job descriptor travels as a kernel parameter (constant bank / uniform registers instead of shared
 // memory), which is ~25 % faster per quartet; used for class jobs large enough to fill the GPU on their own.
 template <int GG>
-__global__ void __launch_bounds__((GG > 128) ? GG : 128) k_shell_jk_one(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
+__global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 128) ? GG : 128)) k_shell_jk_one(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
                                                                          const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
                                                                          double tau, const unsigned long long* scalars, double* evaluated,
                                                                          int rank, int nranks) {
