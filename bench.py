@@ -3,8 +3,9 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload direct:et400|stored:n2_ccpvtz|...]
 
-Headline workload (BASELINE.json configs[4], the one the metric's "1/2/4/8 B200 ... % FP64 peak" is quoted on): the
-synthetic even-tempered N2 diatomic at nbf=400 (ncart 524), direct ERI + J/K, one density.  A "step" is one Fock build:
+Headline workload (BASELINE.json configs[4], the one the metric's "1/2/4/8 B200 ... % FP64 peak" is quoted on, at its largest
+point): the synthetic even-tempered N2 diatomic at nbf=800 (ncart 1102), direct ERI + J/K, one density.  The other sweep
+points (nbf 100/200/400) are measured at N=1 in the same run and reported under "sweep".  A "step" is one Fock build:
 every parity-surviving unique AO quartet is evaluated (Schwarz-screened) and folded into J and K.  At N GPUs the quartet
 list is sharded over ranks (strong scaling) and the partial J/K are summed by one NCCL all-reduce inside the timed region.
 The stored-ERI configuration (configs[1], N2 RHF/cc-pVTZ) is measured in the same run at N=1 and reported under "stored".
@@ -332,6 +333,29 @@ def bench_stored(torch, wl, steps, warmup, device):
     return res, ctx
 
 
+def sweep_point(torch, nbf, tau, fp64_peak, device):
+    """One extra point of the even-tempered sweep at N=1: device-resident direct Fock builds, CUDA-event timed."""
+    import tuna_b200
+    from tuna_b200.basis import flatten
+    from tuna_b200.distributed import FockBuilder
+    wl = load_workload(f"direct:et{nbf}")
+    ctx = tuna_b200.Context(device)
+    ctx.set_basis(*flatten(wl["bfs"]))
+    ctx.set_transform(wl["U"])
+    fb = FockBuilder(ctx, nD=1, tau=tau)
+    fb.dP.copy_(torch.from_numpy(tuna_b200.workloads.fixed_density(wl["nbf"])[None]))
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    steps = 10
+    ms = time_steps(torch, fb.stream, fb.build_device, steps, 3, flush)
+    alg_eri, alg_digest = ctx.algorithmic_flops()
+    c = ctx.counts()
+    out = {"nbf": wl["nbf"], "ncart": wl["ncart"], "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+           "eri_quartets_per_s": c["evaluated_last_direct"] * steps / (ms * 1e-3),
+           "fp64_frac_algorithmic": (alg_eri + alg_digest) / (ms / steps * 1e-3) / 1e12 / fp64_peak if fp64_peak else None}
+    ctx.set_stream(0)
+    return out
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -436,6 +460,7 @@ def run_ours(args, wl):
             sres, sctx = bench_stored(torch, swl, max(args.steps, 20), max(args.warmup, 3), local)
             sres["cpu_baseline"] = cpu_reference(swl)
             line["stored"] = sres
+            line["sweep"] = [sweep_point(torch, nb, args.tau, fp64_peak, local) for nb in (100, 200, 400) if f"et{nb}" != wl["name"]]
     print(json.dumps(line), flush=True)
     if ddist is not None:
         ddist.destroy_process_group()
@@ -447,9 +472,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("TUNA_BENCH_WORKLOAD", "direct:et400"))
+    ap.add_argument("--workload", default=os.environ.get("TUNA_BENCH_WORKLOAD", "direct:et800"))
     ap.add_argument("--tau", type=float, default=1e-16)
-    ap.add_argument("--no-stored", action="store_true", help="skip the extra stored-mode (configs[1]) measurement at N=1")
+    ap.add_argument("--no-stored", action="store_true", help="skip the extra stored-mode (configs[1]) and sweep measurements at N=1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = load_workload(args.workload)
