@@ -187,7 +187,8 @@ struct ClassTablesHost {
     int nout = 0, nk = 0, itmax = 0, smax_rows = 0, nint = 0;
     std::vector<int> chunk_bz0, chunk_e0, chunk_s0, bz_list;
     std::vector<unsigned> p4, p5ptr, p5term, p5off, t_rt, t_xy, t_u, t_s;
-    std::vector<unsigned short> pmap, omap;
+    std::vector<unsigned short> pmap, omap, jst_list;
+    std::vector<unsigned> jst_ptr, jflush;
     long long allowed = 0;            // parity-allowed component quartets = integrals per shell quartet
     double uniq[6] = {0, 0, 0, 0, 0, 0};   // unique AO quartets a shell quartet stands for: [0] generic, [1] A==B, [2] C==D,
                                            // [3] A==B and C==D, [4] AB==CD (A!=B), [5] all four shells equal
@@ -202,27 +203,49 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
     C.La = La; C.Lb = Lb; C.Lc = Lc; C.Ld = Ld;
     const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = Ltot / 2 + 1, NGZ = (Lc + 1) * (Ld + 1);
     const int ncA = T.nc[La], ncB = T.nc[Lb], ncC = T.nc[Lc], ncD = T.nc[Ld];
-    // output blocks KAC KAD KBC KBD JAB JCD and staged density blocks PDB PCB PDA PCA PCD(sym) PAB(sym)
-    const int ob[7] = {0, ncA * ncC, ncA * ncC + ncA * ncD, ncA * ncC + ncA * ncD + ncB * ncC, ncA * ncC + ncA * ncD + ncB * ncC + ncB * ncD,
-                       ncA * ncC + ncA * ncD + ncB * ncC + ncB * ncD + ncA * ncB, 0};
-    C.nout = ob[5] + ncC * ncD;
+    // K: output blocks KAC KAD KBC KBD and staged density blocks PDB PCB PDA PCA, one entry per component pair.
+    // J: accumulated per bra / ket PAIR FUNCTION (ax+bx, ay+by, az, bz): accumulators Jb[beta], Jg[gamma] and staged
+    //    symmetrised densities Pg[gamma] = sum_{(c,d)->gamma} Psym[c][d], Pb[beta] = sum_{(a,b)->beta} Psym[a][b].
+    const int ob[5] = {0, ncA * ncC, ncA * ncC + ncA * ncD, ncA * ncC + ncA * ncD + ncB * ncC, ncA * ncC + ncA * ncD + ncB * ncC + ncB * ncD};
     C.nk = ob[4];
-    const int pb[6] = {0, ncD * ncB, ncD * ncB + ncC * ncB, ncD * ncB + ncC * ncB + ncD * ncA, ncD * ncB + ncC * ncB + ncD * ncA + ncC * ncA,
-                       ncD * ncB + ncC * ncB + ncD * ncA + ncC * ncA + ncC * ncD};
-    auto rc = [](int rsel, int r, int csel, int c, bool sym) { return (unsigned short)((rsel << 5) | r | ((csel << 5 | c) << 8) | (sym ? 0x8000 : 0)); };
-    C.omap.assign(C.nout, 0); C.pmap.assign(C.nout, 0);
-    for (int a = 0; a < ncA; ++a) for (int c = 0; c < ncC; ++c) C.omap[ob[0] + a * ncC + c] = rc(0, a, 2, c, false);
-    for (int a = 0; a < ncA; ++a) for (int d = 0; d < ncD; ++d) C.omap[ob[1] + a * ncD + d] = rc(0, a, 3, d, false);
-    for (int b = 0; b < ncB; ++b) for (int c = 0; c < ncC; ++c) C.omap[ob[2] + b * ncC + c] = rc(1, b, 2, c, false);
-    for (int b = 0; b < ncB; ++b) for (int d = 0; d < ncD; ++d) C.omap[ob[3] + b * ncD + d] = rc(1, b, 3, d, false);
-    for (int a = 0; a < ncA; ++a) for (int b = 0; b < ncB; ++b) C.omap[ob[4] + a * ncB + b] = rc(0, a, 1, b, false);
-    for (int c = 0; c < ncC; ++c) for (int d = 0; d < ncD; ++d) C.omap[ob[5] + c * ncD + d] = rc(2, c, 3, d, false);
-    for (int d = 0; d < ncD; ++d) for (int b = 0; b < ncB; ++b) C.pmap[pb[0] + d * ncB + b] = rc(3, d, 1, b, false);
-    for (int c = 0; c < ncC; ++c) for (int b = 0; b < ncB; ++b) C.pmap[pb[1] + c * ncB + b] = rc(2, c, 1, b, false);
-    for (int d = 0; d < ncD; ++d) for (int a = 0; a < ncA; ++a) C.pmap[pb[2] + d * ncA + a] = rc(3, d, 0, a, false);
-    for (int c = 0; c < ncC; ++c) for (int a = 0; a < ncA; ++a) C.pmap[pb[3] + c * ncA + a] = rc(2, c, 0, a, false);
-    for (int c = 0; c < ncC; ++c) for (int d = 0; d < ncD; ++d) C.pmap[pb[4] + c * ncD + d] = rc(2, c, 3, d, true);
-    for (int a = 0; a < ncA; ++a) for (int b = 0; b < ncB; ++b) C.pmap[pb[5] + a * ncB + b] = rc(0, a, 1, b, true);
+    const int pb[4] = {0, ncD * ncB, ncD * ncB + ncC * ncB, ncD * ncB + ncC * ncB + ncD * ncA};
+    auto rc = [](int rsel, int r, int csel, int c) { return (unsigned short)((rsel << 5) | r | ((csel << 5 | c) << 8)); };
+    std::map<std::tuple<int, int, int, int>, int> beta_of, gamma_of;          // (nx, ny, z1, z2) -> pair-function index
+    std::vector<int> bidx(ncA * ncB), gidx(ncC * ncD);
+    for (int a = 0; a < ncA; ++a)
+        for (int b = 0; b < ncB; ++b) {
+            auto key = std::make_tuple(T.lx[La][a] + T.lx[Lb][b], T.ly[La][a] + T.ly[Lb][b], T.lz[La][a], T.lz[Lb][b]);
+            auto it = beta_of.find(key);
+            if (it == beta_of.end()) it = beta_of.emplace(key, (int)beta_of.size()).first;
+            bidx[a * ncB + b] = it->second;
+        }
+    for (int c = 0; c < ncC; ++c)
+        for (int d = 0; d < ncD; ++d) {
+            auto key = std::make_tuple(T.lx[Lc][c] + T.lx[Ld][d], T.ly[Lc][c] + T.ly[Ld][d], T.lz[Lc][c], T.lz[Ld][d]);
+            auto it = gamma_of.find(key);
+            if (it == gamma_of.end()) it = gamma_of.emplace(key, (int)gamma_of.size()).first;
+            gidx[c * ncD + d] = it->second;
+        }
+    const int nbeta = (int)beta_of.size(), ngamma = (int)gamma_of.size();
+    // accumulator ids (before sorting): [0, nk) K entries, [nk, nk+nbeta) Jb, [nk+nbeta, nk+nbeta+ngamma) Jg
+    // staged density ids:               [0, nk) K entries, [nk, nk+ngamma) Pg, [nk+ngamma, nk+ngamma+nbeta) Pb
+    C.nout = C.nk + nbeta + ngamma;
+    C.omap.assign(C.nout, 0xffff); C.pmap.assign(C.nk, 0);
+    for (int a = 0; a < ncA; ++a) for (int c = 0; c < ncC; ++c) C.omap[ob[0] + a * ncC + c] = rc(0, a, 2, c);
+    for (int a = 0; a < ncA; ++a) for (int d = 0; d < ncD; ++d) C.omap[ob[1] + a * ncD + d] = rc(0, a, 3, d);
+    for (int b = 0; b < ncB; ++b) for (int c = 0; c < ncC; ++c) C.omap[ob[2] + b * ncC + c] = rc(1, b, 2, c);
+    for (int b = 0; b < ncB; ++b) for (int d = 0; d < ncD; ++d) C.omap[ob[3] + b * ncD + d] = rc(1, b, 3, d);
+    for (int d = 0; d < ncD; ++d) for (int b = 0; b < ncB; ++b) C.pmap[pb[0] + d * ncB + b] = rc(3, d, 1, b);
+    for (int c = 0; c < ncC; ++c) for (int b = 0; b < ncB; ++b) C.pmap[pb[1] + c * ncB + b] = rc(2, c, 1, b);
+    for (int d = 0; d < ncD; ++d) for (int a = 0; a < ncA; ++a) C.pmap[pb[2] + d * ncA + a] = rc(3, d, 0, a);
+    for (int c = 0; c < ncC; ++c) for (int a = 0; a < ncA; ++a) C.pmap[pb[3] + c * ncA + a] = rc(2, c, 0, a);
+    {   // staging CSR of the pair-function densities: first the gammas, then the betas
+        std::vector<std::vector<unsigned short>> lists(ngamma + nbeta);
+        for (int c = 0; c < ncC; ++c) for (int d = 0; d < ncD; ++d) lists[gidx[c * ncD + d]].push_back(rc(2, c, 3, d));
+        for (int a = 0; a < ncA; ++a) for (int b = 0; b < ncB; ++b) lists[ngamma + bidx[a * ncB + b]].push_back(rc(0, a, 1, b));
+        C.jst_ptr.push_back(0);
+        for (auto& l : lists) { C.jst_list.insert(C.jst_list.end(), l.begin(), l.end()); C.jst_ptr.push_back((unsigned)C.jst_list.size()); }
+    }
 
     // phase 1-2 work lists
     for (int w = 0; w <= Ltot; ++w)
@@ -365,22 +388,43 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
         }
         std::copy(np4.begin(), np4.end(), C.p4.begin() + 2 * (size_t)e0);
     }
-    // phase 5: CSR over outputs per chunk; outputs ordered by descending total number of terms (same order in every chunk)
+    // phase 5: CSR over accumulators per chunk; accumulators ordered by descending total number of terms (same order in every chunk)
+    // distinct pair-function quartets of every chunk with their (beta, gamma) indices, for the J terms
+    struct PFQ { int slot, beta, gamma; };
+    std::vector<std::vector<PFQ>> pfq(nchunk);
+    {
+        std::map<long long, int> seen;
+        for (int ch = 0; ch < nchunk; ++ch)
+            for (int bi = C.chunk_bz0[ch]; bi < C.chunk_bz0[ch + 1]; ++bi)
+                for (const Quartet& q : per_bz[bi]) {
+                    const long long key = pf_key(bi, q);
+                    if (seen.count(key)) continue;
+                    seen[key] = 1;
+                    pfq[ch].push_back({slot_perm[C.chunk_e0[ch] + slot_of[key]], bidx[q.a * ncB + q.b], gidx[q.c * ncD + q.d]});
+                }
+    }
     std::vector<long long> tot_terms(C.nout, 0);
     for (const auto& v : per_bz)
         for (const Quartet& q : v) {
             ++tot_terms[ob[0] + q.a * ncC + q.c]; ++tot_terms[ob[1] + q.a * ncD + q.d]; ++tot_terms[ob[2] + q.b * ncC + q.c];
-            ++tot_terms[ob[3] + q.b * ncD + q.d]; ++tot_terms[ob[4] + q.a * ncB + q.b]; ++tot_terms[ob[5] + q.c * ncD + q.d];
+            ++tot_terms[ob[3] + q.b * ncD + q.d];
         }
-    std::vector<int> oorder(C.nout), opos(C.nout);       // new position -> old output id, and the inverse
+    for (const auto& v : pfq)
+        for (const PFQ& f : v) { ++tot_terms[C.nk + f.beta]; ++tot_terms[C.nk + nbeta + f.gamma]; }
+    std::vector<int> oorder(C.nout), opos(C.nout);       // new position -> old accumulator id, and the inverse
     for (int o = 0; o < C.nout; ++o) oorder[o] = o;
     std::stable_sort(oorder.begin(), oorder.end(), [&](int x, int y) { return tot_terms[x] > tot_terms[y]; });
     for (int k = 0; k < C.nout; ++k) opos[oorder[k]] = k;
     {
         std::vector<unsigned short> nomap(C.nout);
-        for (int k = 0; k < C.nout; ++k) nomap[k] = (unsigned short)(C.omap[oorder[k]] | (oorder[k] >= C.nk ? 0x8000 : 0));    // bit 15: J entry
+        for (int k = 0; k < C.nout; ++k) nomap[k] = C.omap[oorder[k]];
         C.omap.swap(nomap);
     }
+    // J flush list: every component pair reads its pair-function accumulator
+    for (int a = 0; a < ncA; ++a)
+        for (int b = 0; b < ncB; ++b) C.jflush.push_back((unsigned)rc(0, a, 1, b) | (unsigned)opos[C.nk + bidx[a * ncB + b]] << 16);
+    for (int c = 0; c < ncC; ++c)
+        for (int d = 0; d < ncD; ++d) C.jflush.push_back((unsigned)rc(2, c, 3, d) | (unsigned)opos[C.nk + nbeta + gidx[c * ncD + d]] << 16);
     for (int ch = 0; ch < nchunk; ++ch) {
         std::vector<std::vector<unsigned>> terms(C.nout);
         for (int bi = C.chunk_bz0[ch]; bi < C.chunk_bz0[ch + 1]; ++bi)
@@ -390,9 +434,11 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
                 terms[opos[ob[1] + q.a * ncD + q.d]].push_back(it | (unsigned)(pb[1] + q.c * ncB + q.b) << 16);   // KAD += I P[c][b]
                 terms[opos[ob[2] + q.b * ncC + q.c]].push_back(it | (unsigned)(pb[2] + q.d * ncA + q.a) << 16);   // KBC += I P[d][a]
                 terms[opos[ob[3] + q.b * ncD + q.d]].push_back(it | (unsigned)(pb[3] + q.c * ncA + q.a) << 16);   // KBD += I P[c][a]
-                terms[opos[ob[4] + q.a * ncB + q.b]].push_back(it | (unsigned)(pb[4] + q.c * ncD + q.d) << 16);   // JAB += I (P[c][d]+P[d][c])
-                terms[opos[ob[5] + q.c * ncD + q.d]].push_back(it | (unsigned)(pb[5] + q.a * ncB + q.b) << 16);   // JCD += I (P[a][b]+P[b][a])
             }
+        for (const PFQ& f : pfq[ch]) {
+            terms[opos[C.nk + f.beta]].push_back((unsigned)f.slot | (unsigned)(C.nk + f.gamma) << 16);                    // Jb[beta]  += I Pg[gamma]
+            terms[opos[C.nk + nbeta + f.gamma]].push_back((unsigned)f.slot | (unsigned)(C.nk + ngamma + f.beta) << 16);   // Jg[gamma] += I Pb[beta]
+        }
         C.p5off.push_back((unsigned)C.p5term.size());       // multiple of 4: 16-byte aligned uint4 loads
         unsigned run = 0;                                   // in units of four terms
         for (int o = 0; o < C.nout; ++o) {
@@ -413,6 +459,8 @@ inline ClassTablesDev class_tables_view(const ClassTablesHost& C, PtrOf ptr) {
     V.chunk_bz0 = ptr(C.chunk_bz0); V.chunk_e0 = ptr(C.chunk_e0); V.chunk_s0 = ptr(C.chunk_s0);
     V.p4 = ptr(C.p4); V.p5ptr = ptr(C.p5ptr); V.p5term = ptr(C.p5term); V.p5off = ptr(C.p5off);
     V.pmap = ptr(C.pmap); V.omap = ptr(C.omap);
+    V.njst = (int)C.jst_ptr.size() - 1; V.njfl = (int)C.jflush.size();
+    V.jst_ptr = ptr(C.jst_ptr); V.jst_list = ptr(C.jst_list); V.jflush = ptr(C.jflush);
     V.n_rt = (int)C.t_rt.size(); V.n_xy = (int)C.t_xy.size(); V.n_u = (int)C.t_u.size() / 2;
     V.t_rt = ptr(C.t_rt); V.t_xy = ptr(C.t_xy); V.t_u = ptr(C.t_u); V.t_s = ptr(C.t_s);
     return V;

@@ -65,7 +65,8 @@ TUNA_HD int sp_rec_size(int La, int Lb) { return SP_HDR + sp_ez_size(La, Lb) + s
 //   buffer fit the shared-memory budget).  Phase-4 entry of integral e (2 words):
 //     w0 = xoff | yoff << 16          offsets of the XY rows of the x and y index pairs
 //     w1 = soff | mx0<<16 | mx1<<20 | my0<<24 | my1<<28   S row offset inside the chunk slice and the m / m' ranges
-//   Phase 5 is a CSR per chunk over the NOUT output entries (six blocks KAC,KAD,KBC,KBD,JAB,JCD, in that order):
+//   Phase 5 is a CSR per chunk over the NOUT accumulators (K blocks KAC,KAD,KBC,KBD per component, J per bra / ket pair
+//   function; sorted by work):
 //     term = it_index_in_chunk | pstage_index << 16
 //   The staged density blocks (same sizes/order: P[d][b], P[c][b], P[d][a], P[c][a], P[c][d]+P[d][c], P[a][b]+P[b][a])
 //   and the output blocks are addressed through `pmap` / `omap`: row | col << 8 with row/col = shell_sel << 5 | component.
@@ -77,9 +78,16 @@ struct ClassTablesDev {
     const unsigned* p5ptr;                  // [nchunk * (nout + 1)]
     const unsigned* p5term;                 // concatenated; chunk c starts at p5off[c]
     const unsigned* p5off;                  // [nchunk]
-    const unsigned short* pmap;             // [nout]  staged density entry -> (row, col), high bit 15 = symmetrise
-    const unsigned short* omap;             // [nout]  output entry -> (row, col); bit 15 set = J entry, else K (outputs sorted by work)
-    int nk;                                 // number of K outputs (first nk entries of the output list)
+    const unsigned short* pmap;             // [nk]    staged K density entry -> (row, col)
+    const unsigned short* omap;             // [nout]  accumulator -> (row, col) of its K entry, or 0xffff for a J pair-function accumulator
+    int nk;                                 // number of K density entries: Pst[0..nk) are single-element gathers through pmap
+    // J in pair-function space: component pairs (a,b) with equal (ax+bx, ay+by, az, bz) share one integral row, so the Coulomb
+    // part is accumulated per pair function and expanded to components only at the flush.
+    //   Pst[nk + i], i < njst : sum of the symmetrised density over the component pairs of pair function i
+    //                           (jst_ptr/jst_list CSR; list entry = row | col << 8 like pmap)
+    //   jflush[i], i < njfl   : (row | col << 8) | accumulator position << 16 : Jf[row][col] += Out[position]
+    int njst, njfl;
+    const unsigned* jst_ptr; const unsigned short* jst_list; const unsigned* jflush;
     // phases 1-3 as flat work lists (no per-entry index arithmetic on the device):
     //   t_rt[i]  = (w * NS + n) | w << 16 | n << 24                                   R^n_w entries with 2n + w <= Ltot
     //   t_xy[i]  = ((n12 (Lcd+1) + n34) NS + m) | n12 << 16 | n34 << 20 | m << 24     non-zero XY entries
@@ -191,12 +199,21 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
         // stage the six density blocks and clear the output blocks
         for (int dn = 0; dn < nD; ++dn) {
             const double* P = Pf + dn * nn;
-            TUNA_LANES(x, nout) {
+            TUNA_LANES(x, CT.nk) {
                 const unsigned m = CT.pmap[x];
                 const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
-                Pst[dn * nout + x] = ((m & 0x8000u) ? Psym + dn * nn : P)[(size_t)r * ncart + c];
-                Out[dn * nout + x] = 0.0;
+                Pst[dn * nout + x] = P[(size_t)r * ncart + c];
             }
+            const double* Ps = Psym + dn * nn;
+            TUNA_LANES(x, CT.njst) {
+                double v = 0.0;
+                for (unsigned t = CT.jst_ptr[x]; t < CT.jst_ptr[x + 1]; ++t) {
+                    const unsigned m = CT.jst_list[t];
+                    v += Ps[(size_t)ao[((m >> 5) & 3) * aos + (m & 31)] * ncart + ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)]];
+                }
+                Pst[dn * nout + CT.nk + x] = v;
+            }
+            TUNA_LANES(x, nout) Out[dn * nout + x] = 0.0;
         }
     }
     const int recAsz = sp_rec_size(La, Lb), recCsz = sp_rec_size(Lc, Ld);
@@ -326,9 +343,14 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
         for (int dn = 0; dn < nD; ++dn) {
             TUNA_LANES(x, nout) {
                 const unsigned m = CT.omap[x];
+                if (m == 0xffffu) continue;                    // J pair-function accumulator: expanded below
                 const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
-                double* dst = ((m & 0x8000u) ? Jf : Kf) + dn * nn + (size_t)r * ncart + c;
-                Pol::atomic_add(dst, Out[dn * nout + x]);
+                Pol::atomic_add(Kf + dn * nn + (size_t)r * ncart + c, Out[dn * nout + x]);
+            }
+            TUNA_LANES(x, CT.njfl) {
+                const unsigned e = CT.jflush[x], m = e & 0xffffu;
+                const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
+                Pol::atomic_add(Jf + dn * nn + (size_t)r * ncart + c, Out[dn * nout + (e >> 16)]);
             }
         }
     }

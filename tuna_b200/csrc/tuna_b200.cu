@@ -1290,6 +1290,7 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
     const size_t o_off = add(C.p5off.data(), C.p5off.size() * 4), o_pmap = add(C.pmap.data(), C.pmap.size() * 2);
     const size_t o_omap = add(C.omap.data(), C.omap.size() * 2), o_rt = add(C.t_rt.data(), C.t_rt.size() * 4);
     const size_t o_xy = add(C.t_xy.data(), C.t_xy.size() * 4), o_u = add(C.t_u.data(), C.t_u.size() * 4), o_s = add(C.t_s.data(), C.t_s.size() * 4);
+    const size_t o_jp = add(C.jst_ptr.data(), C.jst_ptr.size() * 4), o_jl = add(C.jst_list.data(), C.jst_list.size() * 2), o_jf = add(C.jflush.data(), C.jflush.size() * 4);
     std::vector<unsigned char> host(total, 0);
     for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
     int rc;
@@ -1304,6 +1305,8 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
     V.p5off = (const unsigned*)(E.blob + o_off); V.pmap = (const unsigned short*)(E.blob + o_pmap); V.omap = (const unsigned short*)(E.blob + o_omap);
     V.t_rt = (const unsigned*)(E.blob + o_rt); V.t_xy = (const unsigned*)(E.blob + o_xy); V.t_u = (const unsigned*)(E.blob + o_u);
     V.t_s = (const unsigned*)(E.blob + o_s);
+    V.njst = (int)C.jst_ptr.size() - 1; V.njfl = (int)C.jflush.size();
+    V.jst_ptr = (const unsigned*)(E.blob + o_jp); V.jst_list = (const unsigned short*)(E.blob + o_jl); V.jflush = (const unsigned*)(E.blob + o_jf);
     *out = &E;
     return TUNA_OK;
 }
