@@ -127,7 +127,19 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
             if (eb) build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH, atoi(eb), atoi(eb)); else build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH);
             J.ct = class_tables_view(CTH, HostPtrOf());
             shell_job_layout(J, nD);
-            std::vector<double> sm(J.total);
+            const char* enb = getenv("TUNA_EMUL_NB");             // quartets batched per group (1 or 2)
+            const int NBATCH = enb ? atoi(enb) : 2;
+            std::vector<double> sm((size_t)2 * J.total);
+            bool act[2] = {false, false};
+            int ABs[2] = {0, 0}, CDs[2] = {0, 0}, nb = 0;
+            double ws[2] = {0.0, 0.0};
+            auto run_batch = [&]() {
+                if (nb == 0) return;
+                if (NBATCH == 2) shell_quartets<HostPolicy, 2>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                else shell_quartets<HostPolicy, 1>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                act[0] = act[1] = false;
+                nb = 0;
+            };
             for (long long item = 0; item < J.nitems; ++item) {
                 int ib, ik;
                 shell_item_decode(J, item, ib, ik);
@@ -137,8 +149,10 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
                 if (S.pairA[AB] == S.pairB[AB]) w *= 0.5;
                 if (S.pairA[CD] == S.pairB[CD]) w *= 0.5;
                 if (AB == CD) w *= 0.5;
-                shell_quartet<HostPolicy>(J, D, true, AB, CD, w, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                act[nb] = true; ABs[nb] = AB; CDs[nb] = CD; ws[nb] = w;
+                if (++nb == NBATCH) run_batch();
             }
+            run_batch();
             nitems_total += J.nitems;
         }
     for (int d = 0; d < nD; ++d)

@@ -172,48 +172,74 @@ TUNA_HD double boys_single(const double* __restrict__ tab, int m, double T) {
 
 #define TUNA_LANES(i, n) for (int i = Pol::lane(); i < (n); i += Pol::G)
 
-// One shell quartet (pair ids AB, CD; degeneracy weight w) folded into the global accumulators Jf, Kf
-// (nD matrices of ncart x ncart each) for densities Pf.  `sm` is this group's private shared-memory slice.
-// `active` = false groups only take part in the barriers.
-template <class Pol>
-TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, int AB, int CD, double w, double* __restrict__ sm,
-                           int nD, const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf, double* Kf, int ncart) {
+// NB shell quartets of the same class (pair ids AB[], CD[]; degeneracy weights w[]) processed TOGETHER by one group and folded
+// into the global accumulators Jf, Kf (nD matrices of ncart x ncart each) for densities Pf.  Batching NB quartets amortises
+// every table-entry decode, loop and barrier over NB independent FMA streams.  Quartet q uses the shared-memory slice
+// sm + q * J.total.  Quartets with active[q] == false only take part in the barriers.
+template <class Pol, int NB>
+TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* active, const int* AB, const int* CD, const double* w,
+                            double* __restrict__ sm, int nD, const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf,
+                            double* Kf, int ncart) {
     const ClassTablesDev& CT = J.ct;
     const int La = J.La, Lb = J.Lb, Lc = J.Lc, Ld = J.Ld;
     const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = J.NS, NGZ = J.NGZ;
     const int NTA = Lab / 2 + 1, NTC = Lcd / 2 + 1, nout = CT.nout;
     const size_t nn = (size_t)ncart * ncart;
-    double* B = sm + J.oB; double* pzt = sm + J.oPz; double* Rt = sm + J.oRt; double* XY = sm + J.oXY;
-    double* U = sm + J.oU; double* S = sm + J.oS; double* It = sm + J.oIt; double* Pst = sm + J.oP; double* Out = sm + J.oOut;
-    int* ao = reinterpret_cast<int*>(sm + J.oAO);          // [4][aostride]
-    const int aos = J.aostride;
+    const int tot = J.total, aos = J.aostride;
+    double* const Bq = sm + J.oB; double* const pzq = sm + J.oPz; double* const Rtq = sm + J.oRt; double* const XYq = sm + J.oXY;
+    double* const Uq = sm + J.oU; double* const Sq = sm + J.oS; double* const Itq = sm + J.oIt; double* const Pstq = sm + J.oP;
+    double* const Outq = sm + J.oOut;
+    int* const aoq = reinterpret_cast<int*>(sm + J.oAO);          // [4][aostride] per quartet; quartet q at + q * 2 * tot ints
 
-    const double* recA = nullptr; const double* recC = nullptr;
-    if (active) {
-        const int sh[4] = {D.pairA[AB], D.pairB[AB], D.pairA[CD], D.pairB[CD]};
-        recA = D.rec + D.pair_rec[AB]; recC = D.rec + D.pair_rec[CD];
+    const double* recA[NB]; const double* recC[NB];
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        recA[q] = nullptr; recC[q] = nullptr;
+        if (!active[q]) continue;
+        any = true;
+        const int sh[4] = {D.pairA[AB[q]], D.pairB[AB[q]], D.pairA[CD[q]], D.pairB[CD[q]]};
+        recA[q] = D.rec + D.pair_rec[AB[q]]; recC[q] = D.rec + D.pair_rec[CD[q]];
+        int* ao = aoq + q * 2 * tot;
         TUNA_LANES(x, 4 * aos) ao[x] = D.sh_ao[sh[x / aos] * SH_NCMAX + x % aos];
     }
     Pol::sync();
-    if (active && !(J.dbg_skip & 64)) {
-        // stage the six density blocks and clear the output blocks
+    if (any && !(J.dbg_skip & 64)) {
+        // stage the density blocks and clear the accumulators
         for (int dn = 0; dn < nD; ++dn) {
             const double* P = Pf + dn * nn;
+            const double* Ps = Psym + dn * nn;
             TUNA_LANES(x, CT.nk) {
                 const unsigned m = CT.pmap[x];
-                const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
-                Pst[dn * nout + x] = P[(size_t)r * ncart + c];
+                const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    if (!active[q]) continue;
+                    const int* ao = aoq + q * 2 * tot;
+                    Pstq[q * tot + dn * nout + x] = P[(size_t)ao[ri] * ncart + ao[ci]];
+                }
             }
-            const double* Ps = Psym + dn * nn;
             TUNA_LANES(x, CT.njst) {
-                double v = 0.0;
+                double v[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) v[q] = 0.0;
                 for (unsigned t = CT.jst_ptr[x]; t < CT.jst_ptr[x + 1]; ++t) {
                     const unsigned m = CT.jst_list[t];
-                    v += Ps[(size_t)ao[((m >> 5) & 3) * aos + (m & 31)] * ncart + ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)]];
+                    const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        if (!active[q]) continue;
+                        const int* ao = aoq + q * 2 * tot;
+                        v[q] += Ps[(size_t)ao[ri] * ncart + ao[ci]];
+                    }
                 }
-                Pst[dn * nout + CT.nk + x] = v;
+#pragma unroll
+                for (int q = 0; q < NB; ++q) Pstq[q * tot + dn * nout + CT.nk + x] = v[q];
             }
-            TUNA_LANES(x, nout) Out[dn * nout + x] = 0.0;
+            TUNA_LANES(x, nout) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) Outq[q * tot + dn * nout + x] = 0.0;
+            }
         }
     }
     const int recAsz = sp_rec_size(La, Lb), recCsz = sp_rec_size(Lc, Ld);
@@ -221,140 +247,199 @@ TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, i
 
     for (int ch = 0; ch < CT.nchunk; ++ch) {
         const int e0 = CT.chunk_e0[ch], ne = CT.chunk_e0[ch + 1] - e0;
-        if (active) {
-            TUNA_LANES(x, ne) It[x] = 0.0;
-            if (Pol::lane() == 0) It[CT.itmax] = 0.0;
+        if (any) {
+            TUNA_LANES(x, ne) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) Itq[q * tot + x] = 0.0;
+            }
+            if (Pol::lane() == 0) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) Itq[q * tot + CT.itmax] = 0.0;
+            }
         }
         for (int ia = 0; ia < J.nppAB; ++ia)
             for (int ic = 0; ic < J.nppCD; ++ic) {
-                const double* rA = recA + (size_t)ia * recAsz;
-                const double* rC = recC + (size_t)ic * recCsz;
-                double pref = 0.0;
+                const double* rA[NB]; const double* rC[NB];
+                double pref[NB];
                 // ---- phase 0: Boys values scaled by (-2 rho)^m, powers of PQz ---------------------------------
-                if (active && !(J.dbg_skip & 1)) {
-                    const double p = rA[0], q = rC[0], pq = p + q, rho = p * q / pq, PQz = rA[1] - rC[1];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    pref[q] = 0.0;
+                    rA[q] = recA[q] + (size_t)ia * recAsz;
+                    rC[q] = recC[q] + (size_t)ic * recCsz;
+                    if (!active[q] || (J.dbg_skip & 1)) continue;
+                    const double p = rA[q][0], qq = rC[q][0], pq = p + qq, rho = p * qq / pq, PQz = rA[q][1] - rC[q][1];
                     const double Targ = rho * PQz * PQz;
-                    pref = w * rA[2] * rC[2] * 34.986836655249725 / (p * q * sqrt(pq));
+                    pref[q] = w[q] * rA[q][2] * rC[q][2] * 34.986836655249725 / (p * qq * sqrt(pq));
                     TUNA_LANES(m, Ltot + 1) {
                         double f = boys_single(D.boys, m, Targ), s = 1.0, z = 1.0;
                         for (int k = 0; k < m; ++k) { s *= -2.0 * rho; z *= PQz; }
-                        B[m] = f * s;
-                        pzt[m] = z;
+                        Bq[q * tot + m] = f * s;
+                        pzq[q * tot + m] = z;
                     }
                 }
                 Pol::sync();
                 // ---- phase 1: R^n_w (closed form) and the x/y convolution table ----------------------------------
-                if (active && !(J.dbg_skip & 2)) {
+                if (any && !(J.dbg_skip & 2)) {
                     TUNA_LANES(i, CT.n_rt) {
                         const unsigned e = CT.t_rt[i];
                         const int wv = (e >> 16) & 255, n = e >> 24;
-                        double r = 0.0;
-                        for (int k = 0; 2 * k <= wv; ++k) r = fma(D.herm[wv * HERM_STRIDE + k] * pzt[wv - 2 * k], B[n + wv - k], r);
-                        Rt[e & 0xffffu] = r;
+                        double r[NB];
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) r[q] = 0.0;
+                        for (int k = 0; 2 * k <= wv; ++k) {
+                            const double h = D.herm[wv * HERM_STRIDE + k];
+#pragma unroll
+                            for (int q = 0; q < NB; ++q) r[q] = fma(h * pzq[q * tot + wv - 2 * k], Bq[q * tot + n + wv - k], r[q]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) Rtq[q * tot + (e & 0xffffu)] = r[q];
                     }
-                    const double* ExA = rA + oExA; const double* ExC = rC + oExC;
                     TUNA_LANES(i, CT.n_xy) {
                         const unsigned e = CT.t_xy[i];
                         const int n12 = (e >> 16) & 15, n34 = (e >> 20) & 15, m = e >> 24, px = n12 & 1;
                         const int tlo = (2 * m - n34 > px) ? 2 * m - n34 : px;
                         const int thi = (2 * m - px < n12) ? 2 * m - px : n12;
-                        double v = 0.0;
-                        for (int t = tlo; t <= thi; t += 2) v = fma(ExA[n12 * NTA + (t >> 1)], ExC[n34 * NTC + ((2 * m - t) >> 1)], v);
-                        v *= odd_dfact(m);
-                        XY[e & 0xffffu] = (n34 & 1) ? -v : v;
+                        const double df = (n34 & 1) ? -odd_dfact(m) : odd_dfact(m);
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            if (!active[q]) continue;
+                            const double* ExA = rA[q] + oExA; const double* ExC = rC[q] + oExC;
+                            double v = 0.0;
+                            for (int t = tlo; t <= thi; t += 2) v = fma(ExA[n12 * NTA + (t >> 1)], ExC[n34 * NTC + ((2 * m - t) >> 1)], v);
+                            XYq[q * tot + (e & 0xffffu)] = v * df;
+                        }
                     }
                 }
                 Pol::sync();
                 // ---- phase 2: U[v][gz][n] = sum_phi (-1)^phi Ez_CD[gz][phi] R^n_{v+phi} ---------------------------
-                if (active && !(J.dbg_skip & 4)) {
-                    const double* EzC = rC + SP_HDR;
+                if (any && !(J.dbg_skip & 4)) {
                     TUNA_LANES(i, CT.n_u) {
                         const unsigned e0w = CT.t_u[2 * i], e1w = CT.t_u[2 * i + 1];
-                        const double* e = EzC + (e1w & 0xffffu);
-                        const double* r = Rt + (e0w >> 16);
                         const int lz34 = e1w >> 16;
-                        double u = 0.0;
-                        for (int phi = 0; phi <= lz34; phi += 2) u = fma(e[phi], r[phi * NS], u);
-                        for (int phi = 1; phi <= lz34; phi += 2) u = fma(-e[phi], r[phi * NS], u);
-                        U[e0w & 0xffffu] = u;
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            if (!active[q]) continue;
+                            const double* e = rC[q] + SP_HDR + (e1w & 0xffffu);
+                            const double* r = Rtq + q * tot + (e0w >> 16);
+                            double u = 0.0;
+                            for (int phi = 0; phi <= lz34; phi += 2) u = fma(e[phi], r[phi * NS], u);
+                            for (int phi = 1; phi <= lz34; phi += 2) u = fma(-e[phi], r[phi * NS], u);
+                            Uq[q * tot + (e0w & 0xffffu)] = u;
+                        }
                     }
                 }
                 Pol::sync();
                 // ---- phase 3: S[row][gz][n] = sum_v Ez_AB[az][bz][v] U[v][gz][n] for the chunk's bra z rows ----------
-                if (active && !(J.dbg_skip & 8)) {
-                    const double* EzA = rA + SP_HDR;
+                if (any && !(J.dbg_skip & 8)) {
                     const int ustride = NGZ * NS;
                     for (int i = CT.chunk_s0[ch] + Pol::lane(); i < CT.chunk_s0[ch + 1]; i += Pol::G) {
                         const unsigned e0w = CT.t_s[2 * i], e1w = CT.t_s[2 * i + 1];
-                        const double* e = EzA + (e1w & 0xffffu);
-                        const double* u = U + (e0w >> 16);
                         const int lz12 = e1w >> 16;
-                        double sacc = 0.0;
-                        for (int v = 0; v <= lz12; ++v) sacc = fma(e[v], u[v * ustride], sacc);
-                        S[e0w & 0xffffu] = sacc;
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            if (!active[q]) continue;
+                            const double* e = rA[q] + SP_HDR + (e1w & 0xffffu);
+                            const double* u = Uq + q * tot + (e0w >> 16);
+                            double sacc = 0.0;
+                            for (int v = 0; v <= lz12; ++v) sacc = fma(e[v], u[v * ustride], sacc);
+                            Sq[q * tot + (e0w & 0xffffu)] = sacc;
+                        }
                     }
                 }
                 Pol::sync();
                 // ---- phase 4: table-driven integral assembly, accumulated over primitive quartets ----------------
-                if (active && !(J.dbg_skip & 16)) {
+                if (any && !(J.dbg_skip & 16)) {
                     const unsigned* p4 = CT.p4 + 2 * (size_t)e0;
                     TUNA_LANES(e, ne) {
                         const unsigned w0 = p4[2 * e], w1 = p4[2 * e + 1];
-                        const double* xr = XY + (w0 & 0xffffu);
-                        const double* yr = XY + (w0 >> 16);
-                        const double* sr = S + (w1 & 0xffffu);
+                        const int xo = w0 & 0xffffu, yo = w0 >> 16, so = w1 & 0xffffu;
                         const int mx0 = (w1 >> 16) & 15, mx1 = (w1 >> 20) & 15, my0 = (w1 >> 24) & 15, my1 = (w1 >> 28) & 15;
-                        double val = 0.0;
+                        double val[NB];
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) val[q] = 0.0;
                         for (int m = mx0; m <= mx1; ++m) {
-                            double t = 0.0;
-                            for (int mp = my0; mp <= my1; ++mp) t = fma(yr[mp], sr[m + mp], t);
-                            val = fma(xr[m], t, val);
+                            double t[NB];
+#pragma unroll
+                            for (int q = 0; q < NB; ++q) t[q] = 0.0;
+                            for (int mp = my0; mp <= my1; ++mp) {
+#pragma unroll
+                                for (int q = 0; q < NB; ++q) t[q] = fma(XYq[q * tot + yo + mp], Sq[q * tot + so + m + mp], t[q]);
+                            }
+#pragma unroll
+                            for (int q = 0; q < NB; ++q) val[q] = fma(XYq[q * tot + xo + m], t[q], val[q]);
                         }
-                        It[e] = fma(pref, val, It[e]);
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) Itq[q * tot + e] = fma(pref[q], val[q], Itq[q * tot + e]);
                     }
                 }
             }
         Pol::sync();
-        // ---- phase 5: table-driven digestion of the chunk: every output entry is owned by one lane.  Term lists are padded
+        // ---- phase 5: table-driven digestion of the chunk: every accumulator is owned by one lane.  Term lists are padded
         // to a multiple of four (dummy terms read the zero slot It[itmax]) so that one 16-byte load brings four terms.
-        if (active && !(J.dbg_skip & 32)) {
+        if (any && !(J.dbg_skip & 32)) {
             const unsigned* ptr = CT.p5ptr + (size_t)ch * (nout + 1);
             const uint4* term = reinterpret_cast<const uint4*>(CT.p5term + CT.p5off[ch]);
             TUNA_LANES(o, nout) {
                 const unsigned t0 = ptr[o], t1 = ptr[o + 1];        // in units of four terms
                 for (int dn = 0; dn < nD; ++dn) {
-                    const double* Pd = Pst + dn * nout;
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    double s0[NB], s1[NB];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) { s0[q] = 0.0; s1[q] = 0.0; }
                     for (unsigned t = t0; t < t1; ++t) {
-                        const uint4 q = term[t];
-                        s0 = fma(It[q.x & 0xffffu], Pd[q.x >> 16], s0);
-                        s1 = fma(It[q.y & 0xffffu], Pd[q.y >> 16], s1);
-                        s2 = fma(It[q.z & 0xffffu], Pd[q.z >> 16], s2);
-                        s3 = fma(It[q.w & 0xffffu], Pd[q.w >> 16], s3);
+                        const uint4 tq = term[t];
+                        const int i0 = tq.x & 0xffffu, p0 = dn * nout + (tq.x >> 16), i1 = tq.y & 0xffffu, p1 = dn * nout + (tq.y >> 16);
+                        const int i2 = tq.z & 0xffffu, p2 = dn * nout + (tq.z >> 16), i3 = tq.w & 0xffffu, p3 = dn * nout + (tq.w >> 16);
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            const double* It = Itq + q * tot; const double* Pd = Pstq + q * tot;
+                            s0[q] = fma(It[i0], Pd[p0], s0[q]);
+                            s1[q] = fma(It[i1], Pd[p1], s1[q]);
+                            s0[q] = fma(It[i2], Pd[p2], s0[q]);
+                            s1[q] = fma(It[i3], Pd[p3], s1[q]);
+                        }
                     }
-                    Out[dn * nout + o] += (s0 + s1) + (s2 + s3);
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) Outq[q * tot + dn * nout + o] += s0[q] + s1[q];
                 }
             }
         }
         Pol::sync();
     }
     // ---- flush the shell blocks: one atomic per block entry per shell quartet ---------------------------------------
-    if (active && !(J.dbg_skip & 128)) {
+    if (any && !(J.dbg_skip & 128)) {
         for (int dn = 0; dn < nD; ++dn) {
             TUNA_LANES(x, nout) {
                 const unsigned m = CT.omap[x];
                 if (m == 0xffffu) continue;                    // J pair-function accumulator: expanded below
-                const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
-                Pol::atomic_add(Kf + dn * nn + (size_t)r * ncart + c, Out[dn * nout + x]);
+                const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    if (!active[q]) continue;
+                    const int* ao = aoq + q * 2 * tot;
+                    Pol::atomic_add(Kf + dn * nn + (size_t)ao[ri] * ncart + ao[ci], Outq[q * tot + dn * nout + x]);
+                }
             }
             TUNA_LANES(x, CT.njfl) {
                 const unsigned e = CT.jflush[x], m = e & 0xffffu;
-                const int r = ao[((m >> 5) & 3) * aos + (m & 31)], c = ao[((m >> 13) & 3) * aos + ((m >> 8) & 31)];
-                Pol::atomic_add(Jf + dn * nn + (size_t)r * ncart + c, Out[dn * nout + (e >> 16)]);
+                const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    if (!active[q]) continue;
+                    const int* ao = aoq + q * 2 * tot;
+                    Pol::atomic_add(Jf + dn * nn + (size_t)ao[ri] * ncart + ao[ci], Outq[q * tot + dn * nout + (e >> 16)]);
+                }
             }
         }
     }
     Pol::sync();
+}
+
+// Single-quartet convenience wrapper.
+template <class Pol>
+TUNA_HD void shell_quartet(const ShellJob& J, const ShellData& D, bool active, int AB, int CD, double w, double* __restrict__ sm,
+                           int nD, const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf, double* Kf, int ncart) {
+    shell_quartets<Pol, 1>(J, D, &active, &AB, &CD, &w, sm, nD, Pf, Psym, Jf, Kf, ncart);
 }
 
 // item index -> (bra position, ket position) through the per-bra prefix of kept kets

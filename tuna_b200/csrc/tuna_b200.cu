@@ -89,11 +89,11 @@ struct tuna_ctx {
     int* d_sh_ao = nullptr; int* d_class_lists = nullptr; long long* d_prefix = nullptr; double* d_finv = nullptr;
     double* d_eval = nullptr;
     std::vector<size_t> class_list_off;
-    struct JobHost { ShellJob job; int G; size_t smem; double allowed; int threads, gpc; bool own_launch = false; };
+    struct JobHost { ShellJob job; int G; size_t smem; double allowed; int threads, gpc, nb = 1; bool own_launch = false; };
     struct ClassTabDev { ClassTablesHost host; ClassTablesDev view; unsigned char* blob = nullptr; };
     std::map<int, ClassTabDev> class_tabs;      // key La | Lb<<4 | Lc<<8 | Ld<<12
     std::vector<JobHost> jobs;
-    struct LaunchGroup { int G = 1, threads = 128, njobs = 0, ctas_per_sm = 1; long long nunits = 0; size_t smem = 0, job_slot_off = 0;
+    struct LaunchGroup { int G = 1, nb = 1, threads = 128, njobs = 0, ctas_per_sm = 1; long long nunits = 0; size_t smem = 0, job_slot_off = 0;
                          ShellJob* d_jobs = nullptr; long long* d_unit_prefix = nullptr; };
     std::vector<LaunchGroup> groups;      // one launch per group size G covers all class jobs with that G
     static constexpr int NAUX = 6;
@@ -555,7 +555,7 @@ struct DevPolicy {
 // walk with a grid stride; units are dealt round-robin to ranks (multi-GPU sharding).  The job descriptor of
 // the current unit is copied into shared memory; the bra position of the unit's first item is found once by binary search,
 // the others by walking the per-bra prefix.
-template <int GG>
+template <int GG, int NB>
 __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 128) ? GG : 128)) k_shell_jk(const ShellJob* __restrict__ jobs, const long long* __restrict__ unit_prefix,
                                                                      int njobs, ShellData D, int nD, const double* __restrict__ Pf,
                                                                      const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
@@ -590,24 +590,30 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 1
         }
         __syncthreads();
         const int ib0 = s_ib0;
-        double* sm = smem_all + (size_t)gid * J.total;
-        for (int k0 = 0; k0 < (int)CH; k0 += gpc) {
-            const long long item = first + k0 + gid;
-            bool active = (k0 + gid) < (int)CH && item < J.nitems;
-            int AB = 0, CD = 0;
-            double w = 1.0;
-            if (active) {
-                int ib = ib0;
-                while (J.item_prefix[ib + 1] <= item) ++ib;
-                AB = J.bra_list[ib]; CD = J.ket_list[(int)(item - J.item_prefix[ib])];
-                if (tau > 0.0 && D.pairQ[AB] * D.pairQ[CD] * dmax < tau) active = false;
-                const bool ab = D.pairA[AB] == D.pairB[AB], cd = D.pairA[CD] == D.pairB[CD], dg = AB == CD;
-                if (ab) w *= 0.5;
-                if (cd) w *= 0.5;
-                if (dg) w *= 0.5;
-                if (active && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+        double* sm = smem_all + (size_t)gid * NB * J.total;
+        for (int k0 = 0; k0 < (int)CH; k0 += gpc * NB) {
+            bool active[NB];
+            int AB[NB], CD[NB];
+            double w[NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const int kk = k0 + gid * NB + q;
+                const long long item = first + kk;
+                active[q] = kk < (int)CH && item < J.nitems;
+                AB[q] = 0; CD[q] = 0; w[q] = 1.0;
+                if (active[q]) {
+                    int ib = ib0;
+                    while (J.item_prefix[ib + 1] <= item) ++ib;
+                    AB[q] = J.bra_list[ib]; CD[q] = J.ket_list[(int)(item - J.item_prefix[ib])];
+                    if (tau > 0.0 && D.pairQ[AB[q]] * D.pairQ[CD[q]] * dmax < tau) active[q] = false;
+                    const bool ab = D.pairA[AB[q]] == D.pairB[AB[q]], cd = D.pairA[CD[q]] == D.pairB[CD[q]], dg = AB[q] == CD[q];
+                    if (ab) w[q] *= 0.5;
+                    if (cd) w[q] *= 0.5;
+                    if (dg) w[q] *= 0.5;
+                    if (active[q] && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+                }
             }
-            shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
+            shell_quartets<DevPolicy<GG>, NB>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
         }
     }
     if (done != 0.0) atomicAdd(evaluated, done);
@@ -615,15 +621,15 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 1
 
 // Single-job variant: the job descriptor travels as a kernel parameter (constant bank / uniform registers instead of shared
 // memory), which is ~25 % faster per quartet; used for class jobs large enough to fill the GPU on their own.
-template <int GG>
+template <int GG, int NB>
 __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 128) ? GG : 128)) k_shell_jk_one(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
                                                                          const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
                                                                          double tau, const unsigned long long* scalars, double* evaluated,
                                                                          int rank, int nranks) {
     extern __shared__ double smem_all[];
     const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
-    int& s_ib0 = *reinterpret_cast<int*>(smem_all + (size_t)gpc * J.total);
-    double* sm = smem_all + (size_t)gid * J.total;
+    int& s_ib0 = *reinterpret_cast<int*>(smem_all + (size_t)gpc * NB * J.total);
+    double* sm = smem_all + (size_t)gid * NB * J.total;
     const double dmax = __longlong_as_double((long long)scalars[0]);
     const long long CH = J.chunk;
     const long long nchunk = (J.nitems + CH - 1) / CH;
@@ -638,23 +644,29 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 1
         __syncthreads();
         const int ib0 = s_ib0;
         __syncthreads();
-        for (int k0 = 0; k0 < (int)CH; k0 += gpc) {
-            const long long item = first + k0 + gid;
-            bool active = (k0 + gid) < (int)CH && item < J.nitems;
-            int AB = 0, CD = 0;
-            double w = 1.0;
-            if (active) {
-                int ib = ib0;
-                while (J.item_prefix[ib + 1] <= item) ++ib;
-                AB = J.bra_list[ib]; CD = J.ket_list[(int)(item - J.item_prefix[ib])];
-                if (tau > 0.0 && D.pairQ[AB] * D.pairQ[CD] * dmax < tau) active = false;
-                const bool ab = D.pairA[AB] == D.pairB[AB], cd = D.pairA[CD] == D.pairB[CD], dg = AB == CD;
-                if (ab) w *= 0.5;
-                if (cd) w *= 0.5;
-                if (dg) w *= 0.5;
-                if (active && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+        for (int k0 = 0; k0 < (int)CH; k0 += gpc * NB) {
+            bool active[NB];
+            int AB[NB], CD[NB];
+            double w[NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const int kk = k0 + gid * NB + q;
+                const long long item = first + kk;
+                active[q] = kk < (int)CH && item < J.nitems;
+                AB[q] = 0; CD[q] = 0; w[q] = 1.0;
+                if (active[q]) {
+                    int ib = ib0;
+                    while (J.item_prefix[ib + 1] <= item) ++ib;
+                    AB[q] = J.bra_list[ib]; CD[q] = J.ket_list[(int)(item - J.item_prefix[ib])];
+                    if (tau > 0.0 && D.pairQ[AB[q]] * D.pairQ[CD[q]] * dmax < tau) active[q] = false;
+                    const bool ab = D.pairA[AB[q]] == D.pairB[AB[q]], cd = D.pairA[CD[q]] == D.pairB[CD[q]], dg = AB[q] == CD[q];
+                    if (ab) w[q] *= 0.5;
+                    if (cd) w[q] *= 0.5;
+                    if (dg) w[q] *= 0.5;
+                    if (active[q] && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+                }
             }
-            shell_quartet<DevPolicy<GG>>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
+            shell_quartets<DevPolicy<GG>, NB>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
         }
     }
     if (done != 0.0) atomicAdd(evaluated, done);
@@ -1382,15 +1394,19 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 shell_job_layout(J, nD);
                 jh.allowed = (double)ctd->host.allowed;
                 for (int u = 0; u < 6; ++u) J.uniq[u] = ctd->host.uniq[u];
+                // NB quartets are batched per group when two slices fit comfortably; the group size G follows the footprint
+                const char* env_nb = getenv("TUNA_B200_NB");
+                int nb = env_nb ? atoi(env_nb) : 2;
+                if ((size_t)2 * J.total * 8 > 96 * 1024) nb = 1;
                 int G = 1;
                 while (G < 256 && G * gdiv < jh.allowed) G *= 2;
-                while (G < 256 && (double)J.total * 8.0 / G > smem_per_lane) G *= 2;
-                while (G < 256 && (size_t)(G <= 32 ? 128 / G : 1) * J.total * 8 > 200 * 1024) G *= 2;
-                jh.G = G;
+                while (G < 256 && (double)nb * J.total * 8.0 / G > smem_per_lane) G *= 2;
+                while (G < 256 && (size_t)(G <= 32 ? 128 / G : 1) * nb * J.total * 8 > 200 * 1024) G *= 2;
+                jh.G = G; jh.nb = nb;
                 jh.threads = G <= 32 ? 128 : G;
                 jh.gpc = jh.threads / G;
                 J.chunk = jh.gpc * SHELL_ITEMS_PER_GROUP;
-                jh.smem = ((size_t)jh.gpc * J.total + 2) * sizeof(double);
+                jh.smem = ((size_t)jh.gpc * nb * J.total + 2) * sizeof(double);
                 if (jh.smem > 220 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 220 KB");
                 ctx->jobs.push_back(jh);
             }
@@ -1412,6 +1428,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
         }
         for (auto& g : ctx->groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
         ctx->groups.clear();
+        for (int nbv = 2; nbv >= 1; --nbv)
         for (int G = 256; G >= 1; G >>= 1)
             for (int bucket = 40; bucket >= 0; --bucket) {       // jobs of similar shared-memory footprint share a launch (occupancy)
                 std::vector<ShellJob> js;
@@ -1419,8 +1436,8 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 size_t max_slices = 0;
                 int threads = 128;
                 for (const auto& jh : ctx->jobs) {
-                    if (jh.G != G || jh.own_launch) continue;
-                    const size_t slices = (size_t)jh.gpc * jh.job.total;
+                    if (jh.G != G || jh.nb != nbv || jh.own_launch) continue;
+                    const size_t slices = (size_t)jh.gpc * jh.nb * jh.job.total;
                     int b = 0;
                     while (((size_t)1 << b) < slices) ++b;
                     b = 2 * b + (slices > ((size_t)3 << (b - 2)) ? 1 : 0);       // half-octave buckets
@@ -1432,7 +1449,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 }
                 if (js.empty()) continue;
                 tuna_ctx::LaunchGroup lg;
-                lg.G = G; lg.threads = threads; lg.njobs = (int)js.size(); lg.nunits = up.back();
+                lg.G = G; lg.nb = nbv; lg.threads = threads; lg.njobs = (int)js.size(); lg.nunits = up.back();
                 lg.job_slot_off = (max_slices + 1) & ~(size_t)1;
                 lg.smem = (lg.job_slot_off + (sizeof(ShellJob) + 7) / 8 + 2) * sizeof(double);
                 lg.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / lg.smem));
@@ -1448,30 +1465,30 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
     return TUNA_OK;
 }
 
-template <int GG>
+template <int GG, int NB>
 static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::LaunchGroup& lg, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                 double* Jf, double* Kf, double tau, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_shell_jk<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_shell_jk<GG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     long long blocks = (lg.nunits - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // units owned by this rank
     if (blocks <= 0) return cudaSuccess;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * lg.ctas_per_sm);
-    k_shell_jk<GG><<<(int)blocks, lg.threads, lg.smem, stream>>>(lg.d_jobs, lg.d_unit_prefix, lg.njobs, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau,
+    k_shell_jk<GG, NB><<<(int)blocks, lg.threads, lg.smem, stream>>>(lg.d_jobs, lg.d_unit_prefix, lg.njobs, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau,
                                                                  ctx->d_scalars, ctx->d_eval, ctx->shard_rank, ctx->shard_n, lg.job_slot_off);
     ctx->launches++;
     return cudaGetLastError();
 }
 
-template <int GG>
+template <int GG, int NB>
 static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                     double* Jf, double* Kf, double tau, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_shell_jk_one<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_shell_jk_one<GG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -1479,7 +1496,7 @@ static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, 
     long long blocks = (nchunk - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // chunks owned by this rank
     if (blocks <= 0) return cudaSuccess;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
-    k_shell_jk_one<GG><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
+    k_shell_jk_one<GG, NB><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
                                                                      ctx->shard_rank, ctx->shard_n);
     ctx->launches++;
     return cudaGetLastError();
@@ -1550,33 +1567,39 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
             if (!jh.own_launch) continue;
             cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
             cudaError_t e;
+#define TUNA_ONE(GV) (jh.nb == 2 ? launch_shell_one<GV, 2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
+                                   : launch_shell_one<GV, 1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st))
             switch (jh.G) {
-                case 1: e = launch_shell_one<1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 2: e = launch_shell_one<2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 4: e = launch_shell_one<4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 8: e = launch_shell_one<8>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 16: e = launch_shell_one<16>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 32: e = launch_shell_one<32>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 64: e = launch_shell_one<64>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 128: e = launch_shell_one<128>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                default: e = launch_shell_one<256>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 1: e = TUNA_ONE(1); break;
+                case 2: e = TUNA_ONE(2); break;
+                case 4: e = TUNA_ONE(4); break;
+                case 8: e = TUNA_ONE(8); break;
+                case 16: e = TUNA_ONE(16); break;
+                case 32: e = TUNA_ONE(32); break;
+                case 64: e = TUNA_ONE(64); break;
+                case 128: e = TUNA_ONE(128); break;
+                default: e = TUNA_ONE(256); break;
             }
+#undef TUNA_ONE
             if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk_one launch: ") + cudaGetErrorString(e));
         }
         for (const auto& lg : ctx->groups) {
             cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
             cudaError_t e;
+#define TUNA_GRP(GV) (lg.nb == 2 ? launch_shell<GV, 2>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
+                                   : launch_shell<GV, 1>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st))
             switch (lg.G) {
-                case 1: e = launch_shell<1>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 2: e = launch_shell<2>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 4: e = launch_shell<4>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 8: e = launch_shell<8>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 16: e = launch_shell<16>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 32: e = launch_shell<32>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 64: e = launch_shell<64>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                case 128: e = launch_shell<128>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
-                default: e = launch_shell<256>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st); break;
+                case 1: e = TUNA_GRP(1); break;
+                case 2: e = TUNA_GRP(2); break;
+                case 4: e = TUNA_GRP(4); break;
+                case 8: e = TUNA_GRP(8); break;
+                case 16: e = TUNA_GRP(16); break;
+                case 32: e = TUNA_GRP(32); break;
+                case 64: e = TUNA_GRP(64); break;
+                case 128: e = TUNA_GRP(128); break;
+                default: e = TUNA_GRP(256); break;
             }
+#undef TUNA_GRP
             if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk launch: ") + cudaGetErrorString(e));
         }
         for (int a = 0; a < tuna_ctx::NAUX; ++a) {
