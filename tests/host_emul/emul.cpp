@@ -127,17 +127,18 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
             if (eb) build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH, atoi(eb), atoi(eb)); else build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH);
             J.ct = class_tables_view(CTH, HostPtrOf());
             shell_job_layout(J, nD);
-            const char* enb = getenv("TUNA_EMUL_NB");             // quartets batched per group (1 or 2)
+            const char* enb = getenv("TUNA_EMUL_NB");             // quartets batched per group (1, 2 or 4)
             const int NBATCH = enb ? atoi(enb) : 2;
-            std::vector<double> sm((size_t)2 * J.total);
-            bool act[2] = {false, false};
-            int ABs[2] = {0, 0}, CDs[2] = {0, 0}, nb = 0;
-            double ws[2] = {0.0, 0.0};
+            std::vector<double> sm((size_t)4 * J.total);
+            bool act[4] = {false, false, false, false};
+            int ABs[4] = {0, 0, 0, 0}, CDs[4] = {0, 0, 0, 0}, nb = 0;
+            double ws[4] = {0.0, 0.0, 0.0, 0.0};
             auto run_batch = [&]() {
                 if (nb == 0) return;
-                if (NBATCH == 2) shell_quartets<HostPolicy, 2>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                if (NBATCH == 4) shell_quartets<HostPolicy, 4>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                else if (NBATCH == 2) shell_quartets<HostPolicy, 2>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
                 else shell_quartets<HostPolicy, 1>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
-                act[0] = act[1] = false;
+                act[0] = act[1] = act[2] = act[3] = false;
                 nb = 0;
             };
             for (long long item = 0; item < J.nitems; ++item) {

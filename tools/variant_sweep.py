@@ -1,0 +1,48 @@
+"""A/B timing of development builds of the shell engine (build/*.so, selected with TUNA_B200_LIB) and of its runtime knobs.
+Development aid: each child prints ms per direct build and two weighted checksums of J and K for a quick parity cross-check."""
+import json, os, subprocess, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    sys.path.insert(0, ROOT)
+    import tuna_b200
+    from tuna_b200 import workloads as w
+    from tuna_b200.basis import flatten, from_arrays
+    nbf = int(sys.argv[2])
+    b = w.even_tempered_diatomic(nbf)
+    bfs = from_arrays(b["origins"], b["lmn"], b["nprim"], b["exps"], b["raw_coefs"])
+    ctx = tuna_b200.Context(0)
+    ctx.set_basis(*flatten(bfs)); ctx.set_transform(np.eye(len(bfs)))
+    P = w.fixed_density(len(bfs))
+    best = 1e30
+    for _ in range(3):
+        J, K = ctx.jk_direct(P, 1e-16)
+        best = min(best, ctx.last_kernel_ms(3))
+    W = np.random.default_rng(5).standard_normal(J.shape[-2:])
+    print(json.dumps({"ms": best, "cj": float((np.asarray(J).reshape(W.shape) * W).sum()), "ck": float((np.asarray(K).reshape(W.shape) * W).sum()),
+                      "nj": float(np.abs(J).max()), "nk": float(np.abs(K).max())}))
+else:
+    sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [400, 800]
+    libs = {"base": "build/lib_base.so", "v2_r64": "build/lib_v2_r64.so", "v2_r96": "build/lib_v2_r96.so", "v2_r128": "build/lib_v2_r128.so", "v2_r48": "build/lib_v2_r48.so"}
+    NB4, NB4S, NB2L, NB1 = {"TUNA_B200_NB": "4"}, {"TUNA_B200_NB": "4", "TUNA_B200_NB_BYTES": "65536"}, {"TUNA_B200_NB": "2", "TUNA_B200_NB_BYTES": "200000"}, {"TUNA_B200_NB": "1"}
+    SPL192, SPL160 = {"TUNA_B200_SMEM_PER_LANE": "192"}, {"TUNA_B200_SMEM_PER_LANE": "160"}
+    combos = [("v2_r64", {}), ("v2_r64", SPL192), ("v2_r48", {}), ("v2_r48", SPL192), ("v2_r48", SPL160), ("v2_r48", dict(NB1, **SPL192)), ("v2_r48", dict(NB1, **SPL160))]
+    ref = {}
+    for nbf in sizes:
+        for name, env in combos:
+            lib = libs[name]
+            if not os.path.exists(os.path.join(ROOT, lib)):
+                continue
+            if True:
+                e = dict(os.environ, TUNA_B200_LIB=os.path.join(ROOT, lib), **env)
+                r = subprocess.run([sys.executable, __file__, "child", str(nbf)], env=e, capture_output=True, text=True)
+                out = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "ERR " + r.stderr[-300:]
+                note = ""
+                try:
+                    d = json.loads(out)
+                    if nbf not in ref:
+                        ref[nbf] = d
+                    note = " dJ=%.2e dK=%.2e" % (abs(d["cj"] - ref[nbf]["cj"]) / ref[nbf]["nj"], abs(d["ck"] - ref[nbf]["ck"]) / ref[nbf]["nk"])
+                except Exception:
+                    pass
+                print(nbf, name, env, out, note, flush=True)

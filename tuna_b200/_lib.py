@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtuna_b200.so")
+LIB_PATH = os.environ.get("TUNA_B200_LIB") or os.path.join(_HERE, "libtuna_b200.so")      # override: development builds only
 
 OK, ERR_ARG, ERR_NOMEM, ERR_CUDA, ERR_STATE = 0, 1, 2, 3, 4
 

@@ -189,6 +189,7 @@ struct ClassTablesHost {
     std::vector<unsigned> p4, p5ptr, p5term, p5off, t_rt, t_xy, t_u, t_s;
     std::vector<unsigned short> pmap, omap, jst_list;
     std::vector<unsigned> jst_ptr, jflush;
+    long long p5real = 0;             // digestion terms before padding (table statistics)
     long long allowed = 0;            // parity-allowed component quartets = integrals per shell quartet
     double uniq[6] = {0, 0, 0, 0, 0, 0};   // unique AO quartets a shell quartet stands for: [0] generic, [1] A==B, [2] C==D,
                                            // [3] A==B and C==D, [4] AB==CD (A!=B), [5] all four shells equal
@@ -439,15 +440,23 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
             terms[opos[C.nk + f.beta]].push_back((unsigned)f.slot | (unsigned)(C.nk + f.gamma) << 16);                    // Jb[beta]  += I Pg[gamma]
             terms[opos[C.nk + nbeta + f.gamma]].push_back((unsigned)f.slot | (unsigned)(C.nk + ngamma + f.beta) << 16);   // Jg[gamma] += I Pb[beta]
         }
+        // transposed storage in blocks of 32 accumulators: quad t of accumulator o at ((ptr[o / 32] + t * 32 + o % 32) * 4 words;
+        // every list of a block is padded to the block's longest (dummy term: zero slot It[itmax], P stage entry 0)
         C.p5off.push_back((unsigned)C.p5term.size());       // multiple of 4: 16-byte aligned uint4 loads
         unsigned run = 0;                                   // in units of four terms
-        for (int o = 0; o < C.nout; ++o) {
+        const int nblk = (C.nout + 31) / 32;
+        for (int blk = 0; blk < nblk; ++blk) {
             C.p5ptr.push_back(run);
-            while (terms[o].size() % 4) terms[o].push_back((unsigned)C.itmax);      // dummy: zero slot It[itmax], P stage entry 0
-            C.p5term.insert(C.p5term.end(), terms[o].begin(), terms[o].end());
-            run += (unsigned)terms[o].size() / 4;
+            size_t mx = 0;
+            for (int o = blk * 32; o < std::min(C.nout, blk * 32 + 32); ++o) mx = std::max(mx, (terms[o].size() + 3) / 4);
+            const size_t base = C.p5term.size();
+            C.p5term.resize(base + mx * 128, (unsigned)C.itmax);
+            for (int o = blk * 32; o < std::min(C.nout, blk * 32 + 32); ++o)
+                for (size_t k = 0; k < terms[o].size(); ++k) C.p5term[base + ((k / 4) * 32 + (size_t)(o & 31)) * 4 + (k & 3)] = terms[o][k];
+            run += (unsigned)mx * 32;
         }
         C.p5ptr.push_back(run);
+        for (int o = 0; o < C.nout; ++o) C.p5real += (long long)terms[o].size();
     }
 }
 

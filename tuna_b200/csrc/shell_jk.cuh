@@ -26,6 +26,8 @@
 
 #if !defined(__CUDACC__)
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 #endif
 
 namespace tuna {
@@ -112,7 +114,7 @@ struct ShellJob {
     double uniq[6];                 // unique AO quartets per shell quartet by degeneracy case (ClassTablesHost::uniq)
     ClassTablesDev ct;
     // shared-memory layout of one group (offsets in doubles)
-    int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oAO, aostride, total;
+    int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oRecA, oRecC, oAO, aostride, total;
 };
 
 struct ShellData {
@@ -139,6 +141,8 @@ inline void shell_job_layout(ShellJob& J, int nD) {
     J.oIt = o; o += J.ct.itmax + 1;       // + the zero slot read by padding terms
     J.oP = o; o += nD * J.ct.nout;
     J.oOut = o; o += nD * J.ct.nout;
+    J.oRecA = o; o += sp_rec_size(J.La, J.Lb);        // primitive shell-pair records of the current primitive quartet
+    J.oRecC = o; o += sp_rec_size(J.Lc, J.Ld);
     int lmax = J.La > J.Lc ? J.La : J.Lc;            // La >= Lb, Lc >= Ld by construction
     if (J.Lb > lmax) lmax = J.Lb;
     if (J.Ld > lmax) lmax = J.Ld;
@@ -172,12 +176,23 @@ TUNA_HD double boys_single(const double* __restrict__ tab, int m, double T) {
 
 #define TUNA_LANES(i, n) for (int i = Pol::lane(); i < (n); i += Pol::G)
 
+// The NB quartets a group works on are INTERLEAVED in shared memory: entry x of array X of quartet q lives at
+// sm[(J.oX + x) * NB + q], so one 16-byte shared load (NB = 2) brings the operand of both quartets and every table-driven
+// address is computed once per entry instead of once per quartet.
+template <int NB>
+struct alignas(NB >= 2 ? 16 : 8) QVec { double v[NB]; };
+template <int NB>
+TUNA_HD QVec<NB> qld(const double* p) { return *reinterpret_cast<const QVec<NB>*>(p); }
+template <int NB>
+TUNA_HD void qst(double* p, const QVec<NB>& x) { *reinterpret_cast<QVec<NB>*>(p) = x; }
+
 // NB shell quartets of the same class (pair ids AB[], CD[]; degeneracy weights w[]) processed TOGETHER by one group and folded
 // into the global accumulators Jf, Kf (nD matrices of ncart x ncart each) for densities Pf.  Batching NB quartets amortises
-// every table-entry decode, loop and barrier over NB independent FMA streams.  Quartet q uses the shared-memory slice
-// sm + q * J.total.  Quartets with active[q] == false only take part in the barriers.
+// every table-entry decode, loop and barrier over NB independent FMA streams.  Quartets with active[q] == false run on the
+// data of an active quartet with weight zero (uniform control flow, no per-quartet branches) and are not flushed; a batch
+// without any active quartet only takes part in the barriers.
 template <class Pol, int NB>
-TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* active, const int* AB, const int* CD, const double* w,
+TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* active, const int* ABin, const int* CDin, const double* win,
                             double* __restrict__ sm, int nD, const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf,
                             double* Kf, int ncart) {
     const ClassTablesDev& CT = J.ct;
@@ -185,23 +200,29 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
     const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = J.NS, NGZ = J.NGZ;
     const int NTA = Lab / 2 + 1, NTC = Lcd / 2 + 1, nout = CT.nout;
     const size_t nn = (size_t)ncart * ncart;
-    const int tot = J.total, aos = J.aostride;
-    double* const Bq = sm + J.oB; double* const pzq = sm + J.oPz; double* const Rtq = sm + J.oRt; double* const XYq = sm + J.oXY;
-    double* const Uq = sm + J.oU; double* const Sq = sm + J.oS; double* const Itq = sm + J.oIt; double* const Pstq = sm + J.oP;
-    double* const Outq = sm + J.oOut;
-    int* const aoq = reinterpret_cast<int*>(sm + J.oAO);          // [4][aostride] per quartet; quartet q at + q * 2 * tot ints
+    const int aos = J.aostride;
+    double* const Bq = sm + J.oB * NB; double* const pzq = sm + J.oPz * NB; double* const Rtq = sm + J.oRt * NB;
+    double* const XYq = sm + J.oXY * NB; double* const Uq = sm + J.oU * NB; double* const Sq = sm + J.oS * NB;
+    double* const Itq = sm + J.oIt * NB; double* const Pstq = sm + J.oP * NB; double* const Outq = sm + J.oOut * NB;
+    double* const RAq = sm + J.oRecA * NB; double* const RCq = sm + J.oRecC * NB;
+    int* const aoq = reinterpret_cast<int*>(sm + J.oAO * NB);          // [NB][4][aostride]
 
+    int qa = -1;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) if (qa < 0 && active[q]) qa = q;
+    const bool any = qa >= 0;
     const double* recA[NB]; const double* recC[NB];
-    bool any = false;
+    double w[NB];
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
-        recA[q] = nullptr; recC[q] = nullptr;
-        if (!active[q]) continue;
-        any = true;
-        const int sh[4] = {D.pairA[AB[q]], D.pairB[AB[q]], D.pairA[CD[q]], D.pairB[CD[q]]};
-        recA[q] = D.rec + D.pair_rec[AB[q]]; recC[q] = D.rec + D.pair_rec[CD[q]];
-        int* ao = aoq + q * 2 * tot;
-        TUNA_LANES(x, 4 * aos) ao[x] = D.sh_ao[sh[x / aos] * SH_NCMAX + x % aos];
+        const int ab = any ? (active[q] ? ABin[q] : ABin[qa]) : 0, cd = any ? (active[q] ? CDin[q] : CDin[qa]) : 0;
+        w[q] = active[q] ? win[q] : 0.0;
+        recA[q] = D.rec + D.pair_rec[ab]; recC[q] = D.rec + D.pair_rec[cd];
+        if (any) {
+            const int sh[4] = {D.pairA[ab], D.pairB[ab], D.pairA[cd], D.pairB[cd]};
+            int* ao = aoq + q * 4 * aos;
+            TUNA_LANES(x, 4 * aos) ao[x] = D.sh_ao[sh[x / aos] * SH_NCMAX + x % aos];
+        }
     }
     Pol::sync();
     if (any && !(J.dbg_skip & 64)) {
@@ -212,70 +233,80 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
             TUNA_LANES(x, CT.nk) {
                 const unsigned m = CT.pmap[x];
                 const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
+                QVec<NB> v;
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
-                    if (!active[q]) continue;
-                    const int* ao = aoq + q * 2 * tot;
-                    Pstq[q * tot + dn * nout + x] = P[(size_t)ao[ri] * ncart + ao[ci]];
+                    const int* ao = aoq + q * 4 * aos;
+                    v.v[q] = P[(size_t)ao[ri] * ncart + ao[ci]];
                 }
+                qst<NB>(Pstq + (size_t)(dn * nout + x) * NB, v);
             }
             TUNA_LANES(x, CT.njst) {
-                double v[NB];
+                QVec<NB> v;
 #pragma unroll
-                for (int q = 0; q < NB; ++q) v[q] = 0.0;
+                for (int q = 0; q < NB; ++q) v.v[q] = 0.0;
                 for (unsigned t = CT.jst_ptr[x]; t < CT.jst_ptr[x + 1]; ++t) {
                     const unsigned m = CT.jst_list[t];
                     const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
 #pragma unroll
                     for (int q = 0; q < NB; ++q) {
-                        if (!active[q]) continue;
-                        const int* ao = aoq + q * 2 * tot;
-                        v[q] += Ps[(size_t)ao[ri] * ncart + ao[ci]];
+                        const int* ao = aoq + q * 4 * aos;
+                        v.v[q] += Ps[(size_t)ao[ri] * ncart + ao[ci]];
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < NB; ++q) Pstq[q * tot + dn * nout + CT.nk + x] = v[q];
-            }
-            TUNA_LANES(x, nout) {
-#pragma unroll
-                for (int q = 0; q < NB; ++q) Outq[q * tot + dn * nout + x] = 0.0;
+                qst<NB>(Pstq + (size_t)(dn * nout + CT.nk + x) * NB, v);
             }
         }
+        TUNA_LANES(x, nD * nout * NB) Outq[x] = 0.0;
     }
     const int recAsz = sp_rec_size(La, Lb), recCsz = sp_rec_size(Lc, Ld);
-    const int oExA = SP_HDR + sp_ez_size(La, Lb), oExC = SP_HDR + sp_ez_size(Lc, Ld);
+    const int nEzC = sp_ez_size(Lc, Ld);
+    const int oExA = SP_HDR + sp_ez_size(La, Lb), oExC = SP_HDR + nEzC;
+    const int nblk = (nout + 31) >> 5;
 
     for (int ch = 0; ch < CT.nchunk; ++ch) {
         const int e0 = CT.chunk_e0[ch], ne = CT.chunk_e0[ch + 1] - e0;
         if (any) {
-            TUNA_LANES(x, ne) {
-#pragma unroll
-                for (int q = 0; q < NB; ++q) Itq[q * tot + x] = 0.0;
-            }
+            TUNA_LANES(x, ne * NB) Itq[x] = 0.0;
             if (Pol::lane() == 0) {
 #pragma unroll
-                for (int q = 0; q < NB; ++q) Itq[q * tot + CT.itmax] = 0.0;
+                for (int q = 0; q < NB; ++q) Itq[(size_t)CT.itmax * NB + q] = 0.0;
             }
         }
         for (int ia = 0; ia < J.nppAB; ++ia)
             for (int ic = 0; ic < J.nppCD; ++ic) {
-                const double* rA[NB]; const double* rC[NB];
                 double pref[NB];
-                // ---- phase 0: Boys values scaled by (-2 rho)^m, powers of PQz ---------------------------------
+                // ---- phase 0: stage the two primitive shell-pair records (the ket z coefficients with the sign (-1)^phi folded
+                // in); Boys values scaled by (-2 rho)^m and the powers of PQz, one (quartet, order) per lane -----------------
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
+                    const double* rA = recA[q] + (size_t)ia * recAsz;
+                    const double* rC = recC[q] + (size_t)ic * recCsz;
                     pref[q] = 0.0;
-                    rA[q] = recA[q] + (size_t)ia * recAsz;
-                    rC[q] = recC[q] + (size_t)ic * recCsz;
-                    if (!active[q] || (J.dbg_skip & 1)) continue;
-                    const double p = rA[q][0], qq = rC[q][0], pq = p + qq, rho = p * qq / pq, PQz = rA[q][1] - rC[q][1];
-                    const double Targ = rho * PQz * PQz;
-                    pref[q] = w[q] * rA[q][2] * rC[q][2] * 34.986836655249725 / (p * qq * sqrt(pq));
-                    TUNA_LANES(m, Ltot + 1) {
-                        double f = boys_single(D.boys, m, Targ), s = 1.0, z = 1.0;
+                    if (!any || (J.dbg_skip & 1)) continue;
+                    const double p = rA[0], qq = rC[0], pq = p + qq;
+                    pref[q] = w[q] * rA[2] * rC[2] * 34.986836655249725 / (p * qq * sqrt(pq));
+                    if (ic == 0) { TUNA_LANES(x, recAsz) RAq[(size_t)x * NB + q] = rA[x]; }
+                    TUNA_LANES(x, recCsz) {
+                        double v = rC[x];
+                        const int rel = x - SP_HDR;
+                        if (rel >= 0 && rel < nEzC && ((rel % (Lcd + 1)) & 1)) v = -v;
+                        RCq[(size_t)x * NB + q] = v;
+                    }
+                }
+                if (any && !(J.dbg_skip & 1)) {
+                    TUNA_LANES(x, NB * (Ltot + 1)) {
+                        const int q = x / (Ltot + 1), m = x - q * (Ltot + 1);
+                        const double* rA = recA[0] + (size_t)ia * recAsz;
+                        const double* rC = recC[0] + (size_t)ic * recCsz;
+#pragma unroll
+                        for (int k = 1; k < NB; ++k) if (q == k) { rA = recA[k] + (size_t)ia * recAsz; rC = recC[k] + (size_t)ic * recCsz; }
+                        const double p = rA[0], qq = rC[0], pq = p + qq, rho = p * qq / pq, PQz = rA[1] - rC[1];
+                        const double f = boys_single(D.boys, m, rho * PQz * PQz);
+                        double s = 1.0, z = 1.0;
                         for (int k = 0; k < m; ++k) { s *= -2.0 * rho; z *= PQz; }
-                        Bq[q * tot + m] = f * s;
-                        pzq[q * tot + m] = z;
+                        Bq[(size_t)m * NB + q] = f * s;
+                        pzq[(size_t)m * NB + q] = z;
                     }
                 }
                 Pol::sync();
@@ -284,16 +315,16 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                     TUNA_LANES(i, CT.n_rt) {
                         const unsigned e = CT.t_rt[i];
                         const int wv = (e >> 16) & 255, n = e >> 24;
-                        double r[NB];
+                        QVec<NB> r;
 #pragma unroll
-                        for (int q = 0; q < NB; ++q) r[q] = 0.0;
+                        for (int q = 0; q < NB; ++q) r.v[q] = 0.0;
                         for (int k = 0; 2 * k <= wv; ++k) {
                             const double h = D.herm[wv * HERM_STRIDE + k];
+                            const QVec<NB> z = qld<NB>(pzq + (size_t)(wv - 2 * k) * NB), b = qld<NB>(Bq + (size_t)(n + wv - k) * NB);
 #pragma unroll
-                            for (int q = 0; q < NB; ++q) r[q] = fma(h * pzq[q * tot + wv - 2 * k], Bq[q * tot + n + wv - k], r[q]);
+                            for (int q = 0; q < NB; ++q) r.v[q] = fma(h * z.v[q], b.v[q], r.v[q]);
                         }
-#pragma unroll
-                        for (int q = 0; q < NB; ++q) Rtq[q * tot + (e & 0xffffu)] = r[q];
+                        qst<NB>(Rtq + (size_t)(e & 0xffffu) * NB, r);
                     }
                     TUNA_LANES(i, CT.n_xy) {
                         const unsigned e = CT.t_xy[i];
@@ -301,14 +332,19 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                         const int tlo = (2 * m - n34 > px) ? 2 * m - n34 : px;
                         const int thi = (2 * m - px < n12) ? 2 * m - px : n12;
                         const double df = (n34 & 1) ? -odd_dfact(m) : odd_dfact(m);
+                        const double* ExA = RAq + (size_t)(oExA + n12 * NTA) * NB;
+                        const double* ExC = RCq + (size_t)(oExC + n34 * NTC) * NB;
+                        QVec<NB> v;
 #pragma unroll
-                        for (int q = 0; q < NB; ++q) {
-                            if (!active[q]) continue;
-                            const double* ExA = rA[q] + oExA; const double* ExC = rC[q] + oExC;
-                            double v = 0.0;
-                            for (int t = tlo; t <= thi; t += 2) v = fma(ExA[n12 * NTA + (t >> 1)], ExC[n34 * NTC + ((2 * m - t) >> 1)], v);
-                            XYq[q * tot + (e & 0xffffu)] = v * df;
+                        for (int q = 0; q < NB; ++q) v.v[q] = 0.0;
+                        for (int t = tlo; t <= thi; t += 2) {
+                            const QVec<NB> a = qld<NB>(ExA + (size_t)(t >> 1) * NB), c = qld<NB>(ExC + (size_t)((2 * m - t) >> 1) * NB);
+#pragma unroll
+                            for (int q = 0; q < NB; ++q) v.v[q] = fma(a.v[q], c.v[q], v.v[q]);
                         }
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) v.v[q] *= df;
+                        qst<NB>(XYq + (size_t)(e & 0xffffu) * NB, v);
                     }
                 }
                 Pol::sync();
@@ -317,16 +353,17 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                     TUNA_LANES(i, CT.n_u) {
                         const unsigned e0w = CT.t_u[2 * i], e1w = CT.t_u[2 * i + 1];
                         const int lz34 = e1w >> 16;
+                        const double* e = RCq + (size_t)(SP_HDR + (e1w & 0xffffu)) * NB;
+                        const double* r = Rtq + (size_t)(e0w >> 16) * NB;
+                        QVec<NB> u;
 #pragma unroll
-                        for (int q = 0; q < NB; ++q) {
-                            if (!active[q]) continue;
-                            const double* e = rC[q] + SP_HDR + (e1w & 0xffffu);
-                            const double* r = Rtq + q * tot + (e0w >> 16);
-                            double u = 0.0;
-                            for (int phi = 0; phi <= lz34; phi += 2) u = fma(e[phi], r[phi * NS], u);
-                            for (int phi = 1; phi <= lz34; phi += 2) u = fma(-e[phi], r[phi * NS], u);
-                            Uq[q * tot + (e0w & 0xffffu)] = u;
+                        for (int q = 0; q < NB; ++q) u.v[q] = 0.0;
+                        for (int phi = 0; phi <= lz34; ++phi) {
+                            const QVec<NB> ev = qld<NB>(e + (size_t)phi * NB), rv = qld<NB>(r + (size_t)phi * NS * NB);
+#pragma unroll
+                            for (int q = 0; q < NB; ++q) u.v[q] = fma(ev.v[q], rv.v[q], u.v[q]);
                         }
+                        qst<NB>(Uq + (size_t)(e0w & 0xffffu) * NB, u);
                     }
                 }
                 Pol::sync();
@@ -336,71 +373,95 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                     for (int i = CT.chunk_s0[ch] + Pol::lane(); i < CT.chunk_s0[ch + 1]; i += Pol::G) {
                         const unsigned e0w = CT.t_s[2 * i], e1w = CT.t_s[2 * i + 1];
                         const int lz12 = e1w >> 16;
+                        const double* e = RAq + (size_t)(SP_HDR + (e1w & 0xffffu)) * NB;
+                        const double* u = Uq + (size_t)(e0w >> 16) * NB;
+                        QVec<NB> sacc;
 #pragma unroll
-                        for (int q = 0; q < NB; ++q) {
-                            if (!active[q]) continue;
-                            const double* e = rA[q] + SP_HDR + (e1w & 0xffffu);
-                            const double* u = Uq + q * tot + (e0w >> 16);
-                            double sacc = 0.0;
-                            for (int v = 0; v <= lz12; ++v) sacc = fma(e[v], u[v * ustride], sacc);
-                            Sq[q * tot + (e0w & 0xffffu)] = sacc;
+                        for (int q = 0; q < NB; ++q) sacc.v[q] = 0.0;
+                        for (int v = 0; v <= lz12; ++v) {
+                            const QVec<NB> ev = qld<NB>(e + (size_t)v * NB), uv = qld<NB>(u + (size_t)v * ustride * NB);
+#pragma unroll
+                            for (int q = 0; q < NB; ++q) sacc.v[q] = fma(ev.v[q], uv.v[q], sacc.v[q]);
                         }
+                        qst<NB>(Sq + (size_t)(e0w & 0xffffu) * NB, sacc);
                     }
                 }
                 Pol::sync();
-                // ---- phase 4: table-driven integral assembly, accumulated over primitive quartets ----------------
+                // ---- phase 4: table-driven integral assembly, accumulated over primitive quartets; the table entry of the
+                // lane's next integral is fetched while the current one is assembled -------------------------------------
                 if (any && !(J.dbg_skip & 16)) {
-                    const unsigned* p4 = CT.p4 + 2 * (size_t)e0;
-                    TUNA_LANES(e, ne) {
-                        const unsigned w0 = p4[2 * e], w1 = p4[2 * e + 1];
+                    const uint2* p4 = reinterpret_cast<const uint2*>(CT.p4) + e0;
+                    int e = Pol::lane();
+                    uint2 nxt = make_uint2(0u, 0u);
+                    if (e < ne) nxt = p4[e];
+                    for (; e < ne; e += Pol::G) {
+                        const unsigned w0 = nxt.x, w1 = nxt.y;
+                        if (e + Pol::G < ne) nxt = p4[e + Pol::G];
                         const int xo = w0 & 0xffffu, yo = w0 >> 16, so = w1 & 0xffffu;
                         const int mx0 = (w1 >> 16) & 15, mx1 = (w1 >> 20) & 15, my0 = (w1 >> 24) & 15, my1 = (w1 >> 28) & 15;
-                        double val[NB];
+                        QVec<NB> val;
 #pragma unroll
-                        for (int q = 0; q < NB; ++q) val[q] = 0.0;
+                        for (int q = 0; q < NB; ++q) val.v[q] = 0.0;
+                        const double* xyx = XYq + (size_t)xo * NB;
+                        const double* xyy = XYq + (size_t)yo * NB;
                         for (int m = mx0; m <= mx1; ++m) {
-                            double t[NB];
+                            QVec<NB> t;
 #pragma unroll
-                            for (int q = 0; q < NB; ++q) t[q] = 0.0;
+                            for (int q = 0; q < NB; ++q) t.v[q] = 0.0;
+                            const double* sp = Sq + (size_t)(so + m) * NB;
                             for (int mp = my0; mp <= my1; ++mp) {
+                                const QVec<NB> y = qld<NB>(xyy + (size_t)mp * NB), s = qld<NB>(sp + (size_t)mp * NB);
 #pragma unroll
-                                for (int q = 0; q < NB; ++q) t[q] = fma(XYq[q * tot + yo + mp], Sq[q * tot + so + m + mp], t[q]);
+                                for (int q = 0; q < NB; ++q) t.v[q] = fma(y.v[q], s.v[q], t.v[q]);
                             }
+                            const QVec<NB> x = qld<NB>(xyx + (size_t)m * NB);
 #pragma unroll
-                            for (int q = 0; q < NB; ++q) val[q] = fma(XYq[q * tot + xo + m], t[q], val[q]);
+                            for (int q = 0; q < NB; ++q) val.v[q] = fma(x.v[q], t.v[q], val.v[q]);
                         }
+                        QVec<NB> it = qld<NB>(Itq + (size_t)e * NB);
 #pragma unroll
-                        for (int q = 0; q < NB; ++q) Itq[q * tot + e] = fma(pref[q], val[q], Itq[q * tot + e]);
+                        for (int q = 0; q < NB; ++q) it.v[q] = fma(pref[q], val.v[q], it.v[q]);
+                        qst<NB>(Itq + (size_t)e * NB, it);
                     }
                 }
             }
         Pol::sync();
-        // ---- phase 5: table-driven digestion of the chunk: every accumulator is owned by one lane.  Term lists are padded
-        // to a multiple of four (dummy terms read the zero slot It[itmax]) so that one 16-byte load brings four terms.
+        // ---- phase 5: table-driven digestion of the chunk: every accumulator is owned by one lane.  The term lists of 32
+        // consecutive accumulators are stored transposed (term quad t of accumulator o at (t * 32 + (o & 31))), padded to the
+        // longest list of the block with dummy terms that read the zero slot It[itmax]: one coalesced 16-byte load per lane
+        // brings four terms, and the next quad is in flight while the current one is digested.
         if (any && !(J.dbg_skip & 32)) {
-            const unsigned* ptr = CT.p5ptr + (size_t)ch * (nout + 1);
+            const unsigned* ptr = CT.p5ptr + (size_t)ch * (nblk + 1);
             const uint4* term = reinterpret_cast<const uint4*>(CT.p5term + CT.p5off[ch]);
             TUNA_LANES(o, nout) {
-                const unsigned t0 = ptr[o], t1 = ptr[o + 1];        // in units of four terms
+                const unsigned b0 = ptr[o >> 5], nq = (ptr[(o >> 5) + 1] - b0) >> 5;
+                if (nq == 0) continue;
+                const uint4* tp = term + b0 + (o & 31);
                 for (int dn = 0; dn < nD; ++dn) {
+                    const double* Pd = Pstq + (size_t)dn * nout * NB;
                     double s0[NB], s1[NB];
 #pragma unroll
                     for (int q = 0; q < NB; ++q) { s0[q] = 0.0; s1[q] = 0.0; }
-                    for (unsigned t = t0; t < t1; ++t) {
-                        const uint4 tq = term[t];
-                        const int i0 = tq.x & 0xffffu, p0 = dn * nout + (tq.x >> 16), i1 = tq.y & 0xffffu, p1 = dn * nout + (tq.y >> 16);
-                        const int i2 = tq.z & 0xffffu, p2 = dn * nout + (tq.z >> 16), i3 = tq.w & 0xffffu, p3 = dn * nout + (tq.w >> 16);
+                    uint4 nxt = tp[0];
+                    for (unsigned t = 0; t < nq; ++t) {
+                        const uint4 tq = nxt;
+                        if (t + 1 < nq) nxt = tp[(size_t)(t + 1) * 32];
+                        const QVec<NB> i0 = qld<NB>(Itq + (size_t)(tq.x & 0xffffu) * NB), p0 = qld<NB>(Pd + (size_t)(tq.x >> 16) * NB);
+                        const QVec<NB> i1 = qld<NB>(Itq + (size_t)(tq.y & 0xffffu) * NB), p1 = qld<NB>(Pd + (size_t)(tq.y >> 16) * NB);
+                        const QVec<NB> i2 = qld<NB>(Itq + (size_t)(tq.z & 0xffffu) * NB), p2 = qld<NB>(Pd + (size_t)(tq.z >> 16) * NB);
+                        const QVec<NB> i3 = qld<NB>(Itq + (size_t)(tq.w & 0xffffu) * NB), p3 = qld<NB>(Pd + (size_t)(tq.w >> 16) * NB);
 #pragma unroll
                         for (int q = 0; q < NB; ++q) {
-                            const double* It = Itq + q * tot; const double* Pd = Pstq + q * tot;
-                            s0[q] = fma(It[i0], Pd[p0], s0[q]);
-                            s1[q] = fma(It[i1], Pd[p1], s1[q]);
-                            s0[q] = fma(It[i2], Pd[p2], s0[q]);
-                            s1[q] = fma(It[i3], Pd[p3], s1[q]);
+                            s0[q] = fma(i0.v[q], p0.v[q], s0[q]);
+                            s1[q] = fma(i1.v[q], p1.v[q], s1[q]);
+                            s0[q] = fma(i2.v[q], p2.v[q], s0[q]);
+                            s1[q] = fma(i3.v[q], p3.v[q], s1[q]);
                         }
                     }
+                    QVec<NB> out = qld<NB>(Outq + (size_t)(dn * nout + o) * NB);
 #pragma unroll
-                    for (int q = 0; q < NB; ++q) Outq[q * tot + dn * nout + o] += s0[q] + s1[q];
+                    for (int q = 0; q < NB; ++q) out.v[q] += s0[q] + s1[q];
+                    qst<NB>(Outq + (size_t)(dn * nout + o) * NB, out);
                 }
             }
         }
@@ -413,21 +474,23 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                 const unsigned m = CT.omap[x];
                 if (m == 0xffffu) continue;                    // J pair-function accumulator: expanded below
                 const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
+                const QVec<NB> v = qld<NB>(Outq + (size_t)(dn * nout + x) * NB);
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
                     if (!active[q]) continue;
-                    const int* ao = aoq + q * 2 * tot;
-                    Pol::atomic_add(Kf + dn * nn + (size_t)ao[ri] * ncart + ao[ci], Outq[q * tot + dn * nout + x]);
+                    const int* ao = aoq + q * 4 * aos;
+                    Pol::atomic_add(Kf + dn * nn + (size_t)ao[ri] * ncart + ao[ci], v.v[q]);
                 }
             }
             TUNA_LANES(x, CT.njfl) {
                 const unsigned e = CT.jflush[x], m = e & 0xffffu;
                 const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
+                const QVec<NB> v = qld<NB>(Outq + (size_t)(dn * nout + (e >> 16)) * NB);
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
                     if (!active[q]) continue;
-                    const int* ao = aoq + q * 2 * tot;
-                    Pol::atomic_add(Jf + dn * nn + (size_t)ao[ri] * ncart + ao[ci], Outq[q * tot + dn * nout + (e >> 16)]);
+                    const int* ao = aoq + q * 4 * aos;
+                    Pol::atomic_add(Jf + dn * nn + (size_t)ao[ri] * ncart + ao[ci], v.v[q]);
                 }
             }
         }

@@ -1273,7 +1273,7 @@ int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
 static int shell_fixed_doubles(const ShellTab& T, int La, int Lb, int Lc, int Ld, int nD) {
     const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = Ltot / 2 + 1, NGZ = (Lc + 1) * (Ld + 1);
     const int nout = T.nc[La] * T.nc[Lc] + T.nc[La] * T.nc[Ld] + T.nc[Lb] * T.nc[Lc] + T.nc[Lb] * T.nc[Ld] + T.nc[La] * T.nc[Lb] + T.nc[Lc] * T.nc[Ld];
-    return 2 * (Ltot + 1) + (Ltot + 1) * NS + (Lab + 1) * (Lcd + 1) * NS + (Lab + 1) * NGZ * NS + 2 * nD * nout + 64;
+    return 2 * (Ltot + 1) + (Ltot + 1) * NS + (Lab + 1) * (Lcd + 1) * NS + (Lab + 1) * NGZ * NS + 2 * nD * nout + sp_rec_size(La, Lb) + sp_rec_size(Lc, Ld) + 64;
 }
 constexpr int SHELL_SMEM_DOUBLES = 26500;      // 207 KB of the 227 KB a CTA may use
 
@@ -1397,7 +1397,10 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 // NB quartets are batched per group when two slices fit comfortably; the group size G follows the footprint
                 const char* env_nb = getenv("TUNA_B200_NB");
                 int nb = env_nb ? atoi(env_nb) : 2;
-                if ((size_t)2 * J.total * 8 > 96 * 1024) nb = 1;
+                if (nb != 1 && nb != 2 && nb != 4) nb = 2;
+                const char* env_nbmax = getenv("TUNA_B200_NB_BYTES");       // batch only while the NB slices stay below this
+                const size_t nb_bytes = env_nbmax ? (size_t)atol(env_nbmax) : 96 * 1024;
+                while (nb > 1 && (size_t)nb * J.total * 8 > nb_bytes) nb >>= 1;
                 int G = 1;
                 while (G < 256 && G * gdiv < jh.allowed) G *= 2;
                 while (G < 256 && (double)nb * J.total * 8.0 / G > smem_per_lane) G *= 2;
@@ -1425,10 +1428,24 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
             const char* et = getenv("TUNA_B200_OWN_LAUNCH_MIN");
             const double thr = (et ? atof(et) : 5.0e5) * ctx->shard_n;
             for (auto& jh : ctx->jobs) jh.own_launch = jh.allowed * (double)jh.job.nitems >= thr;
+            if (const char* dump = getenv("TUNA_B200_DUMP_JOBS")) {       // development aid: the job table in launch order
+                if (FILE* f = fopen(dump, "w")) {
+                    fprintf(f, "idx,La,Lb,Lc,Ld,nppAB,nppCD,G,nb,threads,smem,total,nout,nint,itmax,nchunk,nitems,allowed,own\n");
+                    int idx = 0;
+                    for (const auto& jh : ctx->jobs) {
+                        auto ct = ctx->class_tabs.find(jh.job.La | jh.job.Lb << 4 | jh.job.Lc << 8 | jh.job.Ld << 12 | nD << 16);
+                        fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%zu,%d,%d,%d,%d,%d,%lld,%.0f,%d\n", idx++, jh.job.La, jh.job.Lb, jh.job.Lc, jh.job.Ld,
+                                jh.job.nppAB, jh.job.nppCD, jh.G, jh.nb, jh.threads, jh.smem, jh.job.total, jh.job.ct.nout,
+                                ct != ctx->class_tabs.end() ? ct->second.host.nint : -1, jh.job.ct.itmax, jh.job.ct.nchunk, jh.job.nitems, jh.allowed,
+                                (int)jh.own_launch);
+                    }
+                    fclose(f);
+                }
+            }
         }
         for (auto& g : ctx->groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
         ctx->groups.clear();
-        for (int nbv = 2; nbv >= 1; --nbv)
+        for (int nbv = 4; nbv >= 1; nbv >>= 1)
         for (int G = 256; G >= 1; G >>= 1)
             for (int bucket = 40; bucket >= 0; --bucket) {       // jobs of similar shared-memory footprint share a launch (occupancy)
                 std::vector<ShellJob> js;
@@ -1567,7 +1584,8 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
             if (!jh.own_launch) continue;
             cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
             cudaError_t e;
-#define TUNA_ONE(GV) (jh.nb == 2 ? launch_shell_one<GV, 2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
+#define TUNA_ONE(GV) (jh.nb == 4 ? launch_shell_one<GV, 4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
+                      : jh.nb == 2 ? launch_shell_one<GV, 2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
                                    : launch_shell_one<GV, 1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st))
             switch (jh.G) {
                 case 1: e = TUNA_ONE(1); break;
@@ -1586,7 +1604,8 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
         for (const auto& lg : ctx->groups) {
             cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
             cudaError_t e;
-#define TUNA_GRP(GV) (lg.nb == 2 ? launch_shell<GV, 2>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
+#define TUNA_GRP(GV) (lg.nb == 4 ? launch_shell<GV, 4>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
+                      : lg.nb == 2 ? launch_shell<GV, 2>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
                                    : launch_shell<GV, 1>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st))
             switch (lg.G) {
                 case 1: e = TUNA_GRP(1); break;
