@@ -250,6 +250,25 @@ def run_reference_arm(args, wl):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
+class L2Flush:
+    """Evict L2 between timed steps: write a 256 MB buffer (> the 126 MB L2, so nothing of the previous step survives), then READ
+    a second 256 MB buffer so that L2 is left holding clean lines.  Without the read pass the first ~126 MB a kernel pulls in
+    would each evict a dirty line of the flush buffer, charging up to an L2's worth of HBM write-back to the timed kernel."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.a = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+        self.b = torch.ones(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+        self.sink = None
+
+    def __call__(self):
+        self.a.add_(1.0)
+        self.sink = self.torch.sum(self.b)
+
+
+L2_NOTE = "flushed between steps (256 MB written, then 256 MB of a second buffer read so L2 holds clean lines)"
+
+
 def time_steps(torch, stream, fn, steps, warmup, flush, dist=None):
     """W untimed + K timed steps; each timed step bracketed by CUDA events on the launching stream; L2 flushed between steps."""
     for _ in range(warmup):
@@ -261,7 +280,7 @@ def time_steps(torch, stream, fn, steps, warmup, flush, dist=None):
     total_ms = 0.0
     for _ in range(steps):
         if flush is not None:
-            flush.add_(1.0)                       # > L2 (126 MB): evicts the previous step's lines
+            flush()                               # > L2 (126 MB): evicts the previous step's lines
             torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
@@ -298,14 +317,14 @@ def bench_stored(torch, wl, steps, warmup, device):
     P = np.stack([tuna_b200.workloads.fixed_density(n)] * nD)
     dP = torch.from_numpy(P).cuda()
     dJK = torch.empty((2, nD, n, n), dtype=torch.float64, device="cuda")
-    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")      # 256 MB
+    flush = L2Flush(torch)
     l0 = ctx.counts()["launches"]
     ms = time_steps(torch, stream, lambda: ctx.jk_stored_dev(nD, dP.data_ptr(), dJK[0].data_ptr(), dJK[1].data_ptr()), steps, warmup, flush)
     launches = ctx.counts()["launches"] - l0 - 2 * warmup * ((nD + 3) // 4)
     # per-launch kernel time from the context's own events on the same stream
     kms = []
     for _ in range(5):
-        flush.add_(1.0); torch.cuda.synchronize()
+        flush(); torch.cuda.synchronize()
         ctx.jk_stored_dev(nD, dP.data_ptr(), dJK[0].data_ptr(), dJK[1].data_ptr())
         kms.append(ctx.last_kernel_ms(2))
     k_ms = float(np.median(kms))
@@ -321,11 +340,11 @@ def bench_stored(torch, wl, steps, warmup, device):
         J, K = tuna_b200.coulomb_and_exchange(Ph, handle)
     e2e = steps / (time.perf_counter() - t)
     res = {"workload": wl["description"], "nbf": n, "ncart": wl["ncart"], "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
-           "l2": "flushed between steps (256 MB write); the 8*nbf^4 tensor is read from HBM",
+           "l2": L2_NOTE + "; the 8*nbf^4 tensor is read from HBM",
            "eri_fill_ms": float(min(t_fill)), "cart_to_sph_ms": float(min(t_sph)),
            "eri_quartets_per_s": c["surviving_quartets"] / (min(t_fill) * 1e-3),
            "roofline": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": src, "kernel": "k_jk_stored",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": src, "kernel": "k_jk_stored_sym + k_sym_reduce (whole J/K build: both launches, CUDA events of the context)",
                         "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes},
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * nD * n * n), "d2h_bytes_per_step": int(16 * nD * n * n)},
            "gpu_launches": int(launches)}
@@ -344,7 +363,7 @@ def sweep_point(torch, nbf, tau, fp64_peak, device):
     ctx.set_transform(wl["U"])
     fb = FockBuilder(ctx, nD=1, tau=tau)
     fb.dP.copy_(torch.from_numpy(tuna_b200.workloads.fixed_density(wl["nbf"])[None]))
-    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    flush = L2Flush(torch)
     steps = 10
     ms = time_steps(torch, fb.stream, fb.build_device, steps, 3, flush)
     alg_eri, alg_digest = ctx.algorithmic_flops()
@@ -399,7 +418,7 @@ def run_ours(args, wl):
     fb = FockBuilder(ctx, nD=nD, tau=args.tau)
     P = np.stack([tuna_b200.workloads.fixed_density(n)] * nD)
     fb.dP.copy_(torch.from_numpy(P))
-    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    flush = L2Flush(torch)
     fp64_peak = ctx.fp64_peak_probe() if rank == 0 else 0.0
     sampler.start()
     l0 = None
@@ -441,7 +460,7 @@ def run_ours(args, wl):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["description"], "nbf": n, "ncart": wl["ncart"], "mode": "direct", "densities": nD, "schwarz_tau": args.tau,
                        "parallelism": f"quartet list sharded over {world} GPU(s), one all-reduce of J/K per build",
-                       "l2": "flushed between steps (256 MB write); inputs (pair table, P) are re-read from HBM each step",
+                       "l2": L2_NOTE + "; inputs (pair table, P) are re-read from HBM each step",
                        "pair_table_setup_s": setup_s},
             "eri_quartets_per_s": evaluated * builds_per_s, "surviving_quartets": c["surviving_quartets"], "evaluated_quartets": evaluated,
             "unique_quartets_per_s": c["unique_quartets"] * builds_per_s,
@@ -460,6 +479,12 @@ def run_ours(args, wl):
             sres, sctx = bench_stored(torch, swl, max(args.steps, 20), max(args.warmup, 3), local)
             sres["cpu_baseline"] = cpu_reference(swl)
             line["stored"] = sres
+            sctx = None
+            lwl = load_workload("stored:et100")       # the same stored kernel on a tensor well above L2 (0.8 GB): the HBM-stream regime
+            lwl["description"] = "stored mode at nbf 100 (even-tempered N2, 0.8 GB tensor), 1 density"
+            lres, lctx = bench_stored(torch, lwl, max(args.steps, 20), max(args.warmup, 3), local)
+            line["stored_large"] = lres
+            lctx = None
             line["sweep"] = [sweep_point(torch, nb, args.tau, fp64_peak, local) for nb in (100, 200, 400) if f"et{nb}" != wl["name"]]
     print(json.dumps(line), flush=True)
     if ddist is not None:

@@ -330,3 +330,27 @@ def test_many_densities(tb, oracle):
         assert np.abs(Js[d] - oracle.coulomb(P[d], E)).max() < 1e-10 and np.abs(Ks[d] - oracle.exchange(P[d], E)).max() < 1e-10
     scale = max(1.0, np.abs(Ks).max())
     assert np.abs(Jd - Js).max() < 1e-11 * scale and np.abs(Kd - Ks).max() < 1e-11 * scale
+
+
+@pytest.mark.parametrize("n", [16, 22, 60, 62, 100])
+def test_stored_streaming_kernels_on_uploaded_tensors(tb, n, monkeypatch):
+    """Stored J/K on uploaded tensors vs the reference's two einsums (tuna_scf.py:42,70): a pair-symmetric tensor takes the
+    symmetric streaming kernel (register-resident J, MT = 4 / 8 / 16 variants), an arbitrary tensor must fall back to the
+    general kernels and still be exact; several (also non-symmetric) densities at once."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n * n, n * n))
+    for E in (((A + A.T) / 2).reshape(n, n, n, n), A.reshape(n, n, n, n)):
+        for nD in ((1, 3) if n <= 62 else (1,)):
+            P = rng.standard_normal((nD, n, n))
+            Jr = np.einsum("ijkl,dkl->dij", E, P, optimize=True)
+            Kr = np.einsum("ilkj,dkl->dij", E, P, optimize=True)
+            for kern in ("", "tma"):
+                if kern:
+                    monkeypatch.setenv("TUNA_B200_STORED_KERNEL", kern)
+                else:
+                    monkeypatch.delenv("TUNA_B200_STORED_KERNEL", raising=False)
+                ctx = tb.Context(0)
+                ctx.eri_upload(np.ascontiguousarray(E))
+                J, K = ctx.jk_stored(P)
+                tol = 1e-12 * n * n
+                assert np.abs(np.asarray(J).reshape(Jr.shape) - Jr).max() < tol and np.abs(np.asarray(K).reshape(Kr.shape) - Kr).max() < tol

@@ -19,15 +19,20 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         Jr = np.einsum("ijkl,dkl->dij", E, P, optimize=True); Kr = np.einsum("ilkj,dkl->dij", E, P, optimize=True)
         print("nD", nD, "J err", np.abs(J - Jr).max(), "K err", np.abs(K - Kr).max(), flush=True)
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    flush2 = torch.ones(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    clean = os.environ.get("FLUSH_CLEAN", "1") == "1"
     P = rng.standard_normal((1, n, n))
     ts = []
     for _ in range(10):
-        flush.add_(1.0); torch.cuda.synchronize()
+        flush.add_(1.0)
+        if clean:
+            sink = torch.sum(flush2)
+        torch.cuda.synchronize()
         ctx.jk_stored(P); ts.append(ctx.last_kernel_ms(2))
-    print(json.dumps({"name": name, "n": n, "kernel": os.environ.get("TUNA_B200_STORED_KERNEL", "tma"), "ms_median": float(np.median(ts)), "ms_min": float(min(ts)),
+    print(json.dumps({"name": name, "n": n, "kernel": os.environ.get("TUNA_B200_STORED_KERNEL", "sym"), "ms_median": float(np.median(ts)), "ms_min": float(min(ts)),
                       "GBps": 8.0 * n ** 4 / (np.median(ts) * 1e-3) / 1e9}))
 else:
-    cfgs = [("simple", {}), ("tma", {})]
+    cfgs = [("sym", {}), ("sym", {"FLUSH_CLEAN": "0"}), ("tma", {}), ("sym", {"TUNA_B200_PDL": "0"})]
     for tile in ():
         for st in (3, 4):
             for cps in (1, 2):

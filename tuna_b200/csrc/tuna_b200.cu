@@ -67,6 +67,7 @@ struct tuna_ctx {
     double* d_eri_cart = nullptr;
     double* d_eri_sph = nullptr;      // "stored" tensor of dimension n_stored
     int n_stored = 0;
+    bool eri_pair_sym = false;        // (il|kj) == (kj|il) holds for the stored tensor: the symmetric streaming J/K kernel may be used
 
     // J/K workspaces
     double* d_P = nullptr; double* d_J = nullptr; double* d_K = nullptr;   // nD * n^2 staging (spherical)
@@ -113,6 +114,8 @@ struct tuna_ctx {
     } while (0)
 
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+static int check_pair_symmetry(tuna_ctx* ctx);
 
 template <typename T>
 static int dev_alloc(tuna_ctx* ctx, T** p, size_t count) {
@@ -444,6 +447,197 @@ __global__ void k_kslot_reduce(const double* __restrict__ Kslot, const int* __re
             if (Krow[slot] == i) v += Kslot[((size_t)slot * nD + d) * n + jj];
         }
         K[x] = v;
+    }
+}
+
+// ---- stored J/K, pair-symmetric streaming kernel ------------------------------------------------------------------
+// For a tensor with (il|kj) = (kj|il) (every physical ERI tensor; verified on upload) the Coulomb matrix can be accumulated
+// WITHOUT a per-slab block reduction:  J[k][j] = sum_{i,l} E[i,l,k,j] P[i,l]  — thread (k, j) keeps J[k][j] in a register
+// and multiplies the slab E[i,l,:,:] it streams by the slab-uniform scalar P[i,l].  K[i][j] = sum_{k,l} E[i,l,k,j] P[k,l] is a
+// per-thread register as well (summed over the r thread rows when i changes).  The kernel is then a pure TMA stream:
+//   * one producer thread issues 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) of 2*T-element tiles into a deep ring
+//     (up to 16 stages, ~160 KB in flight per SM) and only waits on per-stage "empty" mbarriers;
+//   * the consumer warps never meet at a CTA barrier inside the stream: they wait on the stage's "full" mbarrier, do two
+//     FMAs per element and one elected lane per warp arrives on the "empty" mbarrier;
+//   * P^T lives in shared memory (P[k][l] for the thread's rows k is a broadcast read).
+// Every CTA writes its partial J (registers -> Jpart[cta]) and partial K rows (Kslot); k_sym_reduce sums both in a fixed order.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int ND, int MT>
+__global__ void __launch_bounds__(1024, 1) k_jk_stored_sym(const double* __restrict__ E, const double* __restrict__ P, double* __restrict__ Jpart,
+                                                             double* __restrict__ Kslot, int* __restrict__ Krow, int n, int r, int nstage,
+                                                             int kslots, int ncons) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = r * n, nn = n * n, tileD = 2 * T;
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    double* Pt = ring + (size_t)nstage * tileD;                 // [ND][l][k] = P[d][k][l]
+    double* sK = Pt + (size_t)ND * nn;                           // [2][ND][r][n]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sK + (size_t)2 * ND * r * n);
+    uint64_t* empty = full + nstage;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int s0 = (int)((long long)nn * blockIdx.x / gridDim.x), s1 = (int)((long long)nn * (blockIdx.x + 1) / gridDim.x);
+    const int qreal = (nn + tileD - 1) / tileD;                  // tiles per slab (<= MT / 2)
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncons >> 5); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int x = tid; x < kslots; x += blockDim.x) Krow[blockIdx.x * kslots + x] = -1;
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;");          // let the reduction kernel's launch overlap this grid (it waits for our completion)
+    if (tid >= ncons) {                                          // producer warp: one thread streams the CTA's slab range
+        if (tid == ncons) {
+            int st = 0;
+            uint32_t ph = 1;                                     // a fresh "empty" barrier passes a wait on the preceding phase
+            for (int s = s0; s < s1; ++s)
+                for (int p = 0; p < qreal; ++p) {
+                    mbar_wait(&empty[st], ph);
+                    const int cnt = min(tileD, nn - p * tileD);
+                    const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(double);
+                    mbar_expect_tx(&full[st], bytes);
+                    tma_bulk_load(ring + (size_t)st * tileD, E + (size_t)s * nn + (size_t)p * tileD, bytes, &full[st]);
+                    if (++st == nstage) { st = 0; ph ^= 1; }
+                }
+        }
+        return;
+    }
+    // ---- consumers ----
+    for (int x = tid; x < ND * nn; x += ncons) {
+        const int d = x / nn, rem = x - d * nn, k = rem / n, l = rem - k * n;
+        Pt[(size_t)d * nn + l * n + k] = P[x];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    const bool act = tid < T;
+    const int j = tid % n, rt = tid / n;
+    double accJ[ND][MT], accK[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        accK[d] = 0.0;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) accJ[d][m] = 0.0;
+    }
+    int st = 0, flushes = 0, kb = 0;
+    uint32_t ph = 0;
+    int cur_i = s0 / n, i = cur_i, l = s0 - cur_i * n;
+    auto flushK = [&]() {
+        double* buf = sK + (size_t)kb * ND * r * n;
+        if (act) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) buf[((size_t)d * r + rt) * n + j] = accK[d];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+        const int slot = blockIdx.x * kslots + flushes;
+        for (int x = tid; x < ND * n; x += ncons) {
+            const int d = x / n, jj = x - d * n;
+            double v = 0.0;
+            for (int qq = 0; qq < r; ++qq) v += buf[((size_t)d * r + qq) * n + jj];
+            Kslot[((size_t)slot * ND + d) * n + jj] = v;
+        }
+        if (tid == 0) Krow[slot] = cur_i;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) accK[d] = 0.0;
+        ++flushes;
+        kb ^= 1;
+    };
+    for (int s = s0; s < s1; ++s) {
+        if (i != cur_i) { flushK(); cur_i = i; }
+        const double* ptl = Pt + (size_t)l * n;
+        double pil[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) pil[d] = ptl[(size_t)d * nn + i];
+#pragma unroll
+        for (int p = 0; p < MT / 2; ++p) {
+            if (p < qreal) {
+                mbar_wait(&full[st], ph);
+                const double* tile = ring + (size_t)st * tileD;
+#pragma unroll
+                for (int mm = 0; mm < 2; ++mm) {
+                    const int m = 2 * p + mm, k = rt + m * r;
+                    if (act && k < n) {
+                        const double e = tile[tid + mm * T];
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) {
+                            accJ[d][m] = fma(e, pil[d], accJ[d][m]);
+                            accK[d] = fma(e, ptl[(size_t)d * nn + k], accK[d]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+                if (++st == nstage) { st = 0; ph ^= 1; }
+            }
+        }
+        if (++l == n) { l = 0; ++i; }
+    }
+    if (s1 > s0) flushK();
+    if (act) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                if (rt + m * r < n) Jpart[((size_t)blockIdx.x * ND + d) * nn + tid + m * T] = accJ[d][m];
+    }
+}
+
+// J[d][e] = sum over CTAs of Jpart, K as in k_kslot_reduce.  A warp owns four consecutive elements: lane = 4 g + ei sums the
+// partials of CTAs c = g (mod 8) for element ei (32-byte sectors fully used), then a fixed shuffle tree adds the eight
+// groups -> deterministic, and the ~grid/8 loads per lane are independent.
+__global__ void __launch_bounds__(256) k_sym_reduce(const double* __restrict__ Jpart, double* __restrict__ J, const double* __restrict__ Kslot,
+                                                    const int* __restrict__ Krow, double* __restrict__ K, int nD, int n, int grid, int kslots) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // programmatic dependent launch: the streaming kernel's results are visible after this
+    const int64_t nn = (int64_t)n * n, total = nD * nn;
+    const int64_t gx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, ei = lane & 3, g = lane >> 2;
+    const int64_t x = (gx >> 5) * 4 + ei;
+    const bool valid = x < total;
+    const int64_t d = valid ? x / nn : 0, e = valid ? x % nn : 0;
+    double v0 = 0.0, v1 = 0.0;
+    if (valid && J) {
+        const double* src = Jpart + (size_t)d * nn + e;
+        const size_t stride = (size_t)nD * nn;
+        for (int c = g; c < grid; c += 16) {
+            v0 += src[(size_t)c * stride];
+            if (c + 8 < grid) v1 += src[(size_t)(c + 8) * stride];
+        }
+    }
+    double v = v0 + v1;
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (valid && g == 0 && J) J[x] = v;
+    if (valid && g == 1 && K) {
+        const long long slabs = nn;
+        const int jj = (int)(e % n), i = (int)(e / n);
+        int c_lo = (int)(((long long)i * n * grid) / slabs);
+        while (c_lo > 0 && slabs * c_lo / grid > (long long)i * n) --c_lo;
+        double kv = 0.0;
+        for (int c = c_lo; c < grid; ++c) {
+            const long long s0 = slabs * c / grid, s1 = slabs * (c + 1) / grid;
+            if (s0 >= (long long)(i + 1) * n) break;
+            if (s1 <= (long long)i * n || s1 == s0) continue;
+            const int slot = c * kslots + (i - (int)(s0 / n));
+            if (Krow[slot] == i) kv += Kslot[((size_t)slot * nD + d) * n + jj];
+        }
+        K[x] = kv;
+    }
+}
+
+// max |E[i,l,k,j] - E[k,j,i,l]| and max |E| (bit patterns of non-negative doubles order like integers)
+__global__ void k_pair_sym_check(const double* __restrict__ E, int n, unsigned long long* out) {
+    const int64_t nn = (int64_t)n * n, total = nn * nn;
+    double md = 0.0, mx = 0.0;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = x / nn, b = x % nn;
+        if (b > a) continue;
+        const double u = E[x], w = E[b * nn + a];
+        md = fmax(md, fabs(u - w));
+        mx = fmax(mx, fmax(fabs(u), fabs(w)));
+    }
+    for (int o = 16; o > 0; o >>= 1) { md = fmax(md, __shfl_down_sync(0xffffffffu, md, o)); mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, (unsigned long long)__double_as_longlong(md));
+        atomicMax(out + 1, (unsigned long long)__double_as_longlong(mx));
     }
 }
 
@@ -1022,6 +1216,7 @@ int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart) {
         }
         CK(cudaEventRecord(ctx->ev[1][1], ctx->stream));
         ctx->n_stored = (int)nc;
+        ctx->eri_pair_sym = true;          // the fill scatters one value to all eight images
         return TUNA_OK;
     }
     if ((rc = dev_alloc(ctx, &t1, (size_t)(nb * nc * nc * nc)))) return rc;
@@ -1041,7 +1236,7 @@ int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart) {
     CK(cudaStreamSynchronize(ctx->stream));
     dev_free(&t3);
     ctx->n_stored = (int)nb;
-    return TUNA_OK;
+    return check_pair_symmetry(ctx);
 }
 
 int tuna_eri_download(tuna_ctx* ctx, int which, double* host_out) {
@@ -1065,7 +1260,7 @@ int tuna_eri_upload(tuna_ctx* ctx, int n, const double* host_in) {
     CK(cudaMemcpyAsync(ctx->d_eri_sph, host_in, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_stored = n;
-    return TUNA_OK;
+    return check_pair_symmetry(ctx);
 }
 
 int tuna_eri_single(tuna_ctx* ctx, int i, int j, int k, int l, double* out) {
@@ -1119,6 +1314,102 @@ int tuna_schwarz(tuna_ctx* ctx, double* host_out) {
 
 }  // extern "C"
 
+// Does the stored tensor have the pair-exchange symmetry (il|kj) = (kj|il) to rounding?  (Any physical ERI tensor does; an
+// arbitrary uploaded array need not, and then the general kernels are used.)
+static int check_pair_symmetry(tuna_ctx* ctx) {
+    ctx->eri_pair_sym = false;
+    if (!ctx->d_eri_sph || ctx->n_stored == 0) return TUNA_OK;
+    const int n = ctx->n_stored;
+    CK(cudaMemsetAsync(ctx->d_scalars + 2, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    k_pair_sym_check<<<grid_for(ctx, (int64_t)n * n * n * n, 256, 8), 256, 0, ctx->stream>>>(ctx->d_eri_sph, n, ctx->d_scalars + 2);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, ctx->d_scalars + 2, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double md, mx;
+    std::memcpy(&md, &h[0], 8); std::memcpy(&mx, &h[1], 8);
+    ctx->eri_pair_sym = md <= 1e-13 * mx;
+    return TUNA_OK;
+}
+
+template <int ND, int MT>
+static cudaError_t launch_jk_sym(tuna_ctx* ctx, const double* P, double* Jpart, double* Kslot, int* Krow, int n, int r, int nstage, int kslots,
+                                 int ncons, int grid, size_t smem) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_jk_stored_sym<ND, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_jk_stored_sym<ND, MT><<<grid, ncons + 32, smem, ctx->stream>>>(ctx->d_eri_sph, P, Jpart, Kslot, Krow, n, r, nstage, kslots, ncons);
+    return cudaGetLastError();
+}
+
+// Symmetric streaming path; returns TUNA_OK with *done = false when the shape does not fit its register / shared-memory budget.
+static int jk_stored_sym(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK, bool* done) {
+    *done = false;
+    const int n = ctx->n_stored;
+    const size_t nn = (size_t)n * n;
+    if (!ctx->eri_pair_sym || (n & 1) || n < 16 || n > 960) return TUNA_OK;
+    const int r = std::min(n, 960 / n), T = r * n, ncons = (T + 31) / 32 * 32;
+    const int mt_need = (n + r - 1) / r;
+    const int MT = mt_need <= 4 ? 4 : mt_need <= 8 ? 8 : mt_need <= 16 ? 16 : 0;
+    const int nd_max = MT == 4 ? 4 : MT == 8 ? 2 : MT == 16 ? 1 : 0;
+    if (MT == 0 || (nD + nd_max - 1) / nd_max > (nD + 3) / 4) return TUNA_OK;      // never more passes over the tensor than the general kernel
+    const int grid = (int)std::min<long long>((long long)ctx->sm_count, (long long)nn);
+    const int kslots = (int)((nn / grid + 1 + n - 1) / n) + 2;
+    const int nslots = grid * kslots;
+    int rc;
+    for (int d0 = 0; d0 < nD; d0 += nd_max) {
+        const int nd = std::min(nd_max, nD - d0);
+        const size_t fixed = ((size_t)nd * nn + (size_t)2 * nd * r * n) * sizeof(double) + 2 * 16 * sizeof(uint64_t) + 128;
+        const size_t tile_bytes = (size_t)2 * T * sizeof(double);
+        if (fixed + 4 * tile_bytes > 227 * 1024) return d0 == 0 ? TUNA_OK : TUNA_ERR_STATE;
+        const int nstage = (int)std::min<size_t>(16, (227 * 1024 - fixed) / tile_bytes);
+        const size_t smem = (size_t)nstage * tile_bytes + fixed;
+        // workspace: Kslot rows | Krow tags | Jpart
+        const size_t o_krow = (size_t)nslots * nd_max * n, o_jpart = o_krow + (size_t)(nslots + 1) / 2 + 2;
+        const size_t need = o_jpart + (size_t)grid * nd_max * nn;
+        if (need > ctx->cap_kpart) {
+            if ((rc = dev_alloc(ctx, &ctx->d_Kpart, need))) return rc;
+            ctx->cap_kpart = need;
+        }
+        double* Kslot = ctx->d_Kpart;
+        int* Krow = reinterpret_cast<int*>(ctx->d_Kpart + o_krow);
+        double* Jpart = ctx->d_Kpart + o_jpart;
+        const double* P = dP + d0 * nn;
+        if (d0 == 0) CK(cudaEventRecord(ctx->ev[2][0], ctx->stream));
+        cudaError_t e = cudaErrorInvalidValue;
+#define TUNA_SYM(NDV, MTV) e = launch_jk_sym<NDV, MTV>(ctx, P, Jpart, Kslot, Krow, n, r, nstage, kslots, ncons, grid, smem)
+        if (MT == 4) { switch (nd) { case 1: TUNA_SYM(1, 4); break; case 2: TUNA_SYM(2, 4); break; case 3: TUNA_SYM(3, 4); break; default: TUNA_SYM(4, 4); break; } }
+        else if (MT == 8) { if (nd == 1) TUNA_SYM(1, 8); else TUNA_SYM(2, 8); }
+        else TUNA_SYM(1, 16);
+#undef TUNA_SYM
+        ctx->launches++;
+        if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_jk_stored_sym launch: ") + cudaGetErrorString(e));
+        {
+            static const bool pdl = getenv("TUNA_B200_PDL") && atoi(getenv("TUNA_B200_PDL")) == 1;     // opt-in: measured slightly slower (36.9 vs 40.1 us at nbf 60)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(((int64_t)nd * nn * 8 + 255) / 256));
+            cfg.blockDim = dim3(256);
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = pdl ? 1 : 0;
+            const double* jp = Jpart; const double* ks = Kslot; const int* kr = Krow;
+            double* jo = dJ ? dJ + d0 * nn : nullptr; double* ko = dK ? dK + d0 * nn : nullptr;
+            CK(cudaLaunchKernelEx(&cfg, k_sym_reduce, jp, jo, ks, kr, ko, nd, n, grid, kslots));
+        }
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[2][1], ctx->stream));
+    *done = true;
+    return TUNA_OK;
+}
+
 template <int ND>
 static cudaError_t launch_jk_tma(tuna_ctx* ctx, const double* P, double* J, double* Kslot, int* Krow, int n, int r, int R, int q, int nstage,
                                  int kslots, int grid, int threads, size_t smem) {
@@ -1142,6 +1433,11 @@ extern "C" int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, doubl
     const size_t nn = (size_t)n * n;
     const char* env_k = getenv("TUNA_B200_STORED_KERNEL");
     const bool want_tma = !(env_k && std::string(env_k) == "simple");
+    if (!env_k || std::string(env_k) == "sym") {
+        bool done = false;
+        if ((rc = jk_stored_sym(ctx, nD, dP, dJ, dK, &done))) return rc;
+        if (done) return TUNA_OK;
+    }
     if (want_tma && (n % 2 == 0) && n >= 8) {
         // ---- TMA-streamed persistent kernel (16-byte alignment of every row tile needs an even n) ----
         const int r = std::max(1, 512 / n);
