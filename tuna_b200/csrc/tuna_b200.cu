@@ -1585,6 +1585,32 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
         const int avail = SHELL_SMEM_DOUBLES - shell_fixed_doubles(ctx->stab, La, Lb, Lc, Ld, nD);     // shrink the chunks for big classes
         if (itb + sb + 2 > avail) { itb = std::max(64, (avail - 2) / 2); sb = std::max(64, avail - 2 - itb); }
         build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb);
+        // Occupancy tier: a class whose single-quartet slice lands between half and all of the SM's shared memory runs ONE 8-warp CTA
+        // per SM (21 % issue utilisation measured); if splitting the bra z rows into two chunks brings the slice under half, two CTAs
+        // fit (34 %) at the price of running the chunk-independent phases 0-2 twice.
+        const char* et = getenv("TUNA_B200_TIER2");
+        if (!(et && atoi(et) == 0)) {
+            auto slice_doubles = [&](const ClassTablesHost& C) {
+                ShellJob Jt;
+                Jt.La = La; Jt.Lb = Lb; Jt.Lc = Lc; Jt.Ld = Ld;
+                Jt.ct.smax_rows = C.smax_rows; Jt.ct.itmax = C.itmax; Jt.ct.nout = C.nout;
+                shell_job_layout(Jt, nD);
+                return Jt.total;
+            };
+            const int tier2 = (225 * 1024 / 2 - 1024 - 64) / 8;            // doubles per CTA so that two CTAs (+1 KB reserved each) fit
+            const int t0 = slice_doubles(E.host);
+            if (t0 > tier2) {
+                const int NGZ = (Lc + 1) * (Ld + 1), NS = (La + Lb + Lc + Ld) / 2 + 1;
+                const int nch0 = (int)E.host.chunk_bz0.size() - 1, nint0 = E.host.nint;
+                bool found = false;
+                for (int want = 2; want <= std::min(4, nch0 + 2) && !found; ++want)        // balanced cuts, fewest chunks first
+                    for (int pct = 100 / want + 2; pct <= 100 / want + 30 / want + 2 && !found; pct += 3) {      // integrals per bra z row are not uniform
+                        ClassTablesHost trial;
+                        build_class_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, (nint0 * pct) / 100), (La + 1) * (Lb + 1) * NGZ * NS);
+                        if ((int)trial.chunk_bz0.size() - 1 == want && slice_doubles(trial) <= tier2) { E.host = trial; found = true; }
+                    }
+            }
+        }
     }
     const ClassTablesHost& C = E.host;
     size_t total = 0;
