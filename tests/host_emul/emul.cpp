@@ -76,6 +76,8 @@ struct HostPolicy {
     static void atomic_add(double* p, double v) { *p += v; }
 };
 
+static double* g_fill_out = nullptr;      // non-null: the driver below runs the engine in fill mode into this dense tensor
+
 extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
                              const double* ceff, int nD, const double* P, double* Jout, double* Kout, double tau, long long* stats) {
     HostBasis B = make_basis(ncart, oz, lmn, nprim, off, exps, ceff);
@@ -111,13 +113,14 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
     ShellData D;
     D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
     D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data();
+    D.eri_out = g_fill_out; D.fnorm = S.fnorm.data();
     long long nitems_total = 0, nskipped = 0;
     const int ncls = (int)S.classes.size();
     for (int cb = 0; cb < ncls; ++cb)
         for (int ck = 0; ck <= cb; ++ck) {
             ShellJob J;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
-            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.dbg_skip = 0; J.chunk = 4;
+            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.dbg_skip = 0; J.chunk = 4; J.fill = g_fill_out ? 1 : 0;
             J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
             std::vector<long long> prefix;
             J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
@@ -165,4 +168,14 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
             }
     if (stats) { stats[0] = (long long)S.shells.size(); stats[1] = (long long)S.pairA.size(); stats[2] = nitems_total; stats[3] = nskipped; stats[4] = ncls; }
     return 0;
+}
+
+// Dense Cartesian tensor through the shell engine's fill mode (out must be zero-initialised, ncart^4 doubles).
+extern "C" int emul_fill_shell(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
+                               const double* ceff, double* out) {
+    std::vector<double> P((size_t)ncart * ncart, 0.0), Jd((size_t)ncart * ncart), Kd((size_t)ncart * ncart);
+    g_fill_out = out;
+    const int rc = emul_jk_shell(ncart, oz, lmn, nprim, off, exps, ceff, 1, P.data(), Jd.data(), Kd.data(), 0.0, nullptr);
+    g_fill_out = nullptr;
+    return rc;
 }

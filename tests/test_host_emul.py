@@ -107,3 +107,26 @@ def test_shell_engine_h_shells(emul, oracle):
                             K.ctypes.data_as(dp), ctypes.c_double(0.0), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
     assert rc == 0 and stats[0] == 7
     assert np.abs(J[0] - oracle.coulomb(P[0], E)).max() < 1e-11 and np.abs(K[0] - oracle.exchange(P[0], E)).max() < 1e-11
+
+
+@pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "et100"])
+def test_shell_engine_fill_mode_vs_oracle(emul, oracle, name):
+    """Fill mode of the shell engine (dense Cartesian tensor for stored mode): element-wise against the oracle, exact zeros for
+    parity-forbidden entries, exact 8-fold symmetry (canonical quartets are scattered to their eight images)."""
+    g = load_golden(name)
+    fb = oracle_basis(oracle, g)
+    n = fb.ncart
+    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    oz = np.ascontiguousarray(fb.origins[:, 2])
+    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
+    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
+    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
+    out = np.zeros((n,) * 4)
+    rc = emul.emul_fill_shell(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                              fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert rc == 0
+    ref = oracle.eri_fill(fb)
+    assert np.all(np.abs(out - ref) <= np.maximum(1e-12, 1e-13 * np.abs(ref)))
+    assert np.array_equal(out == 0.0, ref == 0.0)
+    assert np.array_equal(out, out.transpose(1, 0, 2, 3)) and np.array_equal(out, out.transpose(0, 1, 3, 2)) and np.array_equal(out, out.transpose(2, 3, 0, 1))

@@ -185,8 +185,8 @@ inline long long build_item_prefix(const ShellSystem& S, int cb, int ck, double 
 struct ClassTablesHost {
     int La, Lb, Lc, Ld;
     int nout = 0, nk = 0, itmax = 0, smax_rows = 0, nint = 0;
-    std::vector<int> chunk_bz0, chunk_e0, chunk_s0, bz_list;
-    std::vector<unsigned> p4, p5ptr, p5term, p5off, t_rt, t_xy, t_u, t_s;
+    std::vector<int> chunk_bz0, chunk_e0, chunk_s0, chunk_f0, bz_list;
+    std::vector<unsigned> p4, p5ptr, p5term, p5off, p6, t_rt, t_xy, t_u, t_s;
     std::vector<unsigned short> pmap, omap, jst_list;
     std::vector<unsigned> jst_ptr, jflush;
     long long p5real = 0;             // digestion terms before padding (table statistics)
@@ -404,6 +404,17 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
                     pfq[ch].push_back({slot_perm[C.chunk_e0[ch] + slot_of[key]], bidx[q.a * ncB + q.b], gidx[q.c * ncD + q.d]});
                 }
     }
+    // fill list (dense-tensor mode): every parity-allowed component quartet of the chunk with the It slot it reads
+    C.chunk_f0.push_back(0);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        for (int bi = C.chunk_bz0[ch]; bi < C.chunk_bz0[ch + 1]; ++bi)
+            for (const Quartet& q : per_bz[bi]) {
+                const unsigned it = (unsigned)slot_perm[C.chunk_e0[ch] + slot_of[pf_key(bi, q)]];
+                C.p6.push_back(it | (unsigned)q.a << 16 | (unsigned)q.b << 21 | (unsigned)q.c << 26);
+                C.p6.push_back((unsigned)q.d);
+            }
+        C.chunk_f0.push_back((int)C.p6.size() / 2);
+    }
     std::vector<long long> tot_terms(C.nout, 0);
     for (const auto& v : per_bz)
         for (const Quartet& q : v) {
@@ -472,6 +483,7 @@ inline ClassTablesDev class_tables_view(const ClassTablesHost& C, PtrOf ptr) {
     V.jst_ptr = ptr(C.jst_ptr); V.jst_list = ptr(C.jst_list); V.jflush = ptr(C.jflush);
     V.n_rt = (int)C.t_rt.size(); V.n_xy = (int)C.t_xy.size(); V.n_u = (int)C.t_u.size() / 2;
     V.t_rt = ptr(C.t_rt); V.t_xy = ptr(C.t_xy); V.t_u = ptr(C.t_u); V.t_s = ptr(C.t_s);
+    V.p6 = ptr(C.p6); V.chunk_f0 = ptr(C.chunk_f0);
     return V;
 }
 

@@ -98,6 +98,10 @@ struct ClassTablesDev {
     int n_rt, n_xy, n_u;
     const unsigned* t_rt; const unsigned* t_xy; const unsigned* t_u; const unsigned* t_s;
     const int* chunk_s0;                    // [nchunk+1] first t_s entry of each chunk
+    // dense-tensor fill (stored mode): the parity-allowed component quartets of every chunk,
+    //   p6[2i] = It slot | a << 16 | b << 21 | c << 26,  p6[2i+1] = d   (component indices inside the four shells)
+    const unsigned* p6;
+    const int* chunk_f0;                    // [nchunk+1] first p6 entry of each chunk
 };
 
 // One launch = one (bra pair class, ket pair class) job.
@@ -111,6 +115,7 @@ struct ShellJob {
     int chunk;                      // consecutive items per CTA work unit / sharding unit
     long long nitems;
     int dbg_skip;                   // development aid: bit k set -> phase k is skipped (timing experiments only; 0 in production)
+    int fill;                       // 1: no digestion - the integrals of every chunk are scattered into the dense tensor D.eri_out
     double uniq[6];                 // unique AO quartets per shell quartet by degeneracy case (ClassTablesHost::uniq)
     ClassTablesDev ct;
     // shared-memory layout of one group (offsets in doubles)
@@ -125,6 +130,8 @@ struct ShellData {
     const int* sh_ao;                       // [shell * SH_NCMAX + component] -> AO (Cartesian basis function) index
     const double* boys;
     const double* herm;
+    double* eri_out;                        // fill mode: dense Cartesian tensor [ncart^4] (zero-initialised by the caller)
+    const double* fnorm;                    // fill mode: per-component norms (the engine works with unnormalised components)
 };
 
 inline void shell_job_layout(ShellJob& J, int nD) {
@@ -211,12 +218,14 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
 #pragma unroll
     for (int q = 0; q < NB; ++q) if (qa < 0 && active[q]) qa = q;
     const bool any = qa >= 0;
+    const bool fill = J.fill != 0;
+    const int skip = J.dbg_skip | (fill ? (32 | 64 | 128) : 0);      // fill mode: no density staging, digestion or J/K flush
     const double* recA[NB]; const double* recC[NB];
     double w[NB];
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
         const int ab = any ? (active[q] ? ABin[q] : ABin[qa]) : 0, cd = any ? (active[q] ? CDin[q] : CDin[qa]) : 0;
-        w[q] = active[q] ? win[q] : 0.0;
+        w[q] = active[q] ? (fill ? 1.0 : win[q]) : 0.0;
         recA[q] = D.rec + D.pair_rec[ab]; recC[q] = D.rec + D.pair_rec[cd];
         if (any) {
             const int sh[4] = {D.pairA[ab], D.pairB[ab], D.pairA[cd], D.pairB[cd]};
@@ -225,7 +234,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
         }
     }
     Pol::sync();
-    if (any && !(J.dbg_skip & 64)) {
+    if (any && !(skip & 64)) {
         // stage the density blocks and clear the accumulators
         for (int dn = 0; dn < nD; ++dn) {
             const double* P = Pf + dn * nn;
@@ -283,7 +292,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                     const double* rA = recA[q] + (size_t)ia * recAsz;
                     const double* rC = recC[q] + (size_t)ic * recCsz;
                     pref[q] = 0.0;
-                    if (!any || (J.dbg_skip & 1)) continue;
+                    if (!any || (skip & 1)) continue;
                     const double p = rA[0], qq = rC[0], pq = p + qq;
                     pref[q] = w[q] * rA[2] * rC[2] * 34.986836655249725 / (p * qq * sqrt(pq));
                     if (ic == 0) { TUNA_LANES(x, recAsz) RAq[(size_t)x * NB + q] = rA[x]; }
@@ -294,7 +303,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                         RCq[(size_t)x * NB + q] = v;
                     }
                 }
-                if (any && !(J.dbg_skip & 1)) {
+                if (any && !(skip & 1)) {
                     TUNA_LANES(x, NB * (Ltot + 1)) {
                         const int q = x / (Ltot + 1), m = x - q * (Ltot + 1);
                         const double* rA = recA[0] + (size_t)ia * recAsz;
@@ -311,7 +320,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                 }
                 Pol::sync();
                 // ---- phase 1: R^n_w (closed form) and the x/y convolution table ----------------------------------
-                if (any && !(J.dbg_skip & 2)) {
+                if (any && !(skip & 2)) {
                     TUNA_LANES(i, CT.n_rt) {
                         const unsigned e = CT.t_rt[i];
                         const int wv = (e >> 16) & 255, n = e >> 24;
@@ -349,7 +358,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                 }
                 Pol::sync();
                 // ---- phase 2: U[v][gz][n] = sum_phi (-1)^phi Ez_CD[gz][phi] R^n_{v+phi} ---------------------------
-                if (any && !(J.dbg_skip & 4)) {
+                if (any && !(skip & 4)) {
                     TUNA_LANES(i, CT.n_u) {
                         const unsigned e0w = CT.t_u[2 * i], e1w = CT.t_u[2 * i + 1];
                         const int lz34 = e1w >> 16;
@@ -368,7 +377,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                 }
                 Pol::sync();
                 // ---- phase 3: S[row][gz][n] = sum_v Ez_AB[az][bz][v] U[v][gz][n] for the chunk's bra z rows ----------
-                if (any && !(J.dbg_skip & 8)) {
+                if (any && !(skip & 8)) {
                     const int ustride = NGZ * NS;
                     for (int i = CT.chunk_s0[ch] + Pol::lane(); i < CT.chunk_s0[ch + 1]; i += Pol::G) {
                         const unsigned e0w = CT.t_s[2 * i], e1w = CT.t_s[2 * i + 1];
@@ -389,7 +398,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                 Pol::sync();
                 // ---- phase 4: table-driven integral assembly, accumulated over primitive quartets; the table entry of the
                 // lane's next integral is fetched while the current one is assembled -------------------------------------
-                if (any && !(J.dbg_skip & 16)) {
+                if (any && !(skip & 16)) {
                     const uint2* p4 = reinterpret_cast<const uint2*>(CT.p4) + e0;
                     int e = Pol::lane();
                     uint2 nxt = make_uint2(0u, 0u);
@@ -430,7 +439,39 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
         // consecutive accumulators are stored transposed (term quad t of accumulator o at (t * 32 + (o & 31))), padded to the
         // longest list of the block with dummy terms that read the zero slot It[itmax]: one coalesced 16-byte load per lane
         // brings four terms, and the next quad is in flight while the current one is digested.
-        if (any && !(J.dbg_skip & 32)) {
+        if (any && fill) {
+            // ---- fill mode: scatter the chunk's integrals (normalised) to the eight images of every CANONICAL AO quartet
+            // (i >= j, k >= l, ij >= kl when shells coincide), so the dense tensor is exactly 8-fold symmetric and deterministic
+            const int f0 = CT.chunk_f0[ch], nf = CT.chunk_f0[ch + 1] - f0;
+            const uint2* fl = reinterpret_cast<const uint2*>(CT.p6) + f0;
+            const int ncB = (Lb + 1) * (Lb + 2) / 2, ncD = (Ld + 1) * (Ld + 2) / 2;
+            const size_t n1 = (size_t)ncart, n2 = n1 * n1, n3 = n2 * n1;
+            bool sameAB[NB], sameCD[NB], diag[NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const int ab = active[q] ? ABin[q] : 0, cd = active[q] ? CDin[q] : 0;
+                sameAB[q] = D.pairA[ab] == D.pairB[ab]; sameCD[q] = D.pairA[cd] == D.pairB[cd]; diag[q] = ab == cd;
+            }
+            TUNA_LANES(x, nf) {
+                const uint2 ent = fl[x];
+                const int slot = ent.x & 0xffffu, a = (ent.x >> 16) & 31, b = (ent.x >> 21) & 31, c = (ent.x >> 26) & 31, d = (int)ent.y;
+                const QVec<NB> v = qld<NB>(Itq + (size_t)slot * NB);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    if (!active[q]) continue;
+                    if ((sameAB[q] && b > a) || (sameCD[q] && d > c) || (diag[q] && c * ncD + d > a * ncB + b)) continue;
+                    const int* ao = aoq + q * 4 * aos;
+                    const size_t i = ao[a], j = ao[aos + b], k = ao[2 * aos + c], l = ao[3 * aos + d];
+                    const double val = v.v[q] * D.fnorm[i] * D.fnorm[j] * D.fnorm[k] * D.fnorm[l];
+                    double* E = D.eri_out;
+                    E[i * n3 + j * n2 + k * n1 + l] = val; E[j * n3 + i * n2 + k * n1 + l] = val;
+                    E[i * n3 + j * n2 + l * n1 + k] = val; E[j * n3 + i * n2 + l * n1 + k] = val;
+                    E[k * n3 + l * n2 + i * n1 + j] = val; E[l * n3 + k * n2 + i * n1 + j] = val;
+                    E[k * n3 + l * n2 + j * n1 + i] = val; E[l * n3 + k * n2 + j * n1 + i] = val;
+                }
+            }
+        }
+        if (any && !(skip & 32)) {
             const unsigned* ptr = CT.p5ptr + (size_t)ch * (nblk + 1);
             const uint4* term = reinterpret_cast<const uint4*>(CT.p5term + CT.p5off[ch]);
             TUNA_LANES(o, nout) {
@@ -468,7 +509,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
         Pol::sync();
     }
     // ---- flush the shell blocks: one atomic per block entry per shell quartet ---------------------------------------
-    if (any && !(J.dbg_skip & 128)) {
+    if (any && !(skip & 128)) {
         for (int dn = 0; dn < nD; ++dn) {
             TUNA_LANES(x, nout) {
                 const unsigned m = CT.omap[x];

@@ -73,6 +73,8 @@ struct tuna_ctx {
     double* d_P = nullptr; double* d_J = nullptr; double* d_K = nullptr;   // nD * n^2 staging (spherical)
     double* d_Pc = nullptr; double* d_Jc = nullptr; double* d_Kc = nullptr; double* d_tmp = nullptr;  // Cartesian
     double* d_Kpart = nullptr;
+    double* d_fnorm = nullptr;        // per-component norms (shell engine fill mode)
+    int shell_fill = 0;               // the cached job list was built for fill mode
     size_t cap_mat = 0, cap_cart = 0, cap_kpart = 0;
     double* h_pin = nullptr; size_t cap_pin = 0;
     unsigned long long* d_scalars = nullptr;   // [0] max|P| bits, [1] evaluated-quartet counter
@@ -116,6 +118,7 @@ struct tuna_ctx {
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 
 static int check_pair_symmetry(tuna_ctx* ctx);
+static int shell_fill(tuna_ctx* ctx);
 
 template <typename T>
 static int dev_alloc(tuna_ctx* ctx, T** p, size_t count) {
@@ -219,21 +222,41 @@ __global__ void k_eri_single(const double* __restrict__ ppA, int nA, int clsA, c
 }
 
 // out[o, p, r] = sum_e val[e] * in[o, col[e], r] over the CSR row p: one index of a tensor rotated by a sparse matrix.
-__global__ void __launch_bounds__(256) k_rotate_axis(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ rowptr,
-                                                     const int* __restrict__ col, const double* __restrict__ val, int64_t outer, int n_in,
-                                                     int n_out, int64_t inner) {
-    const int64_t total = outer * n_out * inner;
-    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = x % inner;
-        const int64_t op = x / inner;
-        const int p = (int)(op % n_out);
-        const int64_t o = op / n_out;
-        const double* src = in + o * n_in * inner + r;
+// Two index mappings without 64-bit divisions in the element loop:
+//   k_rotate_axis_wide  (inner >= 128): one (o, p) row per blockIdx.x, threads stride over r -> coalesced loads and stores;
+//   k_rotate_axis_narrow (inner < 128): one o per blockIdx.x, threads stride over the contiguous (p, r) block of that o.
+__global__ void __launch_bounds__(256) k_rotate_axis_wide(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ rowptr,
+                                                          const int* __restrict__ col, const double* __restrict__ val, int n_in, int n_out,
+                                                          int64_t inner) {
+    const int64_t op = blockIdx.x;
+    const int p = (int)(op % n_out);
+    const int64_t o = op / n_out;
+    const int e0 = rowptr[p], e1 = rowptr[p + 1];
+    const double* src = in + o * n_in * inner;
+    double* dst = out + op * inner;
+    for (int64_t r = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; r < inner; r += (int64_t)gridDim.y * blockDim.x) {
         double s = 0.0;
-        for (int e = rowptr[p]; e < rowptr[p + 1]; ++e) s = fma(val[e], src[(int64_t)col[e] * inner], s);
-        out[x] = s;
+        for (int e = e0; e < e1; ++e) s = fma(val[e], src[(int64_t)col[e] * inner + r], s);
+        dst[r] = s;
     }
 }
+
+__global__ void __launch_bounds__(256) k_rotate_axis_narrow(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ rowptr,
+                                                            const int* __restrict__ col, const double* __restrict__ val, int64_t outer, int n_in,
+                                                            int n_out, int inner) {
+    const int block_elems = n_out * inner;
+    for (int64_t o = blockIdx.x; o < outer; o += gridDim.x) {
+        const double* src = in + o * n_in * inner;
+        double* dst = out + o * block_elems;
+        for (int t = threadIdx.x; t < block_elems; t += blockDim.x) {
+            const int p = t / inner, r = t - p * inner;
+            double s = 0.0;
+            for (int e = rowptr[p]; e < rowptr[p + 1]; ++e) s = fma(val[e], src[col[e] * inner + r], s);
+            dst[t] = s;
+        }
+    }
+}
+
 
 // Fused stored-mode J+K.  Block (chunk c, row i) owns the contiguous slabs E[i, l, :, :], l in the chunk.
 // Thread (rt, j): j = tid % n fixed, k = rt, rt + r, ...;  one coalesced read of each element serves
@@ -967,7 +990,16 @@ static int build_csr(tuna_ctx* ctx, CsrDev& M, int rows, int cols, const std::ve
 static int rotate(tuna_ctx* ctx, const CsrDev& M, const double* in, double* out, int64_t outer, int64_t inner) {
     const int64_t total = outer * M.rows * inner;
     if (total == 0) return TUNA_OK;
-    k_rotate_axis<<<grid_for(ctx, total, 256, 16), 256, 0, ctx->stream>>>(in, out, M.rowptr, M.col, M.val, outer, M.cols, M.rows, inner);
+    if (inner >= 128) {
+        const int64_t rows = outer * M.rows;
+        if (rows > 0x7fffffffLL) FAIL(TUNA_ERR_ARG, "rotate: tensor too large");
+        const int ytiles = (int)std::min<int64_t>((inner + 1023) / 1024, 65535);       // up to four elements per thread
+        k_rotate_axis_wide<<<dim3((unsigned)rows, (unsigned)ytiles), 256, 0, ctx->stream>>>(in, out, M.rowptr, M.col, M.val, M.cols, M.rows, inner);
+    } else {
+        const int threads = (int)std::min<int64_t>(256, ((int64_t)M.rows * inner + 31) / 32 * 32);
+        const int64_t blocks = std::min<int64_t>(outer, (int64_t)ctx->sm_count * 64);
+        k_rotate_axis_narrow<<<(unsigned)blocks, threads, 0, ctx->stream>>>(in, out, M.rowptr, M.col, M.val, outer, M.cols, M.rows, (int)inner);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return TUNA_OK;
@@ -1064,7 +1096,7 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     for (auto& kv : ctx->class_tabs) dev_free(&kv.second.blob);
     for (auto& g : ctx->groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
     dev_free(&ctx->d_pairA); dev_free(&ctx->d_pairB); dev_free(&ctx->d_pair_rec); dev_free(&ctx->d_rec);
-    dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_prefix); dev_free(&ctx->d_finv);
+    dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_prefix); dev_free(&ctx->d_finv); dev_free(&ctx->d_fnorm);
     dev_free(&ctx->d_eval);
     dev_free(&ctx->Uf.rowptr); dev_free(&ctx->Uf.col); dev_free(&ctx->Uf.val);
     dev_free(&ctx->Uft.rowptr); dev_free(&ctx->Uft.col); dev_free(&ctx->Uft.val);
@@ -1187,6 +1219,18 @@ int tuna_eri_fill_cart(tuna_ctx* ctx) {
     int rc;
     if ((rc = dev_alloc(ctx, &ctx->d_eri_cart, count))) return rc;
     CK(cudaMemsetAsync(ctx->d_eri_cart, 0, count * sizeof(double), ctx->stream));
+    // Shell-quartet engine in fill mode (Boys / R / convolution tables shared by all components of a shell quartet) when the basis
+    // groups into full shells; the per-component kernel otherwise (or with TUNA_B200_FILL_ENGINE=generic).
+    // The engine walks the primitive quartets of a shell quartet serially (four barriers each), so heavily contracted shells
+    // ((ss|ss) of cc-pVTZ: 4096 primitive quartets) stay with the per-component kernel, which spreads them over a warp.
+    const char* fe = getenv("TUNA_B200_FILL_ENGINE");
+    int max_nprim = 0;
+    for (const auto& sh : ctx->ss.shells) max_nprim = std::max(max_nprim, sh.nprim);
+    const bool want_shell = fe ? std::string(fe) == "shell" : max_nprim <= 2;
+    if (ctx->direct_engine == 1 && ctx->ss.ok && want_shell) {
+        if ((rc = shell_fill(ctx))) return rc;
+        return TUNA_OK;
+    }
     CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
     k_eri_fill<<<grid_for(ctx, ctx->task_begin[4], 128, 16), 128, 0, ctx->stream>>>(table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_eri_cart, ctx->ncart);
     ctx->launches++;
@@ -1219,22 +1263,22 @@ int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart) {
         ctx->eri_pair_sym = true;          // the fill scatters one value to all eight images
         return TUNA_OK;
     }
+    // Four single-index passes ping-ponging between two work buffers; every allocation happens before the timed region and nothing
+    // synchronises inside it (stream order is enough).  Without keep_cart the Cartesian tensor's own storage is the second buffer.
     if ((rc = dev_alloc(ctx, &t1, (size_t)(nb * nc * nc * nc)))) return rc;
-    if ((rc = rotate(ctx, ctx->U, ctx->d_eri_cart, t1, 1, nc * nc * nc))) { dev_free(&t1); return rc; }
-    if (!keep_cart) { CK(cudaStreamSynchronize(ctx->stream)); dev_free(&ctx->d_eri_cart); }
-    if ((rc = dev_alloc(ctx, &t2, (size_t)(nb * nb * nc * nc)))) { dev_free(&t1); return rc; }
-    if ((rc = rotate(ctx, ctx->U, t1, t2, nb, nc * nc))) { dev_free(&t1); dev_free(&t2); return rc; }
-    CK(cudaStreamSynchronize(ctx->stream));
-    dev_free(&t1);
-    if ((rc = dev_alloc(ctx, &t3, (size_t)(nb * nb * nb * nc)))) { dev_free(&t2); return rc; }
-    if ((rc = rotate(ctx, ctx->U, t2, t3, nb * nb, nc))) { dev_free(&t2); dev_free(&t3); return rc; }
-    CK(cudaStreamSynchronize(ctx->stream));
-    dev_free(&t2);
-    if ((rc = dev_alloc(ctx, &ctx->d_eri_sph, (size_t)(nb * nb * nb * nb)))) { dev_free(&t3); return rc; }
-    if ((rc = rotate(ctx, ctx->U, t3, ctx->d_eri_sph, nb * nb * nb, 1))) { dev_free(&t3); return rc; }
-    CK(cudaEventRecord(ctx->ev[1][1], ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    dev_free(&t3);
+    if (keep_cart && (rc = dev_alloc(ctx, &t2, (size_t)(nb * nb * nc * nc)))) { dev_free(&t1); return rc; }
+    if ((rc = dev_alloc(ctx, &ctx->d_eri_sph, (size_t)(nb * nb * nb * nb)))) { dev_free(&t1); dev_free(&t2); return rc; }
+    double* w2 = keep_cart ? t2 : ctx->d_eri_cart;
+    CK(cudaEventRecord(ctx->ev[1][0], ctx->stream));
+    rc = rotate(ctx, ctx->U, ctx->d_eri_cart, t1, 1, nc * nc * nc);
+    if (!rc) rc = rotate(ctx, ctx->U, t1, w2, nb, nc * nc);
+    if (!rc) rc = rotate(ctx, ctx->U, w2, t1, nb * nb, nc);
+    if (!rc) rc = rotate(ctx, ctx->U, t1, ctx->d_eri_sph, nb * nb * nb, 1);
+    if (!rc) { CK(cudaEventRecord(ctx->ev[1][1], ctx->stream)); }
+    cudaStreamSynchronize(ctx->stream);
+    dev_free(&t1); dev_free(&t2);
+    if (!keep_cart) dev_free(&ctx->d_eri_cart);
+    if (rc) { dev_free(&ctx->d_eri_sph); return rc; }
     ctx->n_stored = (int)nb;
     return check_pair_symmetry(ctx);
 }
@@ -1625,6 +1669,7 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
     const size_t o_omap = add(C.omap.data(), C.omap.size() * 2), o_rt = add(C.t_rt.data(), C.t_rt.size() * 4);
     const size_t o_xy = add(C.t_xy.data(), C.t_xy.size() * 4), o_u = add(C.t_u.data(), C.t_u.size() * 4), o_s = add(C.t_s.data(), C.t_s.size() * 4);
     const size_t o_jp = add(C.jst_ptr.data(), C.jst_ptr.size() * 4), o_jl = add(C.jst_list.data(), C.jst_list.size() * 2), o_jf = add(C.jflush.data(), C.jflush.size() * 4);
+    const size_t o_p6 = add(C.p6.data(), C.p6.size() * 4), o_f0 = add(C.chunk_f0.data(), C.chunk_f0.size() * 4);
     std::vector<unsigned char> host(total, 0);
     for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
     int rc;
@@ -1641,12 +1686,13 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
     V.t_s = (const unsigned*)(E.blob + o_s);
     V.njst = (int)C.jst_ptr.size() - 1; V.njfl = (int)C.jflush.size();
     V.jst_ptr = (const unsigned*)(E.blob + o_jp); V.jst_list = (const unsigned short*)(E.blob + o_jl); V.jflush = (const unsigned*)(E.blob + o_jf);
+    V.p6 = (const unsigned*)(E.blob + o_p6); V.chunk_f0 = (const int*)(E.blob + o_f0);
     *out = &E;
     return TUNA_OK;
 }
 
 // Build (or refresh for a new threshold) the shell-pair data and the job list of the shell-quartet engine.
-static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
+static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
     int rc;
     if (!ctx->shell_ready) {
         if ((rc = ensure_schwarz(ctx))) return rc;
@@ -1665,6 +1711,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
         if ((rc = dev_alloc(ctx, &ctx->d_rec, S.rec.size()))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_sh_ao, S.sh_ao.size()))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_finv, (size_t)ctx->ncart))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_fnorm, (size_t)ctx->ncart))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_eval, (size_t)1))) return rc;
         std::vector<int> lists;
         ctx->class_list_off.clear();
@@ -1680,12 +1727,14 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
         CK(cudaMemcpyAsync(ctx->d_sh_ao, S.sh_ao.data(), S.sh_ao.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_class_lists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_finv, finv.data(), finv.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_fnorm, S.fnorm.data(), (size_t)ctx->ncart * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->shell_ready = true;
         ctx->shell_tau = -1.0;
     }
-    if (ctx->shell_tau != tau || ctx->shell_nD != nD || ctx->jobs.empty()) {
+    if (ctx->shell_tau != tau || ctx->shell_nD != nD || ctx->shell_fill != fill || ctx->jobs.empty()) {
         ctx->shell_nD = nD;
+        ctx->shell_fill = fill;
         const ShellSystem& S = ctx->ss;
         const int ncls = (int)S.classes.size();
         std::vector<long long> all_prefix;
@@ -1702,6 +1751,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD) {
                 J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
                 J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
                 { const char* dbg = getenv("TUNA_B200_DBG_SKIP"); J.dbg_skip = dbg ? atoi(dbg) : 0; }
+                J.fill = fill;
                 std::vector<long long> prefix;
                 J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
                 if (J.nitems == 0) continue;
@@ -1813,11 +1863,12 @@ static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::LaunchGroup& lg, 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    long long blocks = (lg.nunits - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // units owned by this rank
+    const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;      // the dense fill is not sharded
+    long long blocks = (lg.nunits - srank + sn - 1) / sn;       // units owned by this rank
     if (blocks <= 0) return cudaSuccess;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * lg.ctas_per_sm);
     k_shell_jk<GG, NB><<<(int)blocks, lg.threads, lg.smem, stream>>>(lg.d_jobs, lg.d_unit_prefix, lg.njobs, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau,
-                                                                 ctx->d_scalars, ctx->d_eval, ctx->shard_rank, ctx->shard_n, lg.job_slot_off);
+                                                                 ctx->d_scalars, ctx->d_eval, srank, sn, lg.job_slot_off);
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -1832,13 +1883,88 @@ static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, 
         attr_set = true;
     }
     const long long nchunk = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
-    long long blocks = (nchunk - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // chunks owned by this rank
+    const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;
+    long long blocks = (nchunk - srank + sn - 1) / sn;       // chunks owned by this rank
     if (blocks <= 0) return cudaSuccess;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
     k_shell_jk_one<GG, NB><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
-                                                                     ctx->shard_rank, ctx->shard_n);
+                                                                     srank, sn);
     ctx->launches++;
     return cudaGetLastError();
+}
+
+// All class jobs of the cached job list: large ones as individual launches, the rest as grouped persistent launches, spread over
+// the auxiliary streams and joined back into ctx->stream.  eri_out != nullptr selects the dense-tensor fill (job list built with fill = 1).
+static int launch_shell_jobs(tuna_ctx* ctx, int nD, const double* Pc, const double* Psym, double* Jc, double* Kc, double tau, double* eri_out) {
+    {
+        ShellData D;
+        D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
+        D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
+        D.eri_out = eri_out; D.fnorm = ctx->d_fnorm;
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
+        int jn = 0;
+        for (const auto& jh : ctx->jobs) {
+            if (!jh.own_launch) continue;
+            cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
+            cudaError_t e;
+#define TUNA_ONE(GV) (jh.nb == 4 ? launch_shell_one<GV, 4>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
+                      : jh.nb == 2 ? launch_shell_one<GV, 2>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
+                                   : launch_shell_one<GV, 1>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st))
+            switch (jh.G) {
+                case 1: e = TUNA_ONE(1); break;
+                case 2: e = TUNA_ONE(2); break;
+                case 4: e = TUNA_ONE(4); break;
+                case 8: e = TUNA_ONE(8); break;
+                case 16: e = TUNA_ONE(16); break;
+                case 32: e = TUNA_ONE(32); break;
+                case 64: e = TUNA_ONE(64); break;
+                case 128: e = TUNA_ONE(128); break;
+                default: e = TUNA_ONE(256); break;
+            }
+#undef TUNA_ONE
+            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk_one launch: ") + cudaGetErrorString(e));
+        }
+        for (const auto& lg : ctx->groups) {
+            cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
+            cudaError_t e;
+#define TUNA_GRP(GV) (lg.nb == 4 ? launch_shell<GV, 4>(ctx, lg, D, nD, Pc, Psym, Jc, Kc, tau, st) \
+                      : lg.nb == 2 ? launch_shell<GV, 2>(ctx, lg, D, nD, Pc, Psym, Jc, Kc, tau, st) \
+                                   : launch_shell<GV, 1>(ctx, lg, D, nD, Pc, Psym, Jc, Kc, tau, st))
+            switch (lg.G) {
+                case 1: e = TUNA_GRP(1); break;
+                case 2: e = TUNA_GRP(2); break;
+                case 4: e = TUNA_GRP(4); break;
+                case 8: e = TUNA_GRP(8); break;
+                case 16: e = TUNA_GRP(16); break;
+                case 32: e = TUNA_GRP(32); break;
+                case 64: e = TUNA_GRP(64); break;
+                case 128: e = TUNA_GRP(128); break;
+                default: e = TUNA_GRP(256); break;
+            }
+#undef TUNA_GRP
+            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk launch: ") + cudaGetErrorString(e));
+        }
+        for (int a = 0; a < tuna_ctx::NAUX; ++a) {
+            CK(cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[a], 0));
+        }
+    }
+    return TUNA_OK;
+}
+
+// Dense Cartesian tensor through the shell-quartet engine: every shell quartet once (no screening), canonical AO quartets
+// scattered to their eight images; ctx->d_eri_cart is allocated and zeroed by the caller (parity-forbidden entries stay exact zeros).
+static int shell_fill(tuna_ctx* ctx) {
+    int rc;
+    if ((rc = ensure_schwarz(ctx))) return rc;
+    if ((rc = ensure_shell(ctx, 0.0, 1, 1))) return rc;
+    CK(cudaMemsetAsync(ctx->d_scalars, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_eval, 0, sizeof(double), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
+    if ((rc = launch_shell_jobs(ctx, 1, nullptr, nullptr, nullptr, nullptr, 0.0, ctx->d_eri_cart))) return rc;
+    CK(cudaEventRecord(ctx->ev[0][1], ctx->stream));
+    return TUNA_OK;
 }
 
 // Core of direct mode on DEVICE buffers: nD densities, bit d of anti_mask marks density d as antisymmetric
@@ -1896,57 +2022,7 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     if (shell) {
         k_add_transpose_signed<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_Pc, ctx->d_tmp, nD, nc, 0u);   // Psym = P + P^T
         ctx->launches++;
-        ShellData D;
-        D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
-        D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
-        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
-        int jn = 0;
-        for (const auto& jh : ctx->jobs) {
-            if (!jh.own_launch) continue;
-            cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
-            cudaError_t e;
-#define TUNA_ONE(GV) (jh.nb == 4 ? launch_shell_one<GV, 4>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
-                      : jh.nb == 2 ? launch_shell_one<GV, 2>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
-                                   : launch_shell_one<GV, 1>(ctx, jh, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st))
-            switch (jh.G) {
-                case 1: e = TUNA_ONE(1); break;
-                case 2: e = TUNA_ONE(2); break;
-                case 4: e = TUNA_ONE(4); break;
-                case 8: e = TUNA_ONE(8); break;
-                case 16: e = TUNA_ONE(16); break;
-                case 32: e = TUNA_ONE(32); break;
-                case 64: e = TUNA_ONE(64); break;
-                case 128: e = TUNA_ONE(128); break;
-                default: e = TUNA_ONE(256); break;
-            }
-#undef TUNA_ONE
-            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk_one launch: ") + cudaGetErrorString(e));
-        }
-        for (const auto& lg : ctx->groups) {
-            cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
-            cudaError_t e;
-#define TUNA_GRP(GV) (lg.nb == 4 ? launch_shell<GV, 4>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
-                      : lg.nb == 2 ? launch_shell<GV, 2>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st) \
-                                   : launch_shell<GV, 1>(ctx, lg, D, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, st))
-            switch (lg.G) {
-                case 1: e = TUNA_GRP(1); break;
-                case 2: e = TUNA_GRP(2); break;
-                case 4: e = TUNA_GRP(4); break;
-                case 8: e = TUNA_GRP(8); break;
-                case 16: e = TUNA_GRP(16); break;
-                case 32: e = TUNA_GRP(32); break;
-                case 64: e = TUNA_GRP(64); break;
-                case 128: e = TUNA_GRP(128); break;
-                default: e = TUNA_GRP(256); break;
-            }
-#undef TUNA_GRP
-            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk launch: ") + cudaGetErrorString(e));
-        }
-        for (int a = 0; a < tuna_ctx::NAUX; ++a) {
-            CK(cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[a], 0));
-        }
+        if ((rc = launch_shell_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, nullptr))) return rc;
     } else {
         k_jk_direct<<<grid_for(ctx, ctx->task_begin[4] / ctx->shard_n + 1, 128, 16), 128, 0, ctx->stream>>>(
             table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, nc, nD, tau, ctx->d_scalars, ctx->d_scalars + 1,
