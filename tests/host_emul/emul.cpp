@@ -127,7 +127,7 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
             J.item_prefix = prefix.data(); J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
             ClassTablesHost CTH;
             const char* eb = getenv("TUNA_EMUL_IT_BUDGET");      // small budgets force the multi-chunk path in tests
-            if (eb) build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH, atoi(eb), atoi(eb)); else build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH);
+            if (eb) build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH, atoi(eb), atoi(eb), g_fill_out != nullptr); else build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH, SH_IT_BUDGET, SH_S_BUDGET, g_fill_out != nullptr);
             J.ct = class_tables_view(CTH, HostPtrOf());
             shell_job_layout(J, nD);
             const char* enb = getenv("TUNA_EMUL_NB");             // quartets batched per group (1, 2 or 4)

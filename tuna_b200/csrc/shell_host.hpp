@@ -199,7 +199,7 @@ constexpr int SH_IT_BUDGET = 6144;    // doubles of shared memory for the integr
 constexpr int SH_S_BUDGET = 6144;     // doubles for the S slice of a chunk
 
 inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld, ClassTablesHost& C, int it_budget = SH_IT_BUDGET,
-                               int s_budget = SH_S_BUDGET) {
+                               int s_budget = SH_S_BUDGET, bool with_fill = false) {
     C = ClassTablesHost();
     C.La = La; C.Lb = Lb; C.Lc = Lc; C.Ld = Ld;
     const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = Ltot / 2 + 1, NGZ = (Lc + 1) * (Ld + 1);
@@ -407,7 +407,7 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
     // fill list (dense-tensor mode): every parity-allowed component quartet of the chunk with the It slot it reads
     C.chunk_f0.push_back(0);
     for (int ch = 0; ch < nchunk; ++ch) {
-        for (int bi = C.chunk_bz0[ch]; bi < C.chunk_bz0[ch + 1]; ++bi)
+        for (int bi = C.chunk_bz0[ch]; with_fill && bi < C.chunk_bz0[ch + 1]; ++bi)
             for (const Quartet& q : per_bz[bi]) {
                 const unsigned it = (unsigned)slot_perm[C.chunk_e0[ch] + slot_of[pf_key(bi, q)]];
                 C.p6.push_back(it | (unsigned)q.a << 16 | (unsigned)q.b << 21 | (unsigned)q.c << 26);

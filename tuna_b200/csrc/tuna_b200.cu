@@ -1221,12 +1221,12 @@ int tuna_eri_fill_cart(tuna_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->d_eri_cart, 0, count * sizeof(double), ctx->stream));
     // Shell-quartet engine in fill mode (Boys / R / convolution tables shared by all components of a shell quartet) when the basis
     // groups into full shells; the per-component kernel otherwise (or with TUNA_B200_FILL_ENGINE=generic).
-    // The engine walks the primitive quartets of a shell quartet serially (four barriers each), so heavily contracted shells
-    // ((ss|ss) of cc-pVTZ: 4096 primitive quartets) stay with the per-component kernel, which spreads them over a warp.
+    // (The engine also walks the primitive quartets of a shell quartet serially, four barriers each: heavily contracted shells such
+    // as (ss|ss) of cc-pVTZ with 4096 primitive quartets are better served by the per-component kernel, which spreads them over a warp.)
     const char* fe = getenv("TUNA_B200_FILL_ENGINE");
-    int max_nprim = 0;
-    for (const auto& sh : ctx->ss.shells) max_nprim = std::max(max_nprim, sh.nprim);
-    const bool want_shell = fe ? std::string(fe) == "shell" : max_nprim <= 2;
+    // Measured (B200): the fill is bound by the scattered 8-byte stores of the eight images, not by the integral math - ET100 1.42 ms
+    // (engine) vs 1.39 ms (per-component kernel), N2/cc-pVTZ 15.8 vs 3.8 ms - so the per-component kernel stays the default.
+    const bool want_shell = fe && std::string(fe) == "shell";
     if (ctx->direct_engine == 1 && ctx->ss.ok && want_shell) {
         if ((rc = shell_fill(ctx))) return rc;
         return TUNA_OK;
@@ -1617,8 +1617,8 @@ static int shell_fixed_doubles(const ShellTab& T, int La, int Lb, int Lc, int Ld
 }
 constexpr int SHELL_SMEM_DOUBLES = 26500;      // 207 KB of the 227 KB a CTA may use
 
-static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int nD, tuna_ctx::ClassTabDev** out) {
-    const int key = La | Lb << 4 | Lc << 8 | Ld << 12 | nD << 16;
+static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int nD, bool fill, tuna_ctx::ClassTabDev** out) {
+    const int key = La | Lb << 4 | Lc << 8 | Ld << 12 | nD << 16 | (fill ? 1 << 24 : 0);
     auto it = ctx->class_tabs.find(key);
     if (it != ctx->class_tabs.end()) { *out = &it->second; return TUNA_OK; }
     tuna_ctx::ClassTabDev& E = ctx->class_tabs[key];
@@ -1628,7 +1628,7 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
         int itb = eb ? atoi(eb) : SH_IT_BUDGET, sb = es ? atoi(es) : SH_S_BUDGET;
         const int avail = SHELL_SMEM_DOUBLES - shell_fixed_doubles(ctx->stab, La, Lb, Lc, Ld, nD);     // shrink the chunks for big classes
         if (itb + sb + 2 > avail) { itb = std::max(64, (avail - 2) / 2); sb = std::max(64, avail - 2 - itb); }
-        build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb);
+        build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb, fill);
         // Occupancy tier: a class whose single-quartet slice lands between half and all of the SM's shared memory runs ONE 8-warp CTA
         // per SM (21 % issue utilisation measured); if splitting the bra z rows into two chunks brings the slice under half, two CTAs
         // fit (34 %) at the price of running the chunk-independent phases 0-2 twice.
@@ -1650,7 +1650,7 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
                 for (int want = 2; want <= std::min(4, nch0 + 2) && !found; ++want)        // balanced cuts, fewest chunks first
                     for (int pct = 100 / want + 2; pct <= 100 / want + 30 / want + 2 && !found; pct += 3) {      // integrals per bra z row are not uniform
                         ClassTablesHost trial;
-                        build_class_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, (nint0 * pct) / 100), (La + 1) * (Lb + 1) * NGZ * NS);
+                        build_class_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, (nint0 * pct) / 100), (La + 1) * (Lb + 1) * NGZ * NS, fill);
                         if ((int)trial.chunk_bz0.size() - 1 == want && slice_doubles(trial) <= tier2) { E.host = trial; found = true; }
                     }
             }
@@ -1761,7 +1761,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
                 prefix_off.push_back(all_prefix.size());
                 all_prefix.insert(all_prefix.end(), prefix.begin(), prefix.end());
                 tuna_ctx::ClassTabDev* ctd = nullptr;
-                if ((rc = get_class_tables(ctx, J.La, J.Lb, J.Lc, J.Ld, nD, &ctd))) return rc;
+                if ((rc = get_class_tables(ctx, J.La, J.Lb, J.Lc, J.Ld, nD, fill != 0, &ctd))) return rc;
                 J.ct = ctd->view;
                 shell_job_layout(J, nD);
                 jh.allowed = (double)ctd->host.allowed;
@@ -1805,7 +1805,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
                     fprintf(f, "idx,La,Lb,Lc,Ld,nppAB,nppCD,G,nb,threads,smem,total,nout,nint,itmax,nchunk,nitems,allowed,own\n");
                     int idx = 0;
                     for (const auto& jh : ctx->jobs) {
-                        auto ct = ctx->class_tabs.find(jh.job.La | jh.job.Lb << 4 | jh.job.Lc << 8 | jh.job.Ld << 12 | nD << 16);
+                        auto ct = ctx->class_tabs.find(jh.job.La | jh.job.Lb << 4 | jh.job.Lc << 8 | jh.job.Ld << 12 | nD << 16 | (fill ? 1 << 24 : 0));
                         fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%zu,%d,%d,%d,%d,%d,%lld,%.0f,%d\n", idx++, jh.job.La, jh.job.Lb, jh.job.Lc, jh.job.Ld,
                                 jh.job.nppAB, jh.job.nppCD, jh.G, jh.nb, jh.threads, jh.smem, jh.job.total, jh.job.ct.nout,
                                 ct != ctx->class_tabs.end() ? ct->second.host.nint : -1, jh.job.ct.itmax, jh.job.ct.nchunk, jh.job.nitems, jh.allowed,
