@@ -352,6 +352,49 @@ def bench_stored(torch, wl, steps, warmup, device):
     return res, ctx
 
 
+def bench_mo_transform(torch, ctx, wl, fp64_peak, flush):
+    """AO->MO transformation (tuna_ci.py:204-255) of the resident stored tensor of `ctx`, square C.
+    Device-resident time = the four k_axis_gemm launches (CUDA events of the context); e2e = the provider call with the
+    ERIHandle in and a host ndarray out (D2H of 8 n^4 bytes inside); CPU = the reference's four einsums on the host cores."""
+    import tuna_b200
+    from oracle import tuna_oracle as orc
+    n = wl["nbf"]
+    rng = np.random.default_rng(20261018)
+    C = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    dC = torch.from_numpy(C).cuda()
+    dOut = torch.empty((n,) * 4, dtype=torch.float64, device="cuda")
+    ms = []
+    for it in range(8):
+        flush(); torch.cuda.synchronize()
+        ctx.eri_transform_dev(n, 0, n, dC.data_ptr(), n, dC.data_ptr(), False, dOut.data_ptr())
+        if it >= 3:
+            ms.append(ctx.last_kernel_ms(4))
+    k_ms = float(np.median(ms))
+    flops = 4 * 2.0 * n ** 5
+    alg_bytes = 4 * 2 * 8.0 * n ** 4
+    handle = tuna_b200.ERIHandle(ctx, n, "sph", "stored")
+    tuna_b200.transform_ERI_AO_to_MO(handle, C, None, True)
+    t = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        T = tuna_b200.transform_ERI_AO_to_MO(handle, C, None, True)
+    e2e_s = (time.perf_counter() - t) / reps
+    E = ctx.eri_download(1)
+    tc = []
+    for _ in range(2):
+        t = time.perf_counter(); ref = orc.transform_eri_ao_to_mo(E, C); tc.append(time.perf_counter() - t)
+    err = float(np.abs(T - ref).max())
+    return {"workload": f"AO->MO transformation of the stored tensor (nbf {n}, square C), tuna_ci.py:204-255", "value": 1e3 / k_ms, "unit": "transforms/s",
+            "ms_per_step": k_ms, "max_abs_diff_vs_oracle": err,
+            "roofline": {"bound": "fp64", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": flops / (k_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None, "traffic": None, "kernel": "k_axis_gemm x4",
+                         "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes, "hbm_gbs": alg_bytes / (k_ms * 1e-3) / 1e9},
+            "e2e": {"value": 1.0 / e2e_s, "unit": "transforms/s", "h2d_bytes_per_step": int(8 * n * n), "d2h_bytes_per_step": int(8 * n ** 4)},
+            "cpu_baseline": {"value": 1.0 / min(tc), "unit": "transforms/s", "cores": host_threads(), "kind": "port",
+                             "sample": "full workload: the reference's four einsums (numpy/OpenBLAS) on the same tensor, best of 2"},
+            "gpu_launches": 4}
+
+
 def sweep_point(torch, nbf, tau, fp64_peak, device):
     """One extra point of the even-tempered sweep at N=1: device-resident direct Fock builds, CUDA-event timed."""
     import tuna_b200
@@ -479,6 +522,10 @@ def run_ours(args, wl):
             sres, sctx = bench_stored(torch, swl, max(args.steps, 20), max(args.warmup, 3), local)
             sres["cpu_baseline"] = cpu_reference(swl)
             line["stored"] = sres
+            try:
+                line["mo_transform"] = bench_mo_transform(torch, sctx, swl, fp64_peak, L2Flush(torch))
+            except Exception as e:       # an extra, never allowed to take the headline line down
+                line["mo_transform"] = {"error": str(e)}
             sctx = None
             lwl = load_workload("stored:et100")       # the same stored kernel on a tensor well above L2 (0.8 GB): the HBM-stream regime
             lwl["description"] = "stored mode at nbf 100 (even-tempered N2, 0.8 GB tensor), 1 density"

@@ -79,13 +79,25 @@ int tuna_jk_direct_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, doub
  * returns PARTIAL J/K, to be summed over ranks by the caller (one all-reduce per build). */
 int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks);
 
+/* AO -> MO / spin-orbital four-index transformation of a dense ERI tensor:
+ *   tuna_ci.transform_ERI_AO_to_MO(ERI_AO, C, ...)        tuna_ci.py:204-255   so_layout = 0, C1 = C2 = C
+ *   tuna_ci.transform_ERI_AO_to_SO(ERI_AO, C_1, C_2, ...)  tuna_ci.py:143-193   so_layout = 1
+ * i.e. the einsum chain "mknl,ls->mnks" (C1), "mnks,kr->mnrs" (C2), "mnrs,nq->mqrs" (C1), "mqrs,mp->prqs" (MO) or
+ * "mqrs,mp->pqrs" (SO) (C2).  eri is n^4 (NULL = the resident stored tensor, which is left untouched), C1 is n x n1 and
+ * C2 is n x n2 (row-major: AO index first).  Output: MO layout [p][r][q][s] = (n2, n2, n1, n1) — interleaved chemists'
+ * notation (pr|qs) — or SO layout [p][q][r][s] = (n2, n1, n2, n1).  Four FP64 GEMM-shaped passes on the device. */
+int tuna_eri_transform(tuna_ctx* ctx, int n, const double* eri_host, int n1, const double* C1, int n2, const double* C2,
+                       int so_layout, double* out_host);
+int tuna_eri_transform_dev(tuna_ctx* ctx, int n, const double* d_eri, int n1, const double* dC1, int n2, const double* dC2,
+                           int so_layout, double* d_out);
+
 /* Introspection for tests and bench.py.
  * counts[0] AO pairs, [1] unique AO quartets, [2] quartets passing the x/y parity test (pyx:1324-1327),
  * [3] primitive quartets among those, [4] quartets evaluated by the last direct build (after screening, this rank),
  * [5] kernels launched by this context so far, [6] ncart, [7] nbf. */
 int tuna_get_counts(const tuna_ctx* ctx, int64_t counts[8]);
 /* Device time (ms, CUDA events on the launching stream) of the dominant kernel of the last call:
- * which = 0 ERI fill, 1 cart->sph, 2 stored J/K, 3 direct J/K.  Synchronises the stream. */
+ * which = 0 ERI fill, 1 cart->sph, 2 stored J/K, 3 direct J/K, 4 AO->MO transformation.  Synchronises the stream. */
 int tuna_last_kernel_ms(tuna_ctx* ctx, int which, float* ms);
 /* Algorithmic FP64 flop count of the reference algorithm for the parity-surviving unique quartets of the
  * current basis (formula F(a,b) of SURVEY.md section 8d), and the J/K digestion flops per density. */

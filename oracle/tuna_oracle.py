@@ -8,6 +8,8 @@ see tests/test_oracle.py.
 Restated here in NumPy (file:line under /root/reference/TUNA/):
     coulomb / exchange      <- tuna_scf.py:55-72, :27-44     (the two einsums)
     cart_to_sph_eri         <- tuna_kernel.py:504-523         ((U (x) U) ERI (U (x) U)^T)
+    transform_eri_ao_to_mo  <- tuna_ci.py:204-255             (four einsums, layout prqs)
+    transform_eri_ao_to_so  <- tuna_ci.py:143-193, :564       (four einsums, layout pqrs; spin blocking)
     FlatBasis.from_*        <- tuna_integrals/tuna_integral.pyx:78-235 (Basis + normalize)
     eri_fill / eri_single   -> oracle/eri_oracle.c            (pyx:961-1414, :1490-1651)
 """
@@ -147,6 +149,27 @@ def cart_to_sph_eri(ERI_cart, U):
     t = np.einsum("qj,pjkl->pqkl", U, t, optimize=True)
     t = np.einsum("rk,pqkl->pqrl", U, t, optimize=True)
     return np.einsum("sl,pqrl->pqrs", U, t, optimize=True)
+
+
+def transform_eri_ao_to_mo(ERI_AO, C):
+    """tuna_ci.py:204-255: the four stepwise einsums of transform_ERI_AO_to_MO; result in interleaved chemists' layout [p][r][q][s]."""
+    t = np.einsum("mknl,ls->mnks", ERI_AO, C, optimize=True)      # :230
+    t = np.einsum("mnks,kr->mnrs", t, C, optimize=True)           # :236
+    t = np.einsum("mnrs,nq->mqrs", t, C, optimize=True)           # :242
+    return np.einsum("mqrs,mp->prqs", t, C, optimize=True)        # :250
+
+
+def transform_eri_ao_to_so(ERI_AO, C_1, C_2):
+    """tuna_ci.py:143-193: transform_ERI_AO_to_SO; result in physicists' layout [p][q][r][s]."""
+    t = np.einsum("mknl,ls->mnks", ERI_AO, C_1, optimize=True)    # :165
+    t = np.einsum("mnks,kr->mnrs", t, C_2, optimize=True)         # :171
+    t = np.einsum("mnrs,nq->mqrs", t, C_1, optimize=True)         # :177
+    return np.einsum("mqrs,mp->pqrs", t, C_2, optimize=True)      # :185
+
+
+def spin_block_eri(ERI_AO):
+    """tuna_ci.py:564: ERI_spin_block = kron(I2, kron(I2, ERI_AO).T)."""
+    return np.kron(np.eye(2), np.kron(np.eye(2), ERI_AO).T)
 
 
 def parity_surviving_quartets(lmn) -> tuple:

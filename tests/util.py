@@ -38,3 +38,24 @@ def context_for(g, device=0):
 def eri_tolerance(ref):
     """1e-12 Eh absolute, relaxed to 1e-13 relative where |ERI| > 10."""
     return np.maximum(1e-12, 1e-13 * np.abs(ref))
+
+
+def mo_inputs(g, n=None, seed=20261018):
+    """Deterministic inputs of the AO->MO transformation tests (the same on the dev box, where the reference produced
+    tests/golden/mo_transform.npz from them, and on the GPU box).  With a golden config g: MO-like coefficients
+    C = X Q (X = S^-1/2 from the fixture, Q a seeded orthogonal matrix), a second set C_beta and orbital energies for the
+    spin-blocking of tuna_ci.py:111-132.  With g = None: a synthetic dense tensor E of dimension n as well."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    if g is None:
+        out["E"] = rng.standard_normal((n, n, n, n))
+        X = np.eye(n) + 0.1 * rng.standard_normal((n, n))
+    else:
+        n = int(g["nbf"])
+        X = np.array(g["X"])
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    Qb, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    out["C"] = np.ascontiguousarray(X @ Q)
+    out["C_beta"] = np.ascontiguousarray(X @ Qb)
+    out["eps"] = rng.standard_normal(2 * n)
+    return out

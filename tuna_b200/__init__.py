@@ -7,6 +7,6 @@ from .basis import Basis  # noqa: F401
 from .provider import (  # noqa: F401
     ERIHandle, calculate_coulomb_matrix, calculate_electron_repulsion_integral, calculate_electron_repulsion_integrals,
     calculate_exchange_matrix, calculate_two_electron_integrals, configure, coulomb_and_exchange, install,
-    transform_to_spherical_harmonics, uninstall)
+    transform_ERI_AO_to_MO, transform_ERI_AO_to_SO, transform_to_spherical_harmonics, uninstall)
 
 __version__ = "0.1.0"

@@ -17,7 +17,7 @@ EXPORTS = [
     "tuna_ctx_create", "tuna_ctx_destroy", "tuna_last_error", "tuna_set_stream", "tuna_set_basis", "tuna_set_transform",
     "tuna_eri_fill_cart", "tuna_eri_cart_to_sph", "tuna_eri_download", "tuna_eri_upload", "tuna_eri_single", "tuna_schwarz",
     "tuna_jk_stored", "tuna_jk_stored_dev", "tuna_jk_direct", "tuna_jk_direct_dev", "tuna_set_shard", "tuna_get_counts",
-    "tuna_last_kernel_ms", "tuna_algorithmic_flops", "tuna_fp64_peak_probe",
+    "tuna_last_kernel_ms", "tuna_algorithmic_flops", "tuna_fp64_peak_probe", "tuna_eri_transform", "tuna_eri_transform_dev",
 ]
 
 _lib = None
@@ -64,6 +64,8 @@ def load() -> ctypes.CDLL:
         "tuna_last_kernel_ms": (ci, [vp, ci, ctypes.POINTER(ctypes.c_float)]),
         "tuna_algorithmic_flops": (ci, [vp, c_dp, c_dp]),
         "tuna_fp64_peak_probe": (ci, [vp, c_dp]),
+        "tuna_eri_transform": (ci, [vp, ci, c_dp, ci, c_dp, ci, c_dp, ci, c_dp]),
+        "tuna_eri_transform_dev": (ci, [vp, ci, vp, ci, vp, ci, vp, ci, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -79,7 +81,7 @@ def _dp(a):
 class Context:
     """One (device, geometry, basis): owns the pair table and any device-resident tensors."""
 
-    KERNEL_ERI, KERNEL_SPH, KERNEL_JK_STORED, KERNEL_JK_DIRECT = 0, 1, 2, 3
+    KERNEL_ERI, KERNEL_SPH, KERNEL_JK_STORED, KERNEL_JK_DIRECT, KERNEL_MO_TRANSFORM = 0, 1, 2, 3, 4
 
     def __init__(self, device: int = 0):
         self._lib = load()
@@ -176,6 +178,31 @@ class Context:
         out = np.zeros((self.ncart, self.ncart))
         self._ck(self._lib.tuna_schwarz(self._h, _dp(out)))
         return out
+
+    def eri_transform(self, C1, C2=None, so_layout=False, eri=None):
+        """AO -> MO (tuna_ci.py:204-255) or spin-orbital (tuna_ci.py:143-193) transformation.  eri = None uses the
+        resident stored tensor; C1 (n, n1), C2 (n, n2) (default C2 = C1).  Returns [p][r][q][s] (MO) or [p][q][r][s] (SO)."""
+        C1 = np.ascontiguousarray(C1, dtype=np.float64)
+        C2 = C1 if C2 is None else np.ascontiguousarray(C2, dtype=np.float64)
+        if eri is not None:
+            eri = np.ascontiguousarray(eri, dtype=np.float64)
+            if eri.ndim != 4 or len(set(eri.shape)) != 1:
+                raise error_class("tuna_b200: ERI tensor must have shape (n, n, n, n)")
+            n = eri.shape[0]
+        else:
+            n = self.n_stored
+            if n == 0:
+                raise error_class("tuna_b200: no stored tensor is resident")
+        if C1.ndim != 2 or C2.ndim != 2 or C1.shape[0] != n or C2.shape[0] != n:
+            raise error_class(f"tuna_b200: MO coefficient matrices must have {n} rows, got {C1.shape} and {C2.shape}")
+        n1, n2 = C1.shape[1], C2.shape[1]
+        out = np.empty((n2, n1, n2, n1) if so_layout else (n2, n2, n1, n1))
+        self._ck(self._lib.tuna_eri_transform(self._h, n, _dp(eri), n1, _dp(C1), n2, _dp(C2), int(bool(so_layout)), _dp(out)))
+        return out
+
+    def eri_transform_dev(self, n, dT, n1, dC1, n2, dC2, so_layout, d_out):
+        self._ck(self._lib.tuna_eri_transform_dev(self._h, n, ctypes.c_void_p(dT), n1, ctypes.c_void_p(dC1), n2, ctypes.c_void_p(dC2),
+                                                  int(bool(so_layout)), ctypes.c_void_p(d_out)))
 
     def _jk(self, fn, P, n, want_j, want_k, *extra):
         P = np.ascontiguousarray(P, dtype=np.float64)

@@ -1,0 +1,118 @@
+// mo_transform.cuh — AO -> MO / spin-orbital four-index transformation of the dense ERI tensor.
+//
+// Reference: TUNA/tuna_ci.py:204-255 (transform_ERI_AO_to_MO) and :143-193 (transform_ERI_AO_to_SO): four NumPy einsums,
+//   "mknl,ls->mnks" (C_1), "mnks,kr->mnrs" (C_2), "mnrs,nq->mqrs" (C_1), "mqrs,mp->prqs" (MO) / "->pqrs" (SO) (C_2),
+// each an N^5 contraction of one index with the MO coefficient matrix (OpenBLAS on the host).
+//
+// Here every step contracts the LAST (contiguous) axis of the current tensor and writes the new index in FRONT:
+//   Out[s][X] = sum_l C[l][s] * T[X][l]        X = the three leading indices flattened
+// Starting from (m k n l) the four steps give (s m k n) -> (q s m k) -> (r q s m) -> (p r q s): exactly the reference's
+// interleaved chemists' layout "prqs"; the spin-orbital layout "pqrs" swaps the two middle indices in the last step's
+// store.  Each step is a tall-skinny FP64 GEMM (rows n^3, inner n, columns n_mo) that reads and writes the tensor once:
+// 2 K M NX flops against 8 NX (K + M) bytes — for K = M = 60 about 15 flop/B, above the FP64 ridge (~5.6 flop/B at
+// 37 TFLOP/s over 6.55 TB/s), so the step is FP64-pipe bound and the tile is sized for the FMA pipe: 128 x 64 outputs per
+// CTA, 8 x 4 per thread, operands staged through shared memory (T tile transposed so that a 16-byte shared load serves
+// two rows).  FP64 tensor-core MMA is not used: on sm_100a DMMA has no throughput advantage over the DFMA pipe.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace tuna {
+
+constexpr int MO_TX = 128;      // X rows per CTA
+constexpr int MO_TS = 64;       // output columns (s) per CTA
+constexpr int MO_KC = 16;       // contraction chunk
+constexpr int MO_TXP = MO_TX + 2;
+
+// swap != 0: X = (a, b, c) with dims (d1, d2, d3) is stored at [s][b][a][c] (spin-orbital layout, last step only).
+__global__ void __launch_bounds__(256, 2) k_axis_gemm(const double* __restrict__ T, const double* __restrict__ C, double* __restrict__ Out,
+                                                      long long NX, int K, int M, int swap, int d1, int d2, int d3) {
+    __shared__ __align__(16) double Ts[MO_KC][MO_TXP];      // [l][x]
+    __shared__ __align__(16) double Cs[MO_KC][MO_TS];       // [l][s]
+    const int t = threadIdx.x;
+    const long long X0 = (long long)blockIdx.x * MO_TX;
+    const int s0 = blockIdx.y * MO_TS;
+    const int tx = t & 15, ts = t >> 4;
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    const int lc = t & 15, lr = t >> 4;       // T tile loader: 16 consecutive l of one row per half-warp (128-byte segments)
+    for (int l0 = 0; l0 < K; l0 += MO_KC) {
+        __syncthreads();
+#pragma unroll
+        for (int pass = 0; pass < MO_TX / 16; ++pass) {
+            const int r = pass * 16 + lr;
+            const long long X = X0 + r;
+            const int l = l0 + lc;
+            Ts[lc][r] = (X < NX && l < K) ? T[X * K + l] : 0.0;
+        }
+#pragma unroll
+        for (int pass = 0; pass < (MO_KC * MO_TS) / 256; ++pass) {
+            const int e = pass * 256 + t, c = e / MO_TS, s = e % MO_TS;
+            const int l = l0 + c;
+            Cs[c][s] = (l < K && s0 + s < M) ? C[(size_t)l * M + s0 + s] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < MO_KC; ++c) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 v = *reinterpret_cast<const double2*>(&Ts[c][i * 32 + tx * 2]);
+                a[2 * i] = v.x; a[2 * i + 1] = v.y;
+            }
+            {
+                const double2 v0 = *reinterpret_cast<const double2*>(&Cs[c][ts * 4]);
+                const double2 v1 = *reinterpret_cast<const double2*>(&Cs[c][ts * 4 + 2]);
+                b[0] = v0.x; b[1] = v0.y; b[2] = v1.x; b[3] = v1.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+    const bool vec = !swap && (NX % 2 == 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int s = s0 + ts * 4 + j;
+        if (s >= M) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long X = X0 + i * 32 + tx * 2;
+            if (X >= NX) continue;
+            if (vec) {       // X even, NX even: X + 1 < NX and the address is 16-byte aligned
+                *reinterpret_cast<double2*>(Out + (size_t)s * NX + X) = make_double2(acc[2 * i][j], acc[2 * i + 1][j]);
+            } else if (!swap) {
+                Out[(size_t)s * NX + X] = acc[2 * i][j];
+                if (X + 1 < NX) Out[(size_t)s * NX + X + 1] = acc[2 * i + 1][j];
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long Xh = X + h;
+                    if (Xh >= NX) continue;
+                    const int c3 = (int)(Xh % d3);
+                    const long long ab = Xh / d3;
+                    const int b2 = (int)(ab % d2), a1 = (int)(ab / d2);
+                    Out[(((size_t)s * d2 + b2) * d1 + a1) * d3 + c3] = acc[2 * i + h][j];
+                }
+            }
+        }
+    }
+}
+
+// One step on `stream`: Out[M][NX] (or the swapped layout) from T[NX][K] and C[K][M].
+inline cudaError_t axis_gemm(cudaStream_t stream, const double* T, const double* C, double* Out, long long NX, int K, int M, int swap, int d1,
+                             int d2, int d3) {
+    const long long gx = (NX + MO_TX - 1) / MO_TX;
+    const int gy = (M + MO_TS - 1) / MO_TS;
+    if (gx <= 0 || gy <= 0) return cudaSuccess;
+    if (gx > 2147483647LL || gy > 65535) return cudaErrorInvalidConfiguration;
+    k_axis_gemm<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(T, C, Out, NX, K, M, swap, d1, d2, d3);
+    return cudaGetLastError();
+}
+
+}  // namespace tuna

@@ -23,6 +23,7 @@
 #include "pairtable.hpp"
 #include "shell_host.hpp"
 #include "shell_jk.cuh"
+#include "mo_transform.cuh"
 
 using namespace tuna;
 
@@ -80,7 +81,11 @@ struct tuna_ctx {
     unsigned long long* d_scalars = nullptr;   // [0] max|P| bits, [1] evaluated-quartet counter
 
     int shard_rank = 0, shard_n = 1;
-    cudaEvent_t ev[4][2] = {};
+    cudaEvent_t ev[5][2] = {};
+
+    // AO -> MO four-index transformation (mo_transform.cuh): two ping-pong work buffers, grown on demand
+    double* d_mo_ws[2] = {nullptr, nullptr};
+    size_t cap_mo[2] = {0, 0};
 
     // shell-quartet engine (shell_jk.cuh)
     ShellTab stab;
@@ -1061,7 +1066,7 @@ int tuna_ctx_create(int device, tuna_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    for (int w = 0; w < 4; ++w)
+    for (int w = 0; w < 5; ++w)
         for (int s = 0; s < 2; ++s) CK(cudaEventCreate(&ctx->ev[w][s]));
     for (int a = 0; a < tuna_ctx::NAUX; ++a) {
         CK(cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking));
@@ -1101,7 +1106,8 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->Uf.rowptr); dev_free(&ctx->Uf.col); dev_free(&ctx->Uf.val);
     dev_free(&ctx->Uft.rowptr); dev_free(&ctx->Uft.col); dev_free(&ctx->Uft.val);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    for (int w = 0; w < 4; ++w)
+    dev_free(&ctx->d_mo_ws[0]); dev_free(&ctx->d_mo_ws[1]);
+    for (int w = 0; w < 5; ++w)
         for (int s = 0; s < 2; ++s) if (ctx->ev[w][s]) cudaEventDestroy(ctx->ev[w][s]);
     for (int a = 0; a < tuna_ctx::NAUX; ++a) {
         if (ctx->aux[a]) { cudaStreamSynchronize(ctx->aux[a]); cudaStreamDestroy(ctx->aux[a]); }
@@ -1607,6 +1613,82 @@ int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
 }
 
 }  // extern "C" (internal helpers follow)
+
+// ------------------------------------------------------------------------------------------------
+// AO -> MO / spin-orbital transformation of the dense tensor (tuna_ci.py:143-255); kernel in mo_transform.cuh
+// ------------------------------------------------------------------------------------------------
+static int mo_transform_core(tuna_ctx* ctx, int n, const double* dT, int n1, const double* dC1, int n2, const double* dC2, int so_layout,
+                             double* d_out) {
+    const size_t N = (size_t)n, N1 = (size_t)n1, N2 = (size_t)n2;
+    const size_t s1 = N1 * N * N * N, s2 = N1 * N1 * N * N, s3 = N2 * N1 * N1 * N;
+    const size_t need[2] = {std::max(s1, s3), s2};
+    int rc;
+    for (int b = 0; b < 2; ++b)
+        if (ctx->cap_mo[b] < need[b]) {
+            ctx->cap_mo[b] = 0;
+            CK(cudaStreamSynchronize(ctx->stream));
+            if ((rc = dev_alloc(ctx, &ctx->d_mo_ws[b], need[b]))) return rc;
+            ctx->cap_mo[b] = need[b];
+        }
+    double* A = ctx->d_mo_ws[0];
+    double* B = ctx->d_mo_ws[1];
+    CK(cudaEventRecord(ctx->ev[4][0], ctx->stream));
+    CK(axis_gemm(ctx->stream, dT, dC1, A, (long long)(N * N * N), n, n1, 0, 0, 0, 0));          // (m k n l) -> (s m k n)
+    CK(axis_gemm(ctx->stream, A, dC1, B, (long long)(N1 * N * N), n, n1, 0, 0, 0, 0));          //           -> (q s m k)
+    CK(axis_gemm(ctx->stream, B, dC2, A, (long long)(N1 * N1 * N), n, n2, 0, 0, 0, 0));         //           -> (r q s m)
+    CK(axis_gemm(ctx->stream, A, dC2, d_out, (long long)(N2 * N1 * N1), n, n2, so_layout ? 1 : 0, n2, n1, n1));   // -> (p r q s) | (p q r s)
+    CK(cudaEventRecord(ctx->ev[4][1], ctx->stream));
+    ctx->launches += 4;
+    return TUNA_OK;
+}
+
+extern "C" {
+
+int tuna_eri_transform_dev(tuna_ctx* ctx, int n, const double* dT, int n1, const double* dC1, int n2, const double* dC2, int so_layout,
+                           double* d_out) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (n <= 0 || n1 <= 0 || n2 <= 0 || !dC1 || !dC2 || !d_out) FAIL(TUNA_ERR_ARG, "tuna_eri_transform: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (!dT) {
+        if (!ctx->d_eri_sph || ctx->n_stored != n) FAIL(TUNA_ERR_STATE, "tuna_eri_transform: no stored tensor of that dimension is resident");
+        dT = ctx->d_eri_sph;
+    }
+    return mo_transform_core(ctx, n, dT, n1, dC1, n2, dC2, so_layout, d_out);
+}
+
+int tuna_eri_transform(tuna_ctx* ctx, int n, const double* eri_host, int n1, const double* C1, int n2, const double* C2, int so_layout,
+                       double* out_host) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (n <= 0 || n1 <= 0 || n2 <= 0 || !C1 || !C2 || !out_host) FAIL(TUNA_ERR_ARG, "tuna_eri_transform: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n4 = (size_t)n * n * n * n, nout = (size_t)n1 * n1 * n2 * n2;
+    if (!eri_host && (!ctx->d_eri_sph || ctx->n_stored != n))
+        FAIL(TUNA_ERR_STATE, "tuna_eri_transform: no stored tensor of that dimension is resident and no host tensor was given");
+    double* dT = nullptr; double* dC = nullptr; double* dOut = nullptr;
+    int rc = TUNA_OK;
+    if (eri_host && (rc = dev_alloc(ctx, &dT, n4))) return rc;
+    if (!rc) rc = dev_alloc(ctx, &dC, (size_t)n * (n1 + n2));
+    if (!rc) rc = dev_alloc(ctx, &dOut, nout);
+    auto cleanup = [&]() { dev_free(&dT); dev_free(&dC); dev_free(&dOut); };
+    if (rc) { cleanup(); return rc; }
+    cudaError_t e = cudaSuccess;
+    if (eri_host) e = cudaMemcpyAsync(dT, eri_host, n4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dC, C1, (size_t)n * n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dC + (size_t)n * n1, C2, (size_t)n * n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cleanup(); ctx->err = std::string("tuna_eri_transform upload: ") + cudaGetErrorString(e); return TUNA_ERR_CUDA; }
+    rc = mo_transform_core(ctx, n, eri_host ? dT : ctx->d_eri_sph, n1, dC, n2, dC + (size_t)n * n1, so_layout, dOut);
+    if (!rc) {
+        e = cudaMemcpyAsync(out_host, dOut, nout * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("tuna_eri_transform: ") + cudaGetErrorString(e); rc = TUNA_ERR_CUDA; }
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cleanup();
+    return rc;
+}
+
+}  // extern "C"
 
 // Per-class work tables: built on the host once per angular class and kept on the device in one blob.
 // Shared-memory doubles of one group that do not depend on the chunking (everything except the S slice and the It buffer).
@@ -2125,7 +2207,7 @@ int tuna_get_counts(const tuna_ctx* c, int64_t counts[8]) {
 }
 
 int tuna_last_kernel_ms(tuna_ctx* ctx, int which, float* ms) {
-    if (!ctx || !ms || which < 0 || which > 3) return TUNA_ERR_ARG;
+    if (!ctx || !ms || which < 0 || which > 4) return TUNA_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));

@@ -12,6 +12,8 @@ no reference edits.  The only compute path is libtuna_b200.so on a CUDA device â
     tuna_kernel.transform_to_spherical_harmonics          tuna_kernel.py:454-529
     tuna_scf.calculate_coulomb_matrix                     tuna_scf.py:55-72
     tuna_scf.calculate_exchange_matrix                    tuna_scf.py:27-44
+    tuna_ci.transform_ERI_AO_to_MO                        tuna_ci.py:204-255      
+    tuna_ci.transform_ERI_AO_to_SO                        tuna_ci.py:143-193
 """
 import os
 import weakref
@@ -283,31 +285,80 @@ def calculate_exchange_matrix(P, ERI_AO):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# tuna_ci level: AO -> MO / spin-orbital transformation (first thing every MPn / CC / CI calculation does with ERI_AO)
+# ---------------------------------------------------------------------------------------------------------
+_scratch = {}
+
+
+def _scratch_context():
+    """A basis-less context for tensors handed in as host ndarrays (e.g. the spin-blocked tensor of tuna_ci.py:564)."""
+    dev = _settings["device"]
+    if dev not in _scratch:
+        _scratch[dev] = _lib.Context(dev)
+    return _scratch[dev]
+
+
+def _transform(ERI_AO, C_1, C_2, so_layout, calculation, silent):
+    timer = _ref_timer()
+    timer("Molecular orbital transformation", 0)
+    log = _log_fn
+    if log is not None and calculation is not None:
+        log("\n Transforming integrals on the device (4 steps)... ", calculation, 1, end="", silent=silent)
+    C_1 = np.asarray(C_1, dtype=np.float64)
+    C_2 = np.asarray(C_2, dtype=np.float64)
+    if isinstance(ERI_AO, ERIHandle) and ERI_AO.mode == "stored" and ERI_AO.basis_kind == "sph" and ERI_AO.ctx.n_stored == ERI_AO.n:
+        out = ERI_AO.ctx.eri_transform(C_1, C_2, so_layout)                     # the tensor is already resident
+    else:
+        arr = np.asarray(ERI_AO, dtype=np.float64)
+        if arr.ndim != 4 or len(set(arr.shape)) != 1:
+            raise _lib.error_class("tuna_b200: ERI_AO must be an ERIHandle or an (n, n, n, n) array")
+        out = _scratch_context().eri_transform(C_1, C_2, so_layout, eri=arr)
+    if log is not None and calculation is not None:
+        log("[Done]", calculation, 1, silent=silent)
+    timer("Molecular orbital transformation", 1)
+    return out
+
+
+def transform_ERI_AO_to_MO(ERI_AO, C, calculation, silent):
+    """ERI_MO[p,r,q,s] = sum_mknl ERI_AO[m,k,n,l] C[m,p] C[k,r] C[n,q] C[l,s] (tuna_ci.py:204-255): interleaved chemists' notation."""
+    return _transform(ERI_AO, C, C, False, calculation, silent)
+
+
+def transform_ERI_AO_to_SO(ERI_AO, C_1, C_2, calculation, silent):
+    """ERI_SO[p,q,r,s] = sum_mknl ERI_AO[m,k,n,l] C_2[m,p] C_1[n,q] C_2[k,r] C_1[l,s] (tuna_ci.py:143-193): physicists' notation."""
+    return _transform(ERI_AO, C_1, C_2, True, calculation, silent)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # installation on the reference's modules
 # ---------------------------------------------------------------------------------------------------------
 _timer_fn = None
+_log_fn = None
 
 
 def _ref_timer():
     return _timer_fn if _timer_fn is not None else (lambda name, flag: None)
 
 
-def install(tuna_integral=None, tuna_kernel=None, tuna_scf=None, tuna_util=None):
-    """Rebind the six hot-path names on the reference's (already imported) modules.  All four are module-global
+def install(tuna_integral=None, tuna_kernel=None, tuna_scf=None, tuna_util=None, tuna_ci=None):
+    """Rebind the hot-path names (six of the SCF path + the two AO->MO transformations of tuna_ci) on the reference's (already imported) modules.  All four are module-global
     lookups at call time, so no reference source is edited.  Returns a dict of the originals."""
     import sys
-    global _timer_fn
+    global _timer_fn, _log_fn
     tuna_integral = tuna_integral or sys.modules.get("tuna_integrals.tuna_integral")
     tuna_kernel = tuna_kernel or sys.modules.get("tuna_kernel")
     tuna_scf = tuna_scf or sys.modules.get("tuna_scf")
     tuna_util = tuna_util or sys.modules.get("tuna_util")
+    tuna_ci = tuna_ci or sys.modules.get("tuna_ci")
     originals = {}
     if tuna_util is not None:
         _lib.error_class = getattr(tuna_util, "TunaError", _lib.error_class)
         _timer_fn = getattr(tuna_util, "timer", None)
+        _log_fn = getattr(tuna_util, "log", None)
     for mod, names in ((tuna_integral, ("calculate_electron_repulsion_integrals", "calculate_electron_repulsion_integral")),
                        (tuna_kernel, ("calculate_two_electron_integrals", "transform_to_spherical_harmonics")),
-                       (tuna_scf, ("calculate_coulomb_matrix", "calculate_exchange_matrix"))):
+                       (tuna_scf, ("calculate_coulomb_matrix", "calculate_exchange_matrix")),
+                       (tuna_ci, ("transform_ERI_AO_to_MO", "transform_ERI_AO_to_SO"))):
         if mod is None:
             continue
         for name in names:
