@@ -91,3 +91,44 @@ def test_handle_forwards_ndarray_protocol():
     assert np.array_equal(2 * h - h.swapaxes(1, 3), 2 * h._host - h._host.swapaxes(1, 3))
     assert np.array_equal(np.einsum("ijkl,kl->ij", h, np.eye(3)), np.einsum("ijkl,kl->ij", h._host, np.eye(3)))
     assert h[1, 2, 0, 1] == h._host[1, 2, 0, 1]
+
+
+def test_install_rebinds_reference_names_and_uninstall_restores():
+    """install() on the UNMODIFIED reference modules (dev container only): the eight names of INTEGRATION.md section 2 are rebound,
+    the reference's TunaError / timer / log are adopted, uninstall() restores the originals.  No compute call (no GPU here)."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+    import tuna_b200
+    from tuna_b200 import _lib, provider
+    ns = rh.load_reference()
+    ci = importlib.import_module("tuna_ci")
+    before = {"eri": ns.ints.calculate_electron_repulsion_integrals, "J": ns.scf.calculate_coulomb_matrix, "mo": ci.transform_ERI_AO_to_MO}
+    saved_err = _lib.error_class
+    originals = tuna_b200.install()
+    try:
+        assert len(originals) == 8
+        assert ns.ints.calculate_electron_repulsion_integrals is tuna_b200.calculate_electron_repulsion_integrals
+        assert ns.ints.calculate_electron_repulsion_integral is tuna_b200.calculate_electron_repulsion_integral
+        assert ns.kern.calculate_two_electron_integrals is tuna_b200.calculate_two_electron_integrals
+        assert ns.kern.transform_to_spherical_harmonics is tuna_b200.transform_to_spherical_harmonics
+        assert ns.scf.calculate_coulomb_matrix is tuna_b200.calculate_coulomb_matrix
+        assert ns.scf.calculate_exchange_matrix is tuna_b200.calculate_exchange_matrix
+        assert ci.transform_ERI_AO_to_MO is tuna_b200.transform_ERI_AO_to_MO and ci.transform_ERI_AO_to_SO is tuna_b200.transform_ERI_AO_to_SO
+        assert _lib.error_class is ns.util.TunaError and provider._timer_fn is ns.util.timer and provider._log_fn is ns.util.log
+        # same positional signatures as the functions they replace
+        import inspect
+        for (modname, name), orig in originals.items():
+            try:
+                ref_params = list(inspect.signature(orig).parameters)
+            except (TypeError, ValueError):
+                continue                                            # cpdef functions of the compiled engine expose no signature
+            assert list(inspect.signature(getattr(tuna_b200, name)).parameters) == ref_params, name
+    finally:
+        tuna_b200.uninstall(originals)
+        _lib.error_class = saved_err
+    assert ns.ints.calculate_electron_repulsion_integrals is before["eri"] and ns.scf.calculate_coulomb_matrix is before["J"]
+    assert ci.transform_ERI_AO_to_MO is before["mo"]
