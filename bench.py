@@ -31,6 +31,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "fock_builds_per_s"
 UNIT = "Fock builds/s"
 
+# ncu-counted FP64 work of one direct build, keyed by (workload, densities, tau): 2*DFMA + DMUL + DADD thread instructions
+# summed over the 241 class-job launches of one ET800 build (profiles/r01f_class_metrics.csv; see profiles/README.md).
+EXECUTED_FP64 = {
+    ("et800", 1, 1e-16): {"fp64_flops_per_build": 2.066e12, "warp_instructions_per_build": 7.21e11, "fp64_share_of_thread_instructions": 0.051,
+                          "issue_active_pct": 42.2, "fp64_pipe_active_pct": 6.1, "source": "profiles/r01f_class_metrics.csv (ncu, round 1)"},
+}
+
 
 # ----------------------------------------------------------------------------------------------------------------
 # workloads
@@ -510,9 +517,17 @@ def run_ours(args, wl):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "traffic": None, "peak_source": "FP64 DFMA stream measured in this run (tuna_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry",
                          "kernel": "k_shell_jk (all class jobs of one build)", "kernel_ms": k_ms, "algorithmic_flops": alg,
-                         "note": "algorithmic = the reference algorithm's flop count F(a,b) (SURVEY.md 8d) + 12 flops/quartet/density of digestion"},
+                         "note": "algorithmic = the reference algorithm's flop count F(a,b) (SURVEY.md 8d) + 12 flops/quartet/density of digestion; "
+                                 "the shell engine EXECUTES far fewer FP64 flops (tables shared by all components of a shell quartet): see `executed`"},
             "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(fb.h2d_bytes), "d2h_bytes_per_step": int(fb.d2h_bytes)},
             "gpu_launches": int(launches), "clocks": clocks}
+    ex = EXECUTED_FP64.get((wl["name"], nD, args.tau))
+    if ex is not None:
+        # "always report the ncu-executed FP64 flop count beside it".  The count is a property of the code + workload
+        # (profiles/r01f_class_metrics.csv, ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on over all class-job
+        # launches of one build); the rate uses THIS run's kernel time.
+        rate = ex["fp64_flops_per_build"] / world / (k_ms * 1e-3) / 1e12
+        line["roofline"]["executed"] = dict(ex, tflops=rate, frac_of_fp64_peak=rate / fp64_peak if fp64_peak else None)
     if world == 1:
         line["cpu_baseline"] = cpu_reference(wl)
         if not args.no_stored:

@@ -78,6 +78,19 @@ def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
 
 
+def _host_tensor(shape):
+    """Result buffer for the large device->host copies (n^4 doubles).  Page-locked memory from torch's caching host
+    allocator (plumbing: the copy then runs at PCIe/C2C speed instead of through the driver's staging buffers and the
+    buffer is not page-faulted in by the copy); the ndarray keeps the torch tensor alive.  Plain np.empty when pinning fails."""
+    if int(np.prod(shape)) * 8 >= (1 << 22) and os.environ.get("TUNA_B200_PINNED_RESULTS", "1") != "0":
+        try:
+            import torch
+            return torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:
+            pass
+    return np.empty(shape)
+
+
 class Context:
     """One (device, geometry, basis): owns the pair table and any device-resident tensors."""
 
@@ -156,7 +169,7 @@ class Context:
     def eri_download(self, which: int, out=None):
         n = self.ncart if which == 0 else self.n_stored
         if out is None:
-            out = np.empty((n, n, n, n))
+            out = _host_tensor((n, n, n, n))
         if out.shape != (n, n, n, n) or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise error_class("tuna_b200: output tensor must be C-contiguous float64 of shape (n, n, n, n)")
         self._ck(self._lib.tuna_eri_download(self._h, which, _dp(out)))
@@ -196,7 +209,7 @@ class Context:
         if C1.ndim != 2 or C2.ndim != 2 or C1.shape[0] != n or C2.shape[0] != n:
             raise error_class(f"tuna_b200: MO coefficient matrices must have {n} rows, got {C1.shape} and {C2.shape}")
         n1, n2 = C1.shape[1], C2.shape[1]
-        out = np.empty((n2, n1, n2, n1) if so_layout else (n2, n2, n1, n1))
+        out = _host_tensor((n2, n1, n2, n1) if so_layout else (n2, n2, n1, n1))
         self._ck(self._lib.tuna_eri_transform(self._h, n, _dp(eri), n1, _dp(C1), n2, _dp(C2), int(bool(so_layout)), _dp(out)))
         return out
 

@@ -12,7 +12,9 @@
 // 2 K M NX flops against 8 NX (K + M) bytes — for K = M = 60 about 15 flop/B, above the FP64 ridge (~5.6 flop/B at
 // 37 TFLOP/s over 6.55 TB/s), so the step is FP64-pipe bound and the tile is sized for the FMA pipe: 128 x 64 outputs per
 // CTA, 8 x 4 per thread, operands staged through shared memory (T tile transposed so that a 16-byte shared load serves
-// two rows).  FP64 tensor-core MMA is not used: on sm_100a DMMA has no throughput advantage over the DFMA pipe.
+// two rows).  Measured (ncu, nbf 110): FP64 pipe 53 % active, shared-memory data pipe 74 % — the 8 x 4 register tile is bound by
+// LSU->register bandwidth (12 operand doubles per 32 DFMA); the next step is FP64 tensor-core MMA (mma.sync m8n8k4 f64), which
+// needs 8x fewer operand bytes per flop.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -30,8 +32,12 @@ __global__ void __launch_bounds__(256, 2) k_axis_gemm(const double* __restrict__
     __shared__ __align__(16) double Ts[MO_KC][MO_TXP];      // [l][x]
     __shared__ __align__(16) double Cs[MO_KC][MO_TS];       // [l][s]
     const int t = threadIdx.x;
-    const long long X0 = (long long)blockIdx.x * MO_TX;
-    const int s0 = blockIdx.y * MO_TS;
+    // 1-D grid with the column tile fastest: the CTAs that read the same T tile (one per column tile) are scheduled together,
+    // so the tile comes from HBM once and from L2 afterwards (a (x, y) grid re-read the tensor once per column tile: ncu
+    // dram__bytes_read 2.34 GB for an algorithmic 1.17 GB at nbf 110)
+    const int ntile_s = (M + MO_TS - 1) / MO_TS;
+    const long long X0 = (long long)(blockIdx.x / ntile_s) * MO_TX;
+    const int s0 = (int)(blockIdx.x % ntile_s) * MO_TS;
     const int tx = t & 15, ts = t >> 4;
     double acc[8][4];
 #pragma unroll
@@ -110,8 +116,8 @@ inline cudaError_t axis_gemm(cudaStream_t stream, const double* T, const double*
     const long long gx = (NX + MO_TX - 1) / MO_TX;
     const int gy = (M + MO_TS - 1) / MO_TS;
     if (gx <= 0 || gy <= 0) return cudaSuccess;
-    if (gx > 2147483647LL || gy > 65535) return cudaErrorInvalidConfiguration;
-    k_axis_gemm<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(T, C, Out, NX, K, M, swap, d1, d2, d3);
+    if (gx * gy > 2147483647LL) return cudaErrorInvalidConfiguration;
+    k_axis_gemm<<<(unsigned)(gx * gy), 256, 0, stream>>>(T, C, Out, NX, K, M, swap, d1, d2, d3);
     return cudaGetLastError();
 }
 
