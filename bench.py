@@ -32,10 +32,10 @@ METRIC = "fock_builds_per_s"
 UNIT = "Fock builds/s"
 
 # ncu-counted FP64 work of one direct build, keyed by (workload, densities, tau): 2*DFMA + DMUL + DADD thread instructions
-# summed over the 241 class-job launches of one ET800 build (profiles/r01f_class_metrics.csv; see profiles/README.md).
+# summed over the 231 class-job launches of one ET800 build (profiles/r01f_class_metrics.csv; see profiles/README.md).
 EXECUTED_FP64 = {
-    ("et800", 1, 1e-16): {"fp64_flops_per_build": 2.066e12, "warp_instructions_per_build": 7.21e11, "fp64_share_of_thread_instructions": 0.051,
-                          "issue_active_pct": 42.2, "fp64_pipe_active_pct": 6.1, "source": "profiles/r01f_class_metrics.csv (ncu, round 1)"},
+    ("et800", 1, 1e-16): {"fp64_flops_per_build": 1.902e12, "warp_instructions_per_build": 6.63e11, "fp64_share_of_thread_instructions": 0.062,
+                          "issue_active_pct": 42.6, "fp64_pipe_active_pct": 6.2, "source": "profiles/r01f_class_metrics.csv (ncu, round 1)"},
 }
 
 
