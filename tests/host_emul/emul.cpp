@@ -132,6 +132,10 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
             shell_job_layout(J, nD);
             const char* enb = getenv("TUNA_EMUL_NB");             // quartets batched per group (1, 2 or 4)
             const int NBATCH = enb ? atoi(enb) : 2;
+#ifdef TUNA_SHELL_WIDE_TERMS
+            const std::vector<unsigned> wide = scale_wide_terms(CTH.p5wide, NBATCH, J.oP - J.oIt);
+            J.ct.p5w = wide.data();
+#endif
             std::vector<double> sm((size_t)4 * J.total);
             bool act[4] = {false, false, false, false};
             int ABs[4] = {0, 0, 0, 0}, CDs[4] = {0, 0, 0, 0}, nb = 0;

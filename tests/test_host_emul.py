@@ -12,18 +12,33 @@ from util import load_golden, oracle_basis
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def emul():
-    so = os.path.join(HERE, "host_emul", "libemul.so")
+# "" = the shipped kernel body; the other entries are the development variants kept behind compile-time macros (off in the
+# default build of libtuna_b200.so): their tables and device code are checked here on the CPU before they are ever timed on a GPU.
+VARIANTS = {"": [], "wide_terms": ["-DTUNA_SHELL_WIDE_TERMS"], "asm_unroll": ["-DTUNA_SHELL_ASM_UNROLL"],
+            "all": ["-DTUNA_SHELL_WIDE_TERMS", "-DTUNA_SHELL_ASM_UNROLL"]}
+
+
+@pytest.fixture(scope="module", params=list(VARIANTS))
+def emul(request):
+    tag = request.param
+    so = os.path.join(HERE, "host_emul", f"libemul{'_' + tag if tag else ''}.so")
     src = os.path.join(HERE, "host_emul", "emul.cpp")
-    subprocess.run(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-x", "c++", "-o", so, src, "-lm"], check=True)
+    subprocess.run(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-x", "c++"] + VARIANTS[tag] + ["-o", so, src, "-lm"], check=True)
     lib = ctypes.CDLL(so)
+    lib.variant = tag
     lib.emul_boys.restype = ctypes.c_double
     lib.emul_boys.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double]
     return lib
 
 
+def only_default(emul, *allowed):
+    """The development variants differ only in phases 4/5 of the shell engine: run them on the cheap engine cases."""
+    if emul.variant and allowed != ("*",):
+        pytest.skip("variant builds run the shell-engine subset only")
+
+
 def test_boys_kernel_function(emul, oracle):
+    only_default(emul)
     rng = np.random.default_rng(3)
     Ts = np.concatenate([[0.0, 1e-12, 0.03125, 39.999, 40.0, 40.001, 1e3, 3e6, 1e13], rng.uniform(0, 45, 200), 10 ** rng.uniform(-6, 6, 100)])
     worst = 0.0
@@ -38,6 +53,7 @@ def test_boys_kernel_function(emul, oracle):
 
 @pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "et100"])
 def test_quartet_math_vs_oracle(emul, oracle, name):
+    only_default(emul)
     g = load_golden(name)
     fb = oracle_basis(oracle, g)
     n = fb.ncart
@@ -59,6 +75,8 @@ def test_quartet_math_vs_oracle(emul, oracle, name):
 def test_shell_engine_vs_oracle(emul, oracle, name):
     """shell_jk.cuh (the direct-mode engine) run serially on the CPU: J/K for two symmetric densities vs the oracle's
     einsums over the oracle's Cartesian tensor, with and without Schwarz screening."""
+    if emul.variant and name == "n2_ccpvtz":
+        pytest.skip("variant builds run the shell-engine subset only")
     g = load_golden(name)
     fb = oracle_basis(oracle, g)
     n = fb.ncart
@@ -113,6 +131,8 @@ def test_shell_engine_h_shells(emul, oracle):
 def test_shell_engine_fill_mode_vs_oracle(emul, oracle, name):
     """Fill mode of the shell engine (dense Cartesian tensor for stored mode): element-wise against the oracle, exact zeros for
     parity-forbidden entries, exact 8-fold symmetry (canonical quartets are scattered to their eight images)."""
+    if emul.variant and name != "h2_631g":
+        pytest.skip("variant builds run the shell-engine subset only")
     g = load_golden(name)
     fb = oracle_basis(oracle, g)
     n = fb.ncart

@@ -23,10 +23,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
                       "nj": float(np.abs(J).max()), "nk": float(np.abs(K).max())}))
 else:
     sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [400, 800]
-    libs = {"cur": "tuna_b200/libtuna_b200.so", "base": "build/lib_base.so", "v2_r64": "build/lib_v2_r64.so", "v2_r96": "build/lib_v2_r96.so", "v2_r128": "build/lib_v2_r128.so", "v2_r48": "build/lib_v2_r48.so"}
-    NB4, NB4S, NB2L, NB1 = {"TUNA_B200_NB": "4"}, {"TUNA_B200_NB": "4", "TUNA_B200_NB_BYTES": "65536"}, {"TUNA_B200_NB": "2", "TUNA_B200_NB_BYTES": "200000"}, {"TUNA_B200_NB": "1"}
-    SPL192, SPL160 = {"TUNA_B200_SMEM_PER_LANE": "192"}, {"TUNA_B200_SMEM_PER_LANE": "160"}
-    combos = [("cur", {"TUNA_B200_TIER2": "0"}), ("cur", {})]
+    # build/*.so come from tools/build_variants.sh (compile-time variants of the shell engine, off in the shipped library)
+    libs = {"cur": "tuna_b200/libtuna_b200.so", "wide": "build/lib_wide.so", "asm": "build/lib_asm.so", "tiers": "build/lib_tiers.so", "v3": "build/lib_v3.so"}
+    combos = [("cur", {}), ("wide", {}), ("asm", {}), ("tiers", {}), ("tiers", {"TUNA_B200_REG_TIER": "0"}), ("v3", {}), ("v3", {"TUNA_B200_REG_TIER": "0"})]
     ref = {}
     for nbf in sizes:
         for name, env in combos:

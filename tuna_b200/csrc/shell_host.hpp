@@ -189,6 +189,9 @@ struct ClassTablesHost {
     std::vector<unsigned> p4, p5ptr, p5term, p5off, p6, t_rt, t_xy, t_u, t_s;
     std::vector<unsigned short> pmap, omap, jst_list;
     std::vector<unsigned> jst_ptr, jflush;
+#ifdef TUNA_SHELL_WIDE_TERMS
+    std::vector<unsigned> p5wide;     // phase-5 terms as (It slot, staged density entry) word pairs in ELEMENT units; scale_wide_terms() makes the device copy
+#endif
     long long p5real = 0;             // digestion terms before padding (table statistics)
     long long allowed = 0;            // parity-allowed component quartets = integrals per shell quartet
     double uniq[6] = {0, 0, 0, 0, 0, 0};   // unique AO quartets a shell quartet stands for: [0] generic, [1] A==B, [2] C==D,
@@ -380,7 +383,17 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
             const int mx = (int)((w1 >> 20) & 15) - (int)((w1 >> 16) & 15) + 1, my = (int)((w1 >> 28) & 15) - (int)((w1 >> 24) & 15) + 1;
             return mx * my;
         };
+#ifdef TUNA_SHELL_ASM_UNROLL
+        // the assembly dispatches on the m' trip count: lanes of a warp should agree on it first, then on the number of m trips
+        auto akey = [&](int i) {
+            const unsigned w1 = C.p4[2 * (size_t)(e0 + i) + 1];
+            const int mx = (int)((w1 >> 20) & 15) - (int)((w1 >> 16) & 15) + 1, my = (int)((w1 >> 28) & 15) - (int)((w1 >> 24) & 15) + 1;
+            return my * 16 + mx;
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return akey(x) > akey(y); });
+#else
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return nterm(x) > nterm(y); });
+#endif
         std::vector<unsigned> np4(2 * (size_t)ne);
         for (int k = 0; k < ne; ++k) {
             np4[2 * k] = C.p4[2 * (size_t)(e0 + order[k])];
@@ -464,6 +477,19 @@ inline void build_class_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld
             C.p5term.resize(base + mx * 128, (unsigned)C.itmax);
             for (int o = blk * 32; o < std::min(C.nout, blk * 32 + 32); ++o)
                 for (size_t k = 0; k < terms[o].size(); ++k) C.p5term[base + ((k / 4) * 32 + (size_t)(o & 31)) * 4 + (k & 3)] = terms[o][k];
+#ifdef TUNA_SHELL_WIDE_TERMS
+            {   // same blocks, two 16-byte entries per quad: half h = (k & 3) >> 1 of quad k / 4 at uint4 index 2 * run + (2 (k / 4) + h) * 32 + lane
+                const size_t wbase = 2 * (size_t)C.p5off.back() + 8 * (size_t)run;
+                C.p5wide.resize(wbase + mx * 256, 0u);
+                for (size_t e = wbase; e < wbase + mx * 256; e += 2) C.p5wide[e] = (unsigned)C.itmax;      // padding: zero slot, density entry 0
+                for (int o = blk * 32; o < std::min(C.nout, blk * 32 + 32); ++o)
+                    for (size_t k = 0; k < terms[o].size(); ++k) {
+                        const size_t w = wbase + 4 * ((2 * (k / 4) + ((k & 3) >> 1)) * 32 + (size_t)(o & 31)) + 2 * (k & 1);
+                        C.p5wide[w] = terms[o][k] & 0xffffu;
+                        C.p5wide[w + 1] = terms[o][k] >> 16;
+                    }
+            }
+#endif
             run += (unsigned)mx * 32;
         }
         C.p5ptr.push_back(run);
@@ -484,8 +510,22 @@ inline ClassTablesDev class_tables_view(const ClassTablesHost& C, PtrOf ptr) {
     V.n_rt = (int)C.t_rt.size(); V.n_xy = (int)C.t_xy.size(); V.n_u = (int)C.t_u.size() / 2;
     V.t_rt = ptr(C.t_rt); V.t_xy = ptr(C.t_xy); V.t_u = ptr(C.t_u); V.t_s = ptr(C.t_s);
     V.p6 = ptr(C.p6); V.chunk_f0 = ptr(C.chunk_f0);
+#ifdef TUNA_SHELL_WIDE_TERMS
+    V.p5w = nullptr;      // set by the caller from scale_wide_terms(C.p5wide, nb)
+#endif
     return V;
 }
+
+#ifdef TUNA_SHELL_WIDE_TERMS
+// Device (or emulation) copy of the wide phase-5 table for a job that batches nb quartets: byte offsets = element offsets * 8 nb.
+// Density words additionally carry p_bias = oP - oIt of the job's shared-memory layout, so that both operands are addressed from
+// the It buffer.
+inline std::vector<unsigned> scale_wide_terms(const std::vector<unsigned>& wide, int nb, int p_bias) {
+    std::vector<unsigned> out(wide.size());
+    for (size_t i = 0; i < wide.size(); ++i) out[i] = (wide[i] + ((i & 1) ? (unsigned)p_bias : 0u)) * 8u * (unsigned)nb;
+    return out;
+}
+#endif
 
 struct HostPtrOf {
     template <class V> const typename V::value_type* operator()(const V& v) const { return v.data(); }

@@ -102,6 +102,13 @@ struct ClassTablesDev {
     //   p6[2i] = It slot | a << 16 | b << 21 | c << 26,  p6[2i+1] = d   (component indices inside the four shells)
     const unsigned* p6;
     const int* chunk_f0;                    // [nchunk+1] first p6 entry of each chunk
+#ifdef TUNA_SHELL_WIDE_TERMS
+    // Development variant (off by default): phase-5 terms as two 32-bit BYTE offsets (It slot, staged density entry), already
+    // multiplied by 8 NB for the job's batch size, in the same transposed 32-accumulator blocks (two 16-byte loads per quad):
+    // no shift/mask decode in the digestion loop.  Both offsets are relative to the It buffer (the density word includes
+    // (oP - oIt) 8 NB).  Chunk c starts at word 2 * p5off[c].
+    const unsigned* p5w;
+#endif
 };
 
 // One launch = one (bra pair class, ket pair class) job.
@@ -192,6 +199,37 @@ template <int NB>
 TUNA_HD QVec<NB> qld(const double* p) { return *reinterpret_cast<const QVec<NB>*>(p); }
 template <int NB>
 TUNA_HD void qst(double* p, const QVec<NB>& x) { *reinterpret_cast<QVec<NB>*>(p) = x; }
+
+#ifdef TUNA_SHELL_ASM_UNROLL
+// Development variant (off by default) of the phase-4 inner loops: the NY x/y-convolution operands of the y pair are loaded into
+// registers once per integral and the m' loop is fully unrolled, so every (m, m') term costs one shared load and NB FMAs instead of
+// two loads, NB FMAs and the control of a 1-4 trip loop.  Same summation order as the generic loop (bit-identical results).
+template <int NB, int NY>
+TUNA_HD QVec<NB> assemble_integral(const double* xyx, const double* xyy, const double* s_row, int mx0, int mx1, int my0) {
+    QVec<NB> y[NY];
+#pragma unroll
+    for (int k = 0; k < NY; ++k) y[k] = qld<NB>(xyy + (size_t)(my0 + k) * NB);
+    QVec<NB> val;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) val.v[q] = 0.0;
+    for (int m = mx0; m <= mx1; ++m) {
+        const double* sp = s_row + (size_t)(m + my0) * NB;
+        QVec<NB> t;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) t.v[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const QVec<NB> sv = qld<NB>(sp + (size_t)k * NB);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) t.v[q] = fma(y[k].v[q], sv.v[q], t.v[q]);
+        }
+        const QVec<NB> x = qld<NB>(xyx + (size_t)m * NB);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) val.v[q] = fma(x.v[q], t.v[q], val.v[q]);
+    }
+    return val;
+}
+#endif
 
 // NB shell quartets of the same class (pair ids AB[], CD[]; degeneracy weights w[]) processed TOGETHER by one group and folded
 // into the global accumulators Jf, Kf (nD matrices of ncart x ncart each) for densities Pf.  Batching NB quartets amortises
@@ -413,6 +451,15 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                         for (int q = 0; q < NB; ++q) val.v[q] = 0.0;
                         const double* xyx = XYq + (size_t)xo * NB;
                         const double* xyy = XYq + (size_t)yo * NB;
+#ifdef TUNA_SHELL_ASM_UNROLL
+                        const double* s_row = Sq + (size_t)so * NB;
+                        switch (my1 - my0) {
+                            case 0: val = assemble_integral<NB, 1>(xyx, xyy, s_row, mx0, mx1, my0); break;
+                            case 1: val = assemble_integral<NB, 2>(xyx, xyy, s_row, mx0, mx1, my0); break;
+                            case 2: val = assemble_integral<NB, 3>(xyx, xyy, s_row, mx0, mx1, my0); break;
+                            case 3: val = assemble_integral<NB, 4>(xyx, xyy, s_row, mx0, mx1, my0); break;
+                            default:
+#endif
                         for (int m = mx0; m <= mx1; ++m) {
                             QVec<NB> t;
 #pragma unroll
@@ -427,6 +474,9 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
 #pragma unroll
                             for (int q = 0; q < NB; ++q) val.v[q] = fma(x.v[q], t.v[q], val.v[q]);
                         }
+#ifdef TUNA_SHELL_ASM_UNROLL
+                        }
+#endif
                         QVec<NB> it = qld<NB>(Itq + (size_t)e * NB);
 #pragma unroll
                         for (int q = 0; q < NB; ++q) it.v[q] = fma(pref[q], val.v[q], it.v[q]);
@@ -471,6 +521,58 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                 }
             }
         }
+#ifdef TUNA_SHELL_WIDE_TERMS
+        if (any && !(skip & 32)) {
+            const unsigned* ptr = CT.p5ptr + (size_t)ch * (nblk + 1);
+            const uint4* term = reinterpret_cast<const uint4*>(CT.p5w + 2 * (size_t)CT.p5off[ch]);
+            TUNA_LANES(o, nout) {
+                const unsigned b0 = ptr[o >> 5], nq = (ptr[(o >> 5) + 1] - b0) >> 5;
+                if (nq == 0) continue;
+                for (int dn = 0; dn < nD; ++dn) {
+                    // both byte offsets of a term are relative to the It buffer (the density offsets carry oP - oIt), so every
+                    // operand address is one base register plus the table word
+                    const char* base = reinterpret_cast<const char*>(Itq) + (size_t)dn * nout * NB * sizeof(double);
+                    const uint4* tp = term + 2 * (size_t)b0 + (o & 31);      // half h of quad t at tp[(2 t + h) * 32]
+                    double s0[NB], s1[NB];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) { s0[q] = 0.0; s1[q] = 0.0; }
+#define TUNA_DIGEST_QUAD(TA, TB)                                                                                                   \
+    {                                                                                                                              \
+        const QVec<NB> i0 = qld<NB>(reinterpret_cast<const double*>(base - (size_t)dn * nout * NB * sizeof(double) + (TA).x));     \
+        const QVec<NB> p0 = qld<NB>(reinterpret_cast<const double*>(base + (TA).y));                                               \
+        const QVec<NB> i1 = qld<NB>(reinterpret_cast<const double*>(base - (size_t)dn * nout * NB * sizeof(double) + (TA).z));     \
+        const QVec<NB> p1 = qld<NB>(reinterpret_cast<const double*>(base + (TA).w));                                               \
+        const QVec<NB> i2 = qld<NB>(reinterpret_cast<const double*>(base - (size_t)dn * nout * NB * sizeof(double) + (TB).x));     \
+        const QVec<NB> p2 = qld<NB>(reinterpret_cast<const double*>(base + (TB).y));                                               \
+        const QVec<NB> i3 = qld<NB>(reinterpret_cast<const double*>(base - (size_t)dn * nout * NB * sizeof(double) + (TB).z));     \
+        const QVec<NB> p3 = qld<NB>(reinterpret_cast<const double*>(base + (TB).w));                                               \
+        _Pragma("unroll") for (int q = 0; q < NB; ++q) {                                                                           \
+            s0[q] = fma(i0.v[q], p0.v[q], s0[q]);                                                                                  \
+            s1[q] = fma(i1.v[q], p1.v[q], s1[q]);                                                                                  \
+            s0[q] = fma(i2.v[q], p2.v[q], s0[q]);                                                                                  \
+            s1[q] = fma(i3.v[q], p3.v[q], s1[q]);                                                                                  \
+        }                                                                                                                          \
+    }
+                    // two quads per trip in two register sets (no copies); the loads of the next trip are issued before the FMAs
+                    uint4 a0 = tp[0], a1 = tp[32];
+                    unsigned t = 0;
+                    for (; t + 1 < nq; t += 2) {
+                        const uint4 c0 = tp[64], c1 = tp[96];
+                        TUNA_DIGEST_QUAD(a0, a1)
+                        tp += 128;
+                        if (t + 2 < nq) { a0 = tp[0]; a1 = tp[32]; }
+                        TUNA_DIGEST_QUAD(c0, c1)
+                    }
+                    if (t < nq) TUNA_DIGEST_QUAD(a0, a1)
+#undef TUNA_DIGEST_QUAD
+                    QVec<NB> out = qld<NB>(Outq + (size_t)(dn * nout + o) * NB);
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) out.v[q] += s0[q] + s1[q];
+                    qst<NB>(Outq + (size_t)(dn * nout + o) * NB, out);
+                }
+            }
+        }
+#else
         if (any && !(skip & 32)) {
             const unsigned* ptr = CT.p5ptr + (size_t)ch * (nblk + 1);
             const uint4* term = reinterpret_cast<const uint4*>(CT.p5term + CT.p5off[ch]);
@@ -506,6 +608,7 @@ TUNA_HD void shell_quartets(const ShellJob& J, const ShellData& D, const bool* a
                 }
             }
         }
+#endif
         Pol::sync();
     }
     // ---- flush the shell blocks: one atomic per block entry per shell quartet ---------------------------------------

@@ -98,7 +98,11 @@ struct tuna_ctx {
     double* d_eval = nullptr;
     std::vector<size_t> class_list_off;
     struct JobHost { ShellJob job; int G; size_t smem; double allowed; int threads, gpc, nb = 1; bool own_launch = false; };
+#ifdef TUNA_SHELL_WIDE_TERMS
+    struct ClassTabDev { ClassTablesHost host; ClassTablesDev view; unsigned char* blob = nullptr; unsigned* wide[3] = {nullptr, nullptr, nullptr}; };   // wide[log2 nb]
+#else
     struct ClassTabDev { ClassTablesHost host; ClassTablesDev view; unsigned char* blob = nullptr; };
+#endif
     std::map<int, ClassTabDev> class_tabs;      // key La | Lb<<4 | Lc<<8 | Ld<<12
     std::vector<JobHost> jobs;
     struct LaunchGroup { int G = 1, nb = 1, threads = 128, njobs = 0, ctas_per_sm = 1; long long nunits = 0; size_t smem = 0, job_slot_off = 0;
@@ -843,8 +847,16 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 1
 
 // Single-job variant: the job descriptor travels as a kernel parameter (constant bank / uniform registers instead of shared
 // memory), which is ~25 % faster per quartet; used for class jobs large enough to fill the GPU on their own.
+#ifdef TUNA_SHELL_REG_TIERS
+// Development variant (off by default): a second instantiation with a 128-register budget for class jobs whose shared-memory
+// footprint already limits the SM to few CTAs, so the extra registers cost no occupancy (the 64-register build spills 144 bytes
+// and rematerialises addresses in the hot loops).
+template <int GG, int NB, int REGS>
+__global__ void __launch_bounds__((GG > 128) ? GG : 128, 65536 / (((GG > 128) ? GG : 128) * REGS)) k_shell_jk_one(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
+#else
 template <int GG, int NB>
 __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 128) ? GG : 128)) k_shell_jk_one(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
+#endif
                                                                          const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
                                                                          double tau, const unsigned long long* scalars, double* evaluated,
                                                                          int rank, int nranks) {
@@ -1099,6 +1111,9 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->d_P); dev_free(&ctx->d_J); dev_free(&ctx->d_K);
     dev_free(&ctx->d_Pc); dev_free(&ctx->d_Jc); dev_free(&ctx->d_Kc); dev_free(&ctx->d_tmp); dev_free(&ctx->d_Kpart);
     for (auto& kv : ctx->class_tabs) dev_free(&kv.second.blob);
+#ifdef TUNA_SHELL_WIDE_TERMS
+    for (auto& kv : ctx->class_tabs) for (int w = 0; w < 3; ++w) dev_free(&kv.second.wide[w]);
+#endif
     for (auto& g : ctx->groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
     dev_free(&ctx->d_pairA); dev_free(&ctx->d_pairB); dev_free(&ctx->d_pair_rec); dev_free(&ctx->d_rec);
     dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_prefix); dev_free(&ctx->d_finv); dev_free(&ctx->d_fnorm);
@@ -1769,6 +1784,9 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
     V.njst = (int)C.jst_ptr.size() - 1; V.njfl = (int)C.jflush.size();
     V.jst_ptr = (const unsigned*)(E.blob + o_jp); V.jst_list = (const unsigned short*)(E.blob + o_jl); V.jflush = (const unsigned*)(E.blob + o_jf);
     V.p6 = (const unsigned*)(E.blob + o_p6); V.chunk_f0 = (const int*)(E.blob + o_f0);
+#ifdef TUNA_SHELL_WIDE_TERMS
+    V.p5w = nullptr;
+#endif
     *out = &E;
     return TUNA_OK;
 }
@@ -1859,6 +1877,18 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
                 while (G < 256 && G * gdiv < jh.allowed) G *= 2;
                 while (G < 256 && (double)nb * J.total * 8.0 / G > smem_per_lane) G *= 2;
                 while (G < 256 && (size_t)(G <= 32 ? 128 / G : 1) * nb * J.total * 8 > 200 * 1024) G *= 2;
+#ifdef TUNA_SHELL_WIDE_TERMS
+                {   // the wide phase-5 table is scaled by 8 nb bytes: one device copy per (class, nb)
+                    const int wi = nb == 4 ? 2 : nb == 2 ? 1 : 0;
+                    if (!ctd->wide[wi]) {
+                        const std::vector<unsigned> w = scale_wide_terms(ctd->host.p5wide, nb, J.oP - J.oIt);
+                        if ((rc = dev_alloc(ctx, &ctd->wide[wi], std::max<size_t>(w.size(), 4)))) return rc;
+                        CK(cudaMemcpyAsync(ctd->wide[wi], w.data(), w.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+                        CK(cudaStreamSynchronize(ctx->stream));
+                    }
+                    J.ct.p5w = ctd->wide[wi];
+                }
+#endif
                 jh.G = G; jh.nb = nb;
                 jh.threads = G <= 32 ? 128 : G;
                 jh.gpc = jh.threads / G;
@@ -1955,6 +1985,40 @@ static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::LaunchGroup& lg, 
     return cudaGetLastError();
 }
 
+#ifdef TUNA_SHELL_REG_TIERS
+template <int GG, int NB, int REGS>
+static cudaError_t launch_shell_one_r(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
+                                      double* Jf, double* Kf, double tau, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_shell_jk_one<GG, NB, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const long long nchunk = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
+    const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;
+    long long blocks = (nchunk - srank + sn - 1) / sn;       // chunks owned by this rank
+    if (blocks <= 0) return cudaSuccess;
+    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
+    k_shell_jk_one<GG, NB, REGS><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars,
+                                                                           ctx->d_eval, srank, sn);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+template <int GG, int NB>
+static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
+                                    double* Jf, double* Kf, double tau, cudaStream_t stream) {
+    // CTAs per SM allowed by shared memory (1 KB reserved per CTA); the wide-register build is used when that many CTAs of
+    // jh.threads threads still fit 128 registers per thread (TUNA_B200_REG_TIER=0 forces the 64-register build)
+    static const bool tiers = !(getenv("TUNA_B200_REG_TIER") && atoi(getenv("TUNA_B200_REG_TIER")) == 0);
+    const size_t by_smem = std::max<size_t>(1, (size_t)(228 * 1024) / (jh.smem + 1024));
+    if constexpr (GG >= 64 && NB <= 2) {
+        if (tiers && by_smem * jh.threads * 128 <= 65536) return launch_shell_one_r<GG, NB, 128>(ctx, jh, D, nD, Pf, Psym, Jf, Kf, tau, stream);
+    }
+    return launch_shell_one_r<GG, NB, 64>(ctx, jh, D, nD, Pf, Psym, Jf, Kf, tau, stream);
+}
+#else
 template <int GG, int NB>
 static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                     double* Jf, double* Kf, double tau, cudaStream_t stream) {
@@ -1974,6 +2038,7 @@ static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, 
     ctx->launches++;
     return cudaGetLastError();
 }
+#endif
 
 // All class jobs of the cached job list: large ones as individual launches, the rest as grouped persistent launches, spread over
 // the auxiliary streams and joined back into ctx->stream.  eri_out != nullptr selects the dense-tensor fill (job list built with fill = 1).
