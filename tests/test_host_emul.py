@@ -150,3 +150,36 @@ def test_shell_engine_fill_mode_vs_oracle(emul, oracle, name):
     assert np.all(np.abs(out - ref) <= np.maximum(1e-12, 1e-13 * np.abs(ref)))
     assert np.array_equal(out == 0.0, ref == 0.0)
     assert np.array_equal(out, out.transpose(1, 0, 2, 3)) and np.array_equal(out, out.transpose(0, 1, 3, 2)) and np.array_equal(out, out.transpose(2, 3, 0, 1))
+
+
+def test_shell_engine_extreme_shells_of_the_headline_basis(emul, oracle):
+    """The tightest and the most diffuse shell of every angular momentum of the ET800 set (s exponent 2.1e5 ... h exponent 1.0) on both
+    atoms, unit-pair densities: sampled J/K elements against single integrals of the oracle (no dense tensor needed).  The same check
+    runs on the GPU at the full nbf 400 / 800 sizes (tests/test_zz_fullsize.py)."""
+    only_default(emul)
+    from tuna_b200 import workloads as w
+    from tuna_b200.basis import from_arrays
+    from util import check_unit_pair_jk, pick_function, unit_pair_density
+    sh = w.even_tempered_shells(800)
+    sel = []
+    for L in range(6):
+        ex = [a for (l, a) in sh if l == L]
+        sel += [(L, [a], [1.0]) for a in sorted({ex[0], ex[-1]})]
+    b = w.shells_to_components([sel, sel], [0.0, 1.10 * w.BOHR_PER_ANGSTROM])
+    fb = oracle.FlatBasis.from_reference_objects(from_arrays(b["origins"], b["lmn"], b["nprim"], b["exps"], b["raw_coefs"]))
+    n = fb.ncart
+    pairs = [(pick_function(fb, 0, 5, True, 0), pick_function(fb, 0, 5, True, 3)), (pick_function(fb, 0, 3, True, 9), pick_function(fb, 1, 5, False, 20))]
+    P = np.stack([unit_pair_density(n, k, l) for k, l in pairs])
+    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    oz = np.ascontiguousarray(fb.origins[:, 2])
+    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
+    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
+    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
+    J, K, stats = np.zeros_like(P), np.zeros_like(P), np.zeros(8, dtype=np.int64)
+    rc = emul.emul_jk_shell(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                            fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), 2, P.ctypes.data_as(dp), J.ctypes.data_as(dp),
+                            K.ctypes.data_as(dp), ctypes.c_double(1e-16), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    assert rc == 0
+    for d, (k, l) in enumerate(pairs):
+        assert check_unit_pair_jk(oracle, fb, k, l, J[d], K[d], n_samples=200) < 1e-12

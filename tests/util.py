@@ -59,3 +59,41 @@ def mo_inputs(g, n=None, seed=20261018):
     out["C_beta"] = np.ascontiguousarray(X @ Qb)
     out["eps"] = rng.standard_normal(2 * n)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full-size parity of direct J/K without a dense oracle tensor: unit-pair densities
+# ---------------------------------------------------------------------------------------------------------------------
+def pick_function(fb, atom, L, tight, comp=0):
+    """Index of component `comp` of the tightest / most diffuse shell of angular momentum L on atom 0 / 1 of a diatomic FlatBasis."""
+    z = fb.origins[:, 2]
+    Ls = np.asarray(fb.lmn).sum(axis=1)
+    m = np.where((Ls == L) & (z == (z.min() if atom == 0 else z.max())))[0]
+    e = np.asarray(fb.exps)[np.asarray(fb.offsets)[m]]
+    m = m[e == (e.max() if tight else e.min())]
+    return int(m[comp])
+
+
+def unit_pair_density(n, k, l):
+    """P = e_k e_l^T + e_l e_k^T: then J_ij = (ij|kl) + (ij|lk) and K_ij = (il|kj) + (ik|lj) (tuna_scf.py:42,70)."""
+    P = np.zeros((n, n))
+    P[k, l] += 1.0
+    P[l, k] += 1.0
+    return P
+
+
+def check_unit_pair_jk(oracle, fb, k, l, J, K, n_samples=300, seed=11):
+    """Compare sampled elements of J and K built from unit_pair_density(k, l) with single integrals of the oracle.
+    Tolerance: two ERIs, each within SURVEY.md 8(d)'s sweep tolerance max(1e-12, 1e-13 |ERI|).  Returns the worst abs error."""
+    rng = np.random.default_rng(seed)
+    n = fb.ncart
+    worst = 0.0
+    for i, j in zip(rng.integers(0, n, n_samples), rng.integers(0, n, n_samples)):
+        i, j = int(i), int(j)
+        a, b = oracle.eri_single(fb, i, j, k, l), oracle.eri_single(fb, i, j, l, k)
+        c, d = oracle.eri_single(fb, i, l, k, j), oracle.eri_single(fb, i, k, l, j)
+        for got, ref, scale in ((J[i, j], a + b, max(abs(a), abs(b))), (K[i, j], c + d, max(abs(c), abs(d)))):
+            err = abs(got - ref)
+            assert err <= 2 * max(1e-12, 1e-13 * scale), f"({i},{j}|{k},{l}): got {got!r}, oracle {ref!r}, diff {err:.2e}"
+            worst = max(worst, err)
+    return worst
