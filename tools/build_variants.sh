@@ -4,6 +4,8 @@
 #   TUNA_SHELL_WIDE_TERMS   phase 5: 8-byte terms with pre-scaled byte offsets, ping-pong quads (no decode, no register copies)
 #   TUNA_SHELL_ASM_UNROLL   phase 4: y operands in registers, m' loop unrolled per trip count
 #   TUNA_SHELL_REG_TIERS    128-register instantiation of k_shell_jk_one for class jobs whose shared memory limits occupancy anyway
+#   TUNA_MO_DMMA            AO->MO steps on the FP64 tensor cores (mma.sync m8n8k4 f64); check with
+#                           TUNA_B200_LIB=build/lib_dmma.so python -m pytest tests/test_mo_transform.py -m gpu && TUNA_B200_LIB=build/lib_dmma.so python tools/mo_quick.py
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p build
@@ -12,4 +14,5 @@ build lib_wide.so  "-DTUNA_SHELL_WIDE_TERMS"
 build lib_asm.so   "-DTUNA_SHELL_ASM_UNROLL"
 build lib_tiers.so "-DTUNA_SHELL_REG_TIERS"
 build lib_v3.so    "-DTUNA_SHELL_WIDE_TERMS -DTUNA_SHELL_ASM_UNROLL -DTUNA_SHELL_REG_TIERS"
+build lib_dmma.so  "-DTUNA_MO_DMMA"
 ls -la build
