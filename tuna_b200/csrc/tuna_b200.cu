@@ -113,7 +113,31 @@ struct tuna_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
     int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
+
+    // CUDA-graph replay of a direct J/K pass (TUNA_B200_GRAPH=1; off by default, NOT yet run on a GPU): small systems are bound by
+    // the ~240 launches of a build (nbf 100: 0.78 ms for 24 us of algorithmic work).  The first call with a given argument set runs
+    // normally (module attributes, allocations, job lists), the second is captured - fork/join over the auxiliary streams included -
+    // and every later one is a single cudaGraphLaunch.
+    struct GraphKey {
+        int nD = 0; const double* dP = nullptr; unsigned anti = 0; double* dJ = nullptr; double* dK = nullptr; double tau = 0.0;
+        int srank = 0, sn = 1; unsigned long long epoch = 0;
+        bool operator==(const GraphKey& o) const {
+            return nD == o.nD && dP == o.dP && anti == o.anti && dJ == o.dJ && dK == o.dK && tau == o.tau && srank == o.srank && sn == o.sn && epoch == o.epoch;
+        }
+    };
+    struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    bool graph_mode = false, capturing = false, warm_valid = false;
+    GraphKey warm_key;
+    std::vector<GraphEntry> graphs;
+    unsigned long long shell_epoch = 0;      // bumped whenever the job list / pair data behind a captured pass may have changed
 };
+
+static void drop_graphs(tuna_ctx* ctx) {
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+    ctx->warm_valid = false;
+    ctx->shell_epoch++;
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -1026,6 +1050,7 @@ static int ensure_mats(tuna_ctx* ctx, int nD, int n, int ncart) {
     int rc;
     const size_t need = (size_t)nD * n * n;
     if (need > ctx->cap_mat) {
+        drop_graphs(ctx);       // captured passes hold these buffers
         if ((rc = dev_alloc(ctx, &ctx->d_P, need))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_J, need))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_K, need))) return rc;
@@ -1033,6 +1058,7 @@ static int ensure_mats(tuna_ctx* ctx, int nD, int n, int ncart) {
     }
     const size_t needc = (size_t)nD * ncart * ncart;
     if (ncart > 0 && needc > ctx->cap_cart) {
+        drop_graphs(ctx);
         if ((rc = dev_alloc(ctx, &ctx->d_Pc, needc))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_Jc, needc))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_Kc, needc))) return rc;
@@ -1078,6 +1104,7 @@ int tuna_ctx_create(int device, tuna_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    { const char* g = getenv("TUNA_B200_GRAPH"); ctx->graph_mode = g && atoi(g) == 1; }
     for (int w = 0; w < 5; ++w)
         for (int s = 0; s < 2; ++s) CK(cudaEventCreate(&ctx->ev[w][s]));
     for (int a = 0; a < tuna_ctx::NAUX; ++a) {
@@ -1122,6 +1149,7 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->Uft.rowptr); dev_free(&ctx->Uft.col); dev_free(&ctx->Uft.val);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     dev_free(&ctx->d_mo_ws[0]); dev_free(&ctx->d_mo_ws[1]);
+    drop_graphs(ctx);
     for (int w = 0; w < 5; ++w)
         for (int s = 0; s < 2; ++s) if (ctx->ev[w][s]) cudaEventDestroy(ctx->ev[w][s]);
     for (int a = 0; a < tuna_ctx::NAUX; ++a) {
@@ -1147,6 +1175,7 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     if (!ctx) return TUNA_ERR_ARG;
     if (ncart <= 0 || !origins_z || !lmn || !nprim || !prim_offset || !exps || !coef_eff) FAIL(TUNA_ERR_ARG, "tuna_set_basis: null or empty basis");
     CK(cudaSetDevice(ctx->device));
+    drop_graphs(ctx);
     HostBasis& B = ctx->hb;
     B = HostBasis();
     B.ncart = ncart;
@@ -1207,6 +1236,7 @@ int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U) {
     if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_set_transform: call tuna_set_basis first");
     if (nbf <= 0 || !U) FAIL(TUNA_ERR_ARG, "tuna_set_transform: bad arguments");
     CK(cudaSetDevice(ctx->device));
+    drop_graphs(ctx);
     const int nc = ctx->ncart;
     std::vector<double> u(U, U + (size_t)nbf * nc), ut((size_t)nc * nbf);
     for (int p = 0; p < nbf; ++p)
@@ -1962,6 +1992,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
                 ctx->groups.push_back(lg);
             }
         ctx->shell_tau = tau;
+        ctx->shell_epoch++;
     }
     return TUNA_OK;
 }
@@ -2117,6 +2148,7 @@ static int shell_fill(tuna_ctx* ctx) {
 // Core of direct mode on DEVICE buffers: nD densities, bit d of anti_mask marks density d as antisymmetric
 // (its K is Kacc - Kacc^T and its J vanishes); all others must be symmetric.
 static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau);
+static int jk_direct_pass_graphed(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau);
 
 // Densities are processed in passes small enough for the largest class of the basis to fit its J/K blocks in shared memory.
 static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau) {
@@ -2133,9 +2165,60 @@ static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     const size_t nn = (size_t)ctx->nbf * ctx->nbf;
     for (int d0 = 0; d0 < nD; d0 += per) {
         const int nd = std::min(per, nD - d0);
-        int rc = jk_direct_pass(ctx, nd, dP + d0 * nn, (anti_mask >> d0) & ((1u << nd) - 1u), dJ ? dJ + d0 * nn : nullptr, dK ? dK + d0 * nn : nullptr, tau);
+        const bool graphed = ctx->graph_mode && ctx->direct_engine == 1 && ctx->ss.ok;
+        int rc = graphed ? jk_direct_pass_graphed(ctx, nd, dP + d0 * nn, (anti_mask >> d0) & ((1u << nd) - 1u), dJ ? dJ + d0 * nn : nullptr, dK ? dK + d0 * nn : nullptr, tau)
+                         : jk_direct_pass(ctx, nd, dP + d0 * nn, (anti_mask >> d0) & ((1u << nd) - 1u), dJ ? dJ + d0 * nn : nullptr, dK ? dK + d0 * nn : nullptr, tau);
         if (rc) return rc;
     }
+    return TUNA_OK;
+}
+
+// Graph mode (see tuna_ctx::GraphKey): replay a captured pass, or run / capture it.
+static int jk_direct_pass_graphed(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau) {
+    tuna_ctx::GraphKey key;
+    key.nD = nD; key.dP = dP; key.anti = anti_mask; key.dJ = dJ; key.dK = dK; key.tau = tau;
+    key.srank = ctx->shard_rank; key.sn = ctx->shard_n; key.epoch = ctx->shell_epoch;
+    for (auto& g : ctx->graphs)
+        if (g.key == key) {
+            CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));        // in graph mode the "dominant kernel" time covers the whole pass
+            CK(cudaGraphLaunch(g.exec, ctx->stream));
+            CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
+            ctx->launches += g.launches;
+            return TUNA_OK;
+        }
+    if (!(ctx->warm_valid && ctx->warm_key == key)) {                // first sighting: plain run (sets attributes, builds tables)
+        int rc = jk_direct_pass(ctx, nD, dP, anti_mask, dJ, dK, tau);
+        key.epoch = ctx->shell_epoch;                                // the run itself may have rebuilt the job list
+        ctx->warm_key = key; ctx->warm_valid = rc == TUNA_OK;
+        return rc;
+    }
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int64_t l0 = ctx->launches;
+    ctx->capturing = true;
+    int rc = jk_direct_pass(ctx, nD, dP, anti_mask, dJ, dK, tau);
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    const int64_t captured = ctx->launches - l0;
+    ctx->launches = l0;
+    if (rc || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->warm_valid = false;
+        if (rc) return rc;
+        FAIL(TUNA_ERR_CUDA, std::string("graph capture of the direct J/K pass failed: ") + cudaGetErrorString(e));
+    }
+    tuna_ctx::GraphEntry ge;
+    ge.key = key; ge.launches = captured;
+    e = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+    ctx->graphs.push_back(ge);
+    CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
+    CK(cudaGraphLaunch(ge.exec, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
+    ctx->launches += captured;
     return TUNA_OK;
 }
 
@@ -2165,7 +2248,7 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     ctx->launches++;
     CK(cudaMemsetAsync(ctx->d_Jc, 0, nD * ncc * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_Kc, 0, nD * ncc * sizeof(double), ctx->stream));
-    CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
+    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
     if (shell) {
         k_add_transpose_signed<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_Pc, ctx->d_tmp, nD, nc, 0u);   // Psym = P + P^T
         ctx->launches++;
@@ -2177,7 +2260,7 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
+    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
     // J = U (Jacc + Jacc^T) U^T,  K = U (Kacc +- Kacc^T) U^T
     for (int which = 0; which < 2; ++which) {
         double* acc = which == 0 ? ctx->d_Jc : ctx->d_Kc;
