@@ -33,6 +33,10 @@ def test_no_cpu_fallback_without_gpu():
     g = load_golden("h2_631g")
     with pytest.raises(tuna_b200.TunaError):
         tuna_b200.calculate_electron_repulsion_integral(*basis_objects(g))
+    with pytest.raises(tuna_b200.TunaError):                      # no CPU path behind the AO->MO transformation either
+        tuna_b200.transform_ERI_AO_to_MO(np.zeros((4,) * 4), np.eye(4), None, True)
+    with pytest.raises(tuna_b200.TunaError):
+        tuna_b200.calculate_coulomb_matrix(np.eye(4), np.zeros((4,) * 4))
 
 
 def test_basis_mirror_normalisation():
