@@ -18,17 +18,29 @@ VARIANTS = {"": [], "wide_terms": ["-DTUNA_SHELL_WIDE_TERMS"], "asm_unroll": ["-
             "all": ["-DTUNA_SHELL_WIDE_TERMS", "-DTUNA_SHELL_ASM_UNROLL"]}
 
 
+class LazyEmul:
+    """Compiles tests/host_emul/emul.cpp with the variant's macros on first use (skipped variant cases cost nothing)."""
+
+    def __init__(self, tag):
+        self.variant = tag
+        self._lib = None
+
+    def __getattr__(self, name):
+        if self._lib is None:
+            tag = self.variant
+            so = os.path.join(HERE, "host_emul", f"libemul{'_' + tag if tag else ''}.so")
+            src = os.path.join(HERE, "host_emul", "emul.cpp")
+            subprocess.run(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-x", "c++"] + VARIANTS[tag] + ["-o", so, src, "-lm"], check=True)
+            lib = ctypes.CDLL(so)
+            lib.emul_boys.restype = ctypes.c_double
+            lib.emul_boys.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double]
+            self._lib = lib
+        return getattr(self._lib, name)
+
+
 @pytest.fixture(scope="module", params=list(VARIANTS))
 def emul(request):
-    tag = request.param
-    so = os.path.join(HERE, "host_emul", f"libemul{'_' + tag if tag else ''}.so")
-    src = os.path.join(HERE, "host_emul", "emul.cpp")
-    subprocess.run(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-x", "c++"] + VARIANTS[tag] + ["-o", so, src, "-lm"], check=True)
-    lib = ctypes.CDLL(so)
-    lib.variant = tag
-    lib.emul_boys.restype = ctypes.c_double
-    lib.emul_boys.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double]
-    return lib
+    return LazyEmul(request.param)
 
 
 def only_default(emul, *allowed):
