@@ -91,13 +91,26 @@ int tuna_eri_transform(tuna_ctx* ctx, int n, const double* eri_host, int n1, con
 int tuna_eri_transform_dev(tuna_ctx* ctx, int n, const double* d_eri, int n1, const double* dC1, int n2, const double* dC2,
                            int so_layout, double* d_out);
 
+/* One-electron integrals of the basis given to tuna_set_basis, in the Cartesian basis:
+ *   tuna_integral.calculate_one_electron_integrals(n_basis, basis_functions, n_atoms, atoms, dipole_origin, num_threads)   pyx:282-445
+ * S overlap, T kinetic energy, V nuclear attraction (sum over the n_atoms nuclei at atom_z with charges atom_charge, all on the z
+ * axis like the reference's own nuclear integral, pyx:783), D[3] dipole (x, y, z) and Q[3] diagonal quadrupole (xx, yy, zz)
+ * about dipole_origin[3].  S, T, V: n x n; D, Q: 3 x n x n. */
+int tuna_one_electron(tuna_ctx* ctx, int n_atoms, const double* atom_z, const double* atom_charge, const double* dipole_origin,
+                      double* S, double* T, double* V, double* D, double* Q);
+/* tuna_integral.calculate_cross_basis_overlap_matrix (pyx:626-778): S12[i][j] = <bf_1[i] | bf_2[j]> for two independent bases,
+ * each passed like the arguments of tuna_set_basis.  Needs no basis in the context. */
+int tuna_cross_overlap(tuna_ctx* ctx, int n1, const double* origins_z1, const int32_t* lmn1, const int32_t* nprim1, const int64_t* prim_offset1,
+                       const double* exps1, const double* coef_eff1, int n2, const double* origins_z2, const int32_t* lmn2, const int32_t* nprim2,
+                       const int64_t* prim_offset2, const double* exps2, const double* coef_eff2, double* S12);
+
 /* Introspection for tests and bench.py.
  * counts[0] AO pairs, [1] unique AO quartets, [2] quartets passing the x/y parity test (pyx:1324-1327),
  * [3] primitive quartets among those, [4] quartets evaluated by the last direct build (after screening, this rank),
  * [5] kernels launched by this context so far, [6] ncart, [7] nbf. */
 int tuna_get_counts(const tuna_ctx* ctx, int64_t counts[8]);
 /* Device time (ms, CUDA events on the launching stream) of the dominant kernel of the last call:
- * which = 0 ERI fill, 1 cart->sph, 2 stored J/K, 3 direct J/K, 4 AO->MO transformation.  Synchronises the stream. */
+ * which = 0 ERI fill, 1 cart->sph, 2 stored J/K, 3 direct J/K, 4 AO->MO transformation, 5 one-electron integrals.  Synchronises the stream. */
 int tuna_last_kernel_ms(tuna_ctx* ctx, int which, float* ms);
 /* Algorithmic FP64 flop count of the reference algorithm for the parity-surviving unique quartets of the
  * current basis (formula F(a,b) of SURVEY.md section 8d), and the J/K digestion flops per density. */

@@ -12,6 +12,7 @@ Restated here in NumPy (file:line under /root/reference/TUNA/):
     transform_eri_ao_to_so  <- tuna_ci.py:143-193, :564       (four einsums, layout pqrs; spin blocking)
     FlatBasis.from_*        <- tuna_integrals/tuna_integral.pyx:78-235 (Basis + normalize)
     eri_fill / eri_single   -> oracle/eri_oracle.c            (pyx:961-1414, :1490-1651)
+    one_electron / cross_overlap -> oracle/oneel_oracle.c     (pyx:282-912, :1428-1489)
 """
 import ctypes
 import os
@@ -35,7 +36,8 @@ def _lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "liboracle.so")
-        if not os.path.exists(path):
+        srcs = [os.path.join(_HERE, f) for f in ("eri_oracle.c", "oneel_oracle.c")]
+        if not os.path.exists(path) or any(os.path.getmtime(f) > os.path.getmtime(path) for f in srcs):
             subprocess.run(["make", "-s", "-C", _HERE, "liboracle.so"], check=True)
         lib = ctypes.CDLL(path)
         dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_long)
@@ -48,6 +50,10 @@ def _lib():
         lib.oracle_normalize.argtypes = [ctypes.c_int] * 3 + [ctypes.c_long, dp, dp, dp]
         lib.oracle_normalize.restype = None
         lib.oracle_max_threads.restype = ctypes.c_int
+        lib.oracle_one_electron.argtypes = [ctypes.c_long, dp, ip, lp, lp, dp, dp, ctypes.c_long, dp, dp, dp, dp, dp, dp, dp, dp, ctypes.c_int]
+        lib.oracle_one_electron.restype = ctypes.c_int
+        lib.oracle_cross_overlap.argtypes = [ctypes.c_long, dp, ip, lp, lp, dp, dp] * 2 + [dp]
+        lib.oracle_cross_overlap.restype = ctypes.c_int
         _LIB = lib
     return _LIB
 
@@ -129,6 +135,36 @@ def eri_fill(basis: FlatBasis, nthreads: int = 0) -> np.ndarray:
 
 def eri_single(basis: FlatBasis, i, j, k, l) -> float:
     return float(_lib().oracle_eri_single(*basis._c_args(), i, j, k, l))
+
+
+def _flat_args(basis: FlatBasis):
+    """(oz, lmn, nprim, offsets, exps, coef_eff) for the one-electron entry points; coef_eff = norm * coefs (pyx:504-508)."""
+    keep = (np.ascontiguousarray(basis.origins[:, 2]), np.ascontiguousarray(basis.lmn, dtype=np.int32), np.ascontiguousarray(basis.nprim, dtype=np.int64),
+            np.ascontiguousarray(basis.offsets, dtype=np.int64), np.ascontiguousarray(basis.exps), np.ascontiguousarray(basis.coefs * basis.norms))
+    return keep, (_p(keep[0], ctypes.c_double), _p(keep[1], ctypes.c_int), _p(keep[2], ctypes.c_long), _p(keep[3], ctypes.c_long),
+                  _p(keep[4], ctypes.c_double), _p(keep[5], ctypes.c_double))
+
+
+def one_electron(basis: FlatBasis, atom_z, atom_charge, dipole_origin):
+    """(S, T, V_NE, D[3], Q[3]) in the Cartesian basis, restating calculate_one_electron_integrals (pyx:282-445)."""
+    n = basis.ncart
+    az = np.ascontiguousarray(atom_z, dtype=np.float64)
+    ac = np.ascontiguousarray(atom_charge, dtype=np.float64)
+    og = np.ascontiguousarray(dipole_origin, dtype=np.float64)
+    S, T, V, D, Q = np.empty((n, n)), np.empty((n, n)), np.empty((n, n)), np.empty((3, n, n)), np.empty((3, n, n))
+    keep, args = _flat_args(basis)
+    d = ctypes.c_double
+    _lib().oracle_one_electron(n, *args, len(az), _p(az, d), _p(ac, d), _p(og, d), _p(S, d), _p(T, d), _p(V, d), _p(D, d), _p(Q, d), 0)
+    return S, T, V, D, Q
+
+
+def cross_overlap(basis_1: FlatBasis, basis_2: FlatBasis):
+    """S12[i, j] = <bf_1[i] | bf_2[j]>, restating calculate_cross_basis_overlap_matrix (pyx:626-778)."""
+    out = np.empty((basis_1.ncart, basis_2.ncart))
+    k1, a1 = _flat_args(basis_1)
+    k2, a2 = _flat_args(basis_2)
+    _lib().oracle_cross_overlap(basis_1.ncart, *a1, basis_2.ncart, *a2, _p(out, ctypes.c_double))
+    return out
 
 
 def boys(m: int, T: float) -> float:

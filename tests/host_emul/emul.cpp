@@ -183,3 +183,33 @@ extern "C" int emul_fill_shell(int ncart, const double* oz, const int* lmn, cons
     g_fill_out = nullptr;
     return rc;
 }
+
+// ---- one-electron integrals (oneel_core.cuh), serial on the CPU ------------------------------------------------------
+#include "../../tuna_b200/csrc/oneel_core.cuh"
+
+extern "C" int emul_one_electron(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
+                                 const double* ceff, int natoms, const double* atom_z, const double* atom_charge, const double* origin, double* S,
+                                 double* T, double* V, double* D, double* Q) {
+    std::vector<double> boys;
+    build_boys_table(boys);
+    const size_t n = (size_t)ncart, nn = n * n;
+    for (int i = 0; i < ncart; ++i)
+        for (int j = 0; j <= i; ++j) {
+            const OneElPair o = one_electron_pair(lmn + 3 * i, oz[i], nprim[i], exps + off[i], ceff + off[i], lmn + 3 * j, oz[j], nprim[j], exps + off[j],
+                                                  ceff + off[j], natoms, atom_z, atom_charge, origin, boys.data());
+            const size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
+            S[ij] = S[ji] = o.s; T[ij] = T[ji] = o.t; V[ij] = V[ji] = o.v;
+            for (int c = 0; c < 3; ++c) { D[c * nn + ij] = D[c * nn + ji] = o.d[c]; Q[c * nn + ij] = Q[c * nn + ji] = o.q[c]; }
+        }
+    return 0;
+}
+
+extern "C" int emul_cross_overlap(int n1, const double* oz1, const int* lmn1, const int* nprim1, const int64_t* off1, const double* exps1,
+                                  const double* ceff1, int n2, const double* oz2, const int* lmn2, const int* nprim2, const int64_t* off2,
+                                  const double* exps2, const double* ceff2, double* S12) {
+    for (int i = 0; i < n1; ++i)
+        for (int j = 0; j < n2; ++j)
+            S12[(size_t)i * n2 + j] = overlap_pair(lmn1 + 3 * i, oz1[i], nprim1[i], exps1 + off1[i], ceff1 + off1[i], lmn2 + 3 * j, oz2[j], nprim2[j],
+                                                   exps2 + off2[j], ceff2 + off2[j]);
+    return 0;
+}

@@ -98,7 +98,7 @@ def test_handle_forwards_ndarray_protocol():
 
 
 def test_install_rebinds_reference_names_and_uninstall_restores():
-    """install() on the UNMODIFIED reference modules (dev container only): the eight names of INTEGRATION.md section 2 are rebound,
+    """install() on the UNMODIFIED reference modules (dev container only): the ten names of INTEGRATION.md section 2 are rebound,
     the reference's TunaError / timer / log are adopted, uninstall() restores the originals.  No compute call (no GPU here)."""
     import importlib
     import sys
@@ -114,7 +114,9 @@ def test_install_rebinds_reference_names_and_uninstall_restores():
     saved_err = _lib.error_class
     originals = tuna_b200.install()
     try:
-        assert len(originals) == 8
+        assert len(originals) == 10
+        assert ns.ints.calculate_one_electron_integrals is tuna_b200.calculate_one_electron_integrals
+        assert ns.ints.calculate_cross_basis_overlap_matrix is tuna_b200.calculate_cross_basis_overlap_matrix
         assert ns.ints.calculate_electron_repulsion_integrals is tuna_b200.calculate_electron_repulsion_integrals
         assert ns.ints.calculate_electron_repulsion_integral is tuna_b200.calculate_electron_repulsion_integral
         assert ns.kern.calculate_two_electron_integrals is tuna_b200.calculate_two_electron_integrals

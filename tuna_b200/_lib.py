@@ -18,6 +18,7 @@ EXPORTS = [
     "tuna_eri_fill_cart", "tuna_eri_cart_to_sph", "tuna_eri_download", "tuna_eri_upload", "tuna_eri_single", "tuna_schwarz",
     "tuna_jk_stored", "tuna_jk_stored_dev", "tuna_jk_direct", "tuna_jk_direct_dev", "tuna_set_shard", "tuna_get_counts",
     "tuna_last_kernel_ms", "tuna_algorithmic_flops", "tuna_fp64_peak_probe", "tuna_eri_transform", "tuna_eri_transform_dev",
+    "tuna_one_electron", "tuna_cross_overlap",
 ]
 
 _lib = None
@@ -66,6 +67,8 @@ def load() -> ctypes.CDLL:
         "tuna_fp64_peak_probe": (ci, [vp, c_dp]),
         "tuna_eri_transform": (ci, [vp, ci, c_dp, ci, c_dp, ci, c_dp, ci, c_dp]),
         "tuna_eri_transform_dev": (ci, [vp, ci, vp, ci, vp, ci, vp, ci, vp]),
+        "tuna_one_electron": (ci, [vp, ci, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+        "tuna_cross_overlap": (ci, [vp] + [ci, c_dp, c_ip, c_ip, c_lp, c_dp, c_dp] * 2 + [c_dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -94,7 +97,7 @@ def _host_tensor(shape):
 class Context:
     """One (device, geometry, basis): owns the pair table and any device-resident tensors."""
 
-    KERNEL_ERI, KERNEL_SPH, KERNEL_JK_STORED, KERNEL_JK_DIRECT, KERNEL_MO_TRANSFORM = 0, 1, 2, 3, 4
+    KERNEL_ERI, KERNEL_SPH, KERNEL_JK_STORED, KERNEL_JK_DIRECT, KERNEL_MO_TRANSFORM, KERNEL_ONE_ELECTRON = 0, 1, 2, 3, 4, 5
 
     def __init__(self, device: int = 0):
         self._lib = load()
@@ -216,6 +219,37 @@ class Context:
     def eri_transform_dev(self, n, dT, n1, dC1, n2, dC2, so_layout, d_out):
         self._ck(self._lib.tuna_eri_transform_dev(self._h, n, ctypes.c_void_p(dT), n1, ctypes.c_void_p(dC1), n2, ctypes.c_void_p(dC2),
                                                   int(bool(so_layout)), ctypes.c_void_p(d_out)))
+
+    def one_electron(self, atom_z, atom_charge, dipole_origin):
+        """(S, T, V_NE, D[3], Q[3]) of the current basis in the Cartesian basis (tuna_integral.calculate_one_electron_integrals, pyx:282-445)."""
+        az = np.ascontiguousarray(atom_z, dtype=np.float64)
+        ac = np.ascontiguousarray(atom_charge, dtype=np.float64)
+        og = np.ascontiguousarray(dipole_origin, dtype=np.float64)
+        if az.ndim != 1 or az.shape != ac.shape or og.shape != (3,) or len(az) == 0:
+            raise error_class("tuna_b200: atoms must be given as equally long z / charge vectors and the origin as 3 numbers")
+        n = self.ncart
+        S, T, V, D, Q = np.empty((n, n)), np.empty((n, n)), np.empty((n, n)), np.empty((3, n, n)), np.empty((3, n, n))
+        self._ck(self._lib.tuna_one_electron(self._h, len(az), _dp(az), _dp(ac), _dp(og), _dp(S), _dp(T), _dp(V), _dp(D), _dp(Q)))
+        return S, T, V, D, Q
+
+    def cross_overlap(self, flat_1, flat_2):
+        """S12[i, j] = <bf_1[i] | bf_2[j]> for two flattened bases (origins_z, lmn, nprim, exps, coef_eff) (pyx:626-778)."""
+        i32p, i64p = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64)
+        args, keep = [], []
+        for oz, lmn, nprim, exps, ce in (flat_1, flat_2):
+            oz = np.ascontiguousarray(oz, dtype=np.float64)
+            lmn = np.ascontiguousarray(lmn, dtype=np.int32).reshape(-1, 3)
+            nprim = np.ascontiguousarray(nprim, dtype=np.int32)
+            off = np.concatenate([[0], np.cumsum(nprim)[:-1]]).astype(np.int64)
+            exps = np.ascontiguousarray(exps, dtype=np.float64)
+            ce = np.ascontiguousarray(ce, dtype=np.float64)
+            if not (len(oz) == len(lmn) == len(nprim)) or len(oz) == 0 or len(exps) != int(nprim.sum()) or len(ce) != len(exps):
+                raise error_class("tuna_b200: inconsistent basis arrays")
+            keep.append((oz, lmn, nprim, off, exps, ce))
+            args += [len(oz), _dp(oz), lmn.ctypes.data_as(i32p), nprim.ctypes.data_as(i32p), off.ctypes.data_as(i64p), _dp(exps), _dp(ce)]
+        out = np.empty((args[0], args[7]))
+        self._ck(self._lib.tuna_cross_overlap(self._h, *args, _dp(out)))
+        return out
 
     def _jk(self, fn, P, n, want_j, want_k, *extra):
         P = np.ascontiguousarray(P, dtype=np.float64)

@@ -24,6 +24,7 @@
 #include "shell_host.hpp"
 #include "shell_jk.cuh"
 #include "mo_transform.cuh"
+#include "oneel_core.cuh"
 
 using namespace tuna;
 
@@ -81,7 +82,7 @@ struct tuna_ctx {
     unsigned long long* d_scalars = nullptr;   // [0] max|P| bits, [1] evaluated-quartet counter
 
     int shard_rank = 0, shard_n = 1;
-    cudaEvent_t ev[5][2] = {};
+    cudaEvent_t ev[6][2] = {};
 
     // AO -> MO four-index transformation (mo_transform.cuh): two ping-pong work buffers, grown on demand
     double* d_mo_ws[2] = {nullptr, nullptr};
@@ -1105,7 +1106,7 @@ int tuna_ctx_create(int device, tuna_ctx** out) {
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     { const char* g = getenv("TUNA_B200_GRAPH"); ctx->graph_mode = g && atoi(g) == 1; }
-    for (int w = 0; w < 5; ++w)
+    for (int w = 0; w < 6; ++w)
         for (int s = 0; s < 2; ++s) CK(cudaEventCreate(&ctx->ev[w][s]));
     for (int a = 0; a < tuna_ctx::NAUX; ++a) {
         CK(cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking));
@@ -1150,7 +1151,7 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     dev_free(&ctx->d_mo_ws[0]); dev_free(&ctx->d_mo_ws[1]);
     drop_graphs(ctx);
-    for (int w = 0; w < 5; ++w)
+    for (int w = 0; w < 6; ++w)
         for (int s = 0; s < 2; ++s) if (ctx->ev[w][s]) cudaEventDestroy(ctx->ev[w][s]);
     for (int a = 0; a < tuna_ctx::NAUX; ++a) {
         if (ctx->aux[a]) { cudaStreamSynchronize(ctx->aux[a]); cudaStreamDestroy(ctx->aux[a]); }
@@ -1731,6 +1732,149 @@ int tuna_eri_transform(tuna_ctx* ctx, int n, const double* eri_host, int n1, con
     }
     cleanup();
     return rc;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// One-electron integrals: overlap, kinetic, nuclear attraction, dipole, diagonal quadrupole
+// (tuna_integral.pyx:282-445) and the cross-basis overlap (:626-778); math in oneel_core.cuh
+// ------------------------------------------------------------------------------------------------
+struct BasisDev {
+    int n = 0;
+    double* oz = nullptr; int* lmn = nullptr; int* nprim = nullptr; int64_t* off = nullptr; double* exps = nullptr; double* ceff = nullptr;
+};
+
+static void basis_dev_free(BasisDev& B) {
+    dev_free(&B.oz); dev_free(&B.lmn); dev_free(&B.nprim); dev_free(&B.off); dev_free(&B.exps); dev_free(&B.ceff);
+}
+
+static int basis_dev_upload(tuna_ctx* ctx, BasisDev& B, int n, const double* oz, const int32_t* lmn, const int32_t* nprim, const int64_t* off,
+                            const double* exps, const double* ceff) {
+    int64_t tot = 0;
+    for (int i = 0; i < n; ++i) {
+        if (nprim[i] <= 0) FAIL(TUNA_ERR_ARG, "basis function without primitives");
+        for (int c = 0; c < 3; ++c)
+            if (lmn[3 * i + c] < 0 || lmn[3 * i] + lmn[3 * i + 1] + lmn[3 * i + 2] > OE_LMAX) FAIL(TUNA_ERR_ARG, "angular momentum outside 0..5 (only up to H functions, tuna_molecule.py:612-618)");
+        tot = std::max<int64_t>(tot, off[i] + nprim[i]);
+    }
+    B.n = n;
+    int rc;
+    if ((rc = dev_alloc(ctx, &B.oz, (size_t)n)) || (rc = dev_alloc(ctx, &B.lmn, (size_t)3 * n)) || (rc = dev_alloc(ctx, &B.nprim, (size_t)n)) ||
+        (rc = dev_alloc(ctx, &B.off, (size_t)n)) || (rc = dev_alloc(ctx, &B.exps, (size_t)tot)) || (rc = dev_alloc(ctx, &B.ceff, (size_t)tot)))
+        return rc;
+    CK(cudaMemcpyAsync(B.oz, oz, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.lmn, lmn, (size_t)3 * n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.nprim, nprim, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.off, off, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.exps, exps, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.ceff, ceff, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return TUNA_OK;
+}
+
+// One thread per AO pair i >= j; out = [S | T | V | D(3) | Q(3)], nine n x n matrices, both triangles written.
+__global__ void __launch_bounds__(128) k_one_electron(BasisDev B, int natoms, const double* __restrict__ atoms /* z[natoms] | charge[natoms] | origin[3] */,
+                                                      const double* __restrict__ boys, double* __restrict__ out) {
+    const long long n = B.n, idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    if (j > i) return;
+    const OneElPair o = one_electron_pair(B.lmn + 3 * i, B.oz[i], B.nprim[i], B.exps + B.off[i], B.ceff + B.off[i], B.lmn + 3 * j, B.oz[j], B.nprim[j],
+                                          B.exps + B.off[j], B.ceff + B.off[j], natoms, atoms, atoms + natoms, atoms + 2 * natoms, boys);
+    const size_t nn = (size_t)n * n, ij = (size_t)i * n + j, ji = (size_t)j * n + i;
+    out[ij] = o.s; out[ji] = o.s;
+    out[nn + ij] = o.t; out[nn + ji] = o.t;
+    out[2 * nn + ij] = o.v; out[2 * nn + ji] = o.v;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        out[(3 + c) * nn + ij] = o.d[c]; out[(3 + c) * nn + ji] = o.d[c];
+        out[(6 + c) * nn + ij] = o.q[c]; out[(6 + c) * nn + ji] = o.q[c];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_cross_overlap(BasisDev A, BasisDev B, double* __restrict__ out) {
+    const long long n2 = B.n, idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)A.n * n2) return;
+    const int i = (int)(idx / n2), j = (int)(idx % n2);
+    out[idx] = overlap_pair(A.lmn + 3 * i, A.oz[i], A.nprim[i], A.exps + A.off[i], A.ceff + A.off[i], B.lmn + 3 * j, B.oz[j], B.nprim[j], B.exps + B.off[j],
+                            B.ceff + B.off[j]);
+}
+
+extern "C" {
+
+int tuna_one_electron(tuna_ctx* ctx, int n_atoms, const double* atom_z, const double* atom_charge, const double* dipole_origin, double* S, double* T,
+                      double* V, double* D, double* Q) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_one_electron: call tuna_set_basis first");
+    if (n_atoms <= 0 || !atom_z || !atom_charge || !dipole_origin || !S || !T || !V || !D || !Q) FAIL(TUNA_ERR_ARG, "tuna_one_electron: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const HostBasis& H = ctx->hb;
+    const int n = ctx->ncart;
+    const size_t nn = (size_t)n * n;
+    std::vector<int32_t> np32(H.nprim.begin(), H.nprim.end()), lmn32(H.lmn.begin(), H.lmn.end());
+    std::vector<double> at((size_t)2 * n_atoms + 3);
+    for (int a = 0; a < n_atoms; ++a) { at[a] = atom_z[a]; at[n_atoms + a] = atom_charge[a]; }
+    for (int c = 0; c < 3; ++c) at[2 * n_atoms + c] = dipole_origin[c];
+    BasisDev B;
+    double* d_at = nullptr; double* d_out = nullptr;
+    int rc = basis_dev_upload(ctx, B, n, H.oz.data(), lmn32.data(), np32.data(), H.off.data(), H.exps.data(), H.ceff.data());
+    if (!rc) rc = dev_alloc(ctx, &d_at, at.size());
+    if (!rc) rc = dev_alloc(ctx, &d_out, 9 * nn);
+    cudaError_t e = cudaSuccess;
+    std::vector<double> host;
+    if (!rc) {
+        e = cudaMemcpyAsync(d_at, at.data(), at.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5][0], ctx->stream);
+        if (e == cudaSuccess) {
+            k_one_electron<<<(unsigned)((nn + 127) / 128), 128, 0, ctx->stream>>>(B, n_atoms, d_at, ctx->d_boys, d_out);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5][1], ctx->stream);
+        host.resize(9 * nn);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), d_out, 9 * nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    basis_dev_free(B); dev_free(&d_at); dev_free(&d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("tuna_one_electron: ") + cudaGetErrorString(e));
+    std::memcpy(S, host.data(), nn * sizeof(double));
+    std::memcpy(T, host.data() + nn, nn * sizeof(double));
+    std::memcpy(V, host.data() + 2 * nn, nn * sizeof(double));
+    std::memcpy(D, host.data() + 3 * nn, 3 * nn * sizeof(double));
+    std::memcpy(Q, host.data() + 6 * nn, 3 * nn * sizeof(double));
+    return TUNA_OK;
+}
+
+int tuna_cross_overlap(tuna_ctx* ctx, int n1, const double* oz1, const int32_t* lmn1, const int32_t* nprim1, const int64_t* off1, const double* exps1,
+                       const double* ceff1, int n2, const double* oz2, const int32_t* lmn2, const int32_t* nprim2, const int64_t* off2,
+                       const double* exps2, const double* ceff2, double* S12) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (n1 <= 0 || n2 <= 0 || !oz1 || !lmn1 || !nprim1 || !off1 || !exps1 || !ceff1 || !oz2 || !lmn2 || !nprim2 || !off2 || !exps2 || !ceff2 || !S12)
+        FAIL(TUNA_ERR_ARG, "tuna_cross_overlap: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    BasisDev A, B;
+    double* d_out = nullptr;
+    const size_t count = (size_t)n1 * n2;
+    int rc = basis_dev_upload(ctx, A, n1, oz1, lmn1, nprim1, off1, exps1, ceff1);
+    if (!rc) rc = basis_dev_upload(ctx, B, n2, oz2, lmn2, nprim2, off2, exps2, ceff2);
+    if (!rc) rc = dev_alloc(ctx, &d_out, count);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        k_cross_overlap<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(A, B, d_out);
+        ctx->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(S12, d_out, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    basis_dev_free(A); basis_dev_free(B); dev_free(&d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("tuna_cross_overlap: ") + cudaGetErrorString(e));
+    return TUNA_OK;
 }
 
 }  // extern "C"
@@ -2355,7 +2499,7 @@ int tuna_get_counts(const tuna_ctx* c, int64_t counts[8]) {
 }
 
 int tuna_last_kernel_ms(tuna_ctx* ctx, int which, float* ms) {
-    if (!ctx || !ms || which < 0 || which > 4) return TUNA_ERR_ARG;
+    if (!ctx || !ms || which < 0 || which > 5) return TUNA_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));

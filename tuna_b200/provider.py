@@ -14,6 +14,8 @@ no reference edits.  The only compute path is libtuna_b200.so on a CUDA device â
     tuna_scf.calculate_exchange_matrix                    tuna_scf.py:27-44
     tuna_ci.transform_ERI_AO_to_MO                        tuna_ci.py:204-255      
     tuna_ci.transform_ERI_AO_to_SO                        tuna_ci.py:143-193
+    tuna_integral.calculate_one_electron_integrals        pyx:282-445             
+    tuna_integral.calculate_cross_basis_overlap_matrix    pyx:626-778
 """
 import os
 import weakref
@@ -330,6 +332,35 @@ def transform_ERI_AO_to_SO(ERI_AO, C_1, C_2, calculation, silent):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# tuna_integral level: one-electron integrals
+# ---------------------------------------------------------------------------------------------------------
+def calculate_one_electron_integrals(n_basis, basis_functions, n_atoms, atoms, dipole_origin, num_threads):
+    """(S_cart, T_cart, V_cart, D_cart, Q_cart) in Cartesian harmonics (pyx:282-445): overlap, kinetic, nuclear attraction,
+    dipole (3, n, n) and diagonal quadrupole (3, n, n) about `dipole_origin`.  `num_threads` is advisory and ignored."""
+    if len(basis_functions) != n_basis or len(atoms) != n_atoms:
+        raise _lib.error_class("tuna_b200: n_basis / n_atoms do not match the lists")
+    pos = np.array([np.asarray(a.origin, dtype=np.float64) for a in atoms]).reshape(n_atoms, 3)
+    if np.any(pos[:, :2] != 0.0):
+        raise _lib.error_class("tuna_b200: all atoms must lie on the z axis")       # as the reference's nuclear integral requires (pyx:783)
+    ctx = _context_for(basis_functions)
+    try:
+        return ctx.one_electron(pos[:, 2], [float(a.charge) for a in atoms], np.asarray(dipole_origin, dtype=np.float64))
+    finally:
+        ctx.close()
+
+
+def calculate_cross_basis_overlap_matrix(n_basis_1, n_basis_2, basis_functions_1, basis_functions_2, num_threads):
+    """S_cross[i, j] = <bf_1[i] | bf_2[j]> between two basis sets (pyx:626-778; the minimal-basis guess projection, tuna_guess.py:281)."""
+    if len(basis_functions_1) != n_basis_1 or len(basis_functions_2) != n_basis_2:
+        raise _lib.error_class("tuna_b200: basis sizes do not match the lists")
+    try:
+        f1, f2 = flatten(basis_functions_1), flatten(basis_functions_2)
+    except ValueError as e:
+        raise _lib.error_class(f"tuna_b200: {e}")
+    return _scratch_context().cross_overlap(f1, f2)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # installation on the reference's modules
 # ---------------------------------------------------------------------------------------------------------
 _timer_fn = None
@@ -341,7 +372,7 @@ def _ref_timer():
 
 
 def install(tuna_integral=None, tuna_kernel=None, tuna_scf=None, tuna_util=None, tuna_ci=None):
-    """Rebind the hot-path names (six of the SCF path + the two AO->MO transformations of tuna_ci) on the reference's (already imported) modules.  All four are module-global
+    """Rebind the hot-path names (six of the SCF path, the two AO->MO transformations of tuna_ci, the two one-electron entry points) on the reference's (already imported) modules.  All four are module-global
     lookups at call time, so no reference source is edited.  Returns a dict of the originals."""
     import sys
     global _timer_fn, _log_fn
@@ -355,7 +386,8 @@ def install(tuna_integral=None, tuna_kernel=None, tuna_scf=None, tuna_util=None,
         _lib.error_class = getattr(tuna_util, "TunaError", _lib.error_class)
         _timer_fn = getattr(tuna_util, "timer", None)
         _log_fn = getattr(tuna_util, "log", None)
-    for mod, names in ((tuna_integral, ("calculate_electron_repulsion_integrals", "calculate_electron_repulsion_integral")),
+    for mod, names in ((tuna_integral, ("calculate_electron_repulsion_integrals", "calculate_electron_repulsion_integral",
+                                        "calculate_one_electron_integrals", "calculate_cross_basis_overlap_matrix")),
                        (tuna_kernel, ("calculate_two_electron_integrals", "transform_to_spherical_harmonics")),
                        (tuna_scf, ("calculate_coulomb_matrix", "calculate_exchange_matrix")),
                        (tuna_ci, ("transform_ERI_AO_to_MO", "transform_ERI_AO_to_SO"))):
