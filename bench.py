@@ -402,6 +402,44 @@ def bench_mo_transform(torch, ctx, wl, fp64_peak, flush):
             "gpu_launches": 4}
 
 
+def bench_one_electron(wl, charges=(7.0, 7.0)):
+    """one-electron integrals (S, T, V_NE, dipole, quadrupole; pyx:282-445) of the workload's basis through the
+    reference-signature call (host lists in, host matrices out) with the reference's compiled engine beside it."""
+    import tuna_b200
+    from types import SimpleNamespace
+    from oracle import tuna_oracle as orc
+    bfs = wl["bfs"]
+    n = len(bfs)
+    zs = sorted({float(np.asarray(b.origin)[2]) for b in bfs})
+    atoms = [SimpleNamespace(origin=np.array([0.0, 0.0, z]), charge=float(c)) for z, c in zip(zs, charges)]
+    origin = np.array([0.0, 0.0, 0.5 * (zs[0] + zs[-1])])
+    tuna_b200.calculate_one_electron_integrals(n, bfs, len(atoms), atoms, origin, 1)          # warm-up (module load, tables)
+    ts, ks = [], []
+    for _ in range(3):
+        ctx = tuna_b200.Context(0)
+        from tuna_b200.basis import flatten
+        ctx.set_basis(*flatten(bfs))
+        t = time.perf_counter()
+        got = ctx.one_electron(zs, list(charges), origin)
+        ts.append(time.perf_counter() - t)
+        ks.append(ctx.last_kernel_ms(5))
+        ctx.close()
+    out = {"workload": f"one-electron integrals, {wl['description']}", "ncart": n, "kernel_ms": float(np.median(ks)), "call_ms": 1e3 * min(ts),
+           "pairs_per_s": n * (n + 1) / 2 / (np.median(ks) * 1e-3), "gpu_launches": 1}
+    eng = orc.reference_engine()
+    if eng is not None:
+        fb = orc.FlatBasis.from_reference_objects(bfs)
+        rb = orc.reference_basis_objects(fb)
+        tr = []
+        for _ in range(2):
+            t = time.perf_counter()
+            ref = eng.calculate_one_electron_integrals(n, rb, len(atoms), atoms, origin, host_threads())
+            tr.append(time.perf_counter() - t)
+        out["cpu_baseline"] = {"value_ms": 1e3 * min(tr), "cores": host_threads(), "kind": "reference", "sample": "full workload, best of 2"}
+        out["max_abs_diff_vs_reference"] = float(max(np.abs(np.asarray(a) - b).max() for a, b in zip(ref, got)))
+    return out
+
+
 def sweep_point(torch, nbf, tau, fp64_peak, device):
     """One extra point of the even-tempered sweep at N=1: device-resident direct Fock builds, CUDA-event timed."""
     import tuna_b200
@@ -548,6 +586,13 @@ def run_ours(args, wl):
             line["stored_large"] = lres
             lctx = None
             line["sweep"] = [sweep_point(torch, nb, args.tau, fp64_peak, local) for nb in (100, 200, 400) if f"et{nb}" != wl["name"]]
+            # extra: in a child process, so that nothing in it can take the headline line down
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extra-one-electron", "--workload", args.workload],
+                                   capture_output=True, text=True, timeout=240)
+                line["one_electron"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"error": (r.stderr or "no output")[-300:]}
+            except Exception as e:
+                line["one_electron"] = {"error": str(e)}
     print(json.dumps(line), flush=True)
     if ddist is not None:
         ddist.destroy_process_group()
@@ -562,7 +607,11 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("TUNA_BENCH_WORKLOAD", "direct:et800"))
     ap.add_argument("--tau", type=float, default=1e-16)
     ap.add_argument("--no-stored", action="store_true", help="skip the extra stored-mode (configs[1]) and sweep measurements at N=1")
+    ap.add_argument("--extra-one-electron", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.extra_one_electron:       # child of the N=1 run: one-electron integrals of configs[1] and of the headline basis
+        print(json.dumps([bench_one_electron(load_workload("stored:n2_ccpvtz")), bench_one_electron(load_workload(args.workload))]), flush=True)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = load_workload(args.workload)
     if args.impl == "reference":
