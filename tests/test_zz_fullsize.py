@@ -72,27 +72,12 @@ def test_direct_jk_full_size(oracle, nbf):
 # Python signatures.  Tolerance as in tests/test_one_electron.py.
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "ne2_uhf_ccpvqz", "et100"])
-def test_one_electron_integrals_gpu(oracle, name):
-    from types import SimpleNamespace
-    import tuna_b200
-    from test_one_electron import NAMES, close, molecule_inputs, sub_basis
-    from util import basis_objects, load_golden, oracle_basis
-    g = load_golden(name)
-    fb = oracle_basis(oracle, g)
-    zs, ch, origin = molecule_inputs(fb, name)
-    bfs = basis_objects(g)
-    atoms = [SimpleNamespace(origin=np.array([0.0, 0.0, z]), charge=float(c)) for z, c in zip(zs, ch)]
-    got = tuna_b200.calculate_one_electron_integrals(len(bfs), bfs, len(atoms), atoms, origin, 4)
-    ref = oracle.one_electron(fb, zs, ch, origin)
-    assert len(got) == 5 and got[3].shape == (3, fb.ncart, fb.ncart)
-    for nm, a, b in zip(NAMES, got, ref):
-        close(a, b, f"{name} {nm}")
-    U = np.array(g["U"])                          # the reference's own spherical matrices of this configuration
-    assert np.abs(U @ got[0] @ U.T - np.array(g["S"])).max() < 1e-12
-    assert np.abs(U @ got[1] @ U.T - np.array(g["T"])).max() < 1e-11 and np.abs(U @ got[2] @ U.T - np.array(g["V_NE"])).max() < 1e-11
-    idx = np.arange(0, fb.ncart, 3)
-    sub = sub_basis(oracle, fb, idx)
-    S12 = tuna_b200.calculate_cross_basis_overlap_matrix(len(bfs), len(idx), bfs, [bfs[i] for i in idx], 4)
-    close(S12, oracle.cross_overlap(fb, sub), f"{name} S_cross")
-    with pytest.raises(tuna_b200.TunaError):
-        tuna_b200.calculate_one_electron_integrals(len(bfs), bfs, 1, [SimpleNamespace(origin=np.array([0.1, 0.0, 0.0]), charge=1.0)], origin, 4)
+def test_one_electron_integrals_gpu(name):
+    """Runs tests/oneel_gpu_case.py in a child process: this CUDA path has never run on a GPU, and a crash in it must not take
+    the rest of the suite's report down."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "oneel_gpu_case.py"), name], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, f"child failed (rc {r.returncode}):\n{r.stdout[-1500:]}\n{r.stderr[-3000:]}"
