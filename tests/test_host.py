@@ -138,3 +138,40 @@ def test_install_rebinds_reference_names_and_uninstall_restores():
         _lib.error_class = saved_err
     assert ns.ints.calculate_electron_repulsion_integrals is before["eri"] and ns.scf.calculate_coulomb_matrix is before["J"]
     assert ci.transform_ERI_AO_to_MO is before["mo"]
+
+
+def test_mode_selection_follows_the_reference_dispatch():
+    """`auto` must keep the dense tensor exactly when kern.run_post_SCF_energy_calculation will hand ERI_AO to a consumer that
+    needs an ndarray (tuna_kernel.py:1146-1175): checked with the reference's own Calculation / Method objects."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+    from tuna_b200 import provider
+    ns = rh.load_reference()
+    names = {m.name for m in ns.util.electronic_structure_methods}
+    expect = {"HF": False, "B3LYP": False, "MP2": True, "CCSD": True, "CIS": True}
+    checked = 0
+    for method, dense in expect.items():
+        if method not in names:
+            continue
+        calc, _, _ = rh.parse_line(ns, f"SPE : H H 0.74 : {method} 6-31G")
+        assert provider._dense_needed(calc) is dense, method
+        checked += 1
+    assert checked >= 3
+    # memory rule of `auto` (no post-HF consumer): stored while 2.2 x 8 n^4 bytes fit 40 % of the free device memory
+    calc, _, _ = rh.parse_line(ns, "SPE : H H 0.74 : HF 6-31G")
+    saved = provider._free_device_bytes
+    try:
+        provider._free_device_bytes = lambda: 10 * 2 ** 30
+        provider.configure(mode="auto")
+        assert provider._choose_mode(70, calc) == "stored" and provider._choose_mode(140, calc) == "direct"
+        calc_mp2, _, _ = rh.parse_line(ns, "SPE : H H 0.74 : MP2 6-31G") if "MP2" in names else (calc, None, None)
+        if "MP2" in names:
+            assert provider._choose_mode(140, calc_mp2) == "stored"
+        provider.configure(mode="direct")
+        assert provider._choose_mode(4, calc) == "direct"
+    finally:
+        provider._free_device_bytes = saved
+        provider.configure(mode="auto")
