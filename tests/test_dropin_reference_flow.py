@@ -180,9 +180,12 @@ def run_unpatched(ns, line):
 
 
 @pytest.mark.parametrize("line", ["SPE : H H 0.74 : UHF 6-31G : NOROTATE NODIIS", "SPE : H H 0.74 : HF 6-31G : CARTHARM NODIIS", "SPE : HE : HF 6-31G : NODIIS",
-                                  "SPE : H H 0.74 : B3LYP 6-31G : NODIIS"])
+                                  "SPE : H H 0.74 : B3LYP 6-31G : NODIIS", "SPE : H H 0.74 : CCSD 6-31G : NODIIS", "SPE : H H 0.74 : CIS 6-31G : NODIIS",
+                                  "SPE : H H 0.74 : UMP2 6-31G : NOROTATE NODIIS", "SPE : H H 0.74 : B2PLYP 6-31G : NODIIS"])
 def test_other_flows_match_the_unpatched_reference(installed, line):
-    """UHF (J/K per spin), CARTHARM (no rotation, tuna_kernel.py:481-483), a single atom, hybrid DFT (exact exchange through K).
+    """UHF (J/K per spin), CARTHARM (no rotation, tuna_kernel.py:481-483), a single atom, hybrid DFT (exact exchange through K), and the
+    post-HF consumers of the dense tensor: coupled cluster, CIS, unrestricted MP2 (three spin-orbital transformations, tuna_mp.py:1055-1057),
+    a double hybrid.
     NODIIS: with default keywords H2/6-31G is round-off chaotic in the reference itself (1e-15 perturbations move E by 1e-7)."""
     ns, tb = installed
     tb.configure(mode="auto")
