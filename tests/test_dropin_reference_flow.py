@@ -213,3 +213,24 @@ def _remember_reference_functions():
             for n in names:
                 _REF_ORIGINALS[(mod.__name__, n)] = getattr(mod, n)
     yield
+
+
+@pytest.mark.parametrize("mode", ["stored", "direct"])
+def test_general_density_through_the_reference_signatures(installed, mode):
+    """The reference's J/K accept ANY real matrix (DIIS / damped / guess densities are not exactly symmetric): so do the provider's, in both modes."""
+    ns, tb = installed
+    from types import SimpleNamespace
+    from oracle import tuna_oracle as orc
+    from util import basis_objects, oracle_basis
+    g = load_golden("h2_631g")
+    bfs = basis_objects(g)
+    tb.configure(mode=mode)
+    calc = SimpleNamespace(cartesian_harmonics=False, number_of_threads=1, method=SimpleNamespace(method_base="HF"))
+    h = tb.calculate_two_electron_integrals(len(bfs), bfs, calc)
+    one = np.eye(len(bfs))
+    *_, eri = tb.transform_to_spherical_harmonics(one, one, one, np.stack([one] * 3), np.stack([one] * 3), h, SimpleNamespace(spherical_harmonic_transformation_matrix=g["U"]), calc, True)
+    assert eri.mode == mode
+    P = np.random.default_rng(2).standard_normal((int(g["nbf"]),) * 2)
+    E = orc.cart_to_sph_eri(orc.eri_fill(oracle_basis(orc, g)), np.array(g["U"]))
+    assert np.abs(tb.calculate_coulomb_matrix(P, eri) - np.einsum("ijkl,kl->ij", E, P)).max() < 1e-12
+    assert np.abs(tb.calculate_exchange_matrix(P, eri) - np.einsum("ilkj,kl->ij", E, P)).max() < 1e-12

@@ -255,12 +255,9 @@ def coulomb_and_exchange(P, ERI_AO, want_j=True, want_k=True):
     P = np.asarray(P, dtype=np.float64)
     if h.mode == "stored":
         return h.ctx.jk_stored(P, want_j, want_k)
-    sym = np.array_equal(P, np.swapaxes(P, -1, -2))
-    if sym:
-        return h.ctx.jk_direct(P, _settings["tau"], want_j, want_k)
-    # K is not symmetric for a non-symmetric P: K[P] = K[S] + K[A] with K[A] antisymmetric.  The direct kernel
-    # assumes a symmetric density, so a general P needs the stored path.
-    raise _lib.error_class("tuna_b200: direct mode requires symmetric density matrices; use stored mode for a general P")
+    # any real P: the library splits a non-symmetric density into its symmetric and antisymmetric parts (K[P] = K[S] + K[A] with
+    # K[A] antisymmetric, J[P] = J[S]); the reference's guess densities are asymmetric at the 1e-8 level
+    return h.ctx.jk_direct(P, _settings["tau"], want_j, want_k)
 
 
 def _cached_jk(P, ERI_AO, which):
