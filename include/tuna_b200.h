@@ -72,7 +72,8 @@ int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, doub
 
 /* Direct (integral-driven) Fock contraction: same J and K, in the basis of U (nbf x nbf matrices), never
  * materialising the tensor: 8-fold symmetry, Schwarz screening |Q_ij Q_kl| max|P| < tau skipped.
- * P must be symmetric (SCF densities are); tau <= 0 disables screening. */
+ * tau <= 0 disables screening.  tuna_jk_direct accepts any real P (a non-symmetric density is split into its symmetric and
+ * antisymmetric parts: J[P] = J[S], K[P] = K[S] + K[A]); tuna_jk_direct_dev expects symmetric densities (SCF densities are). */
 int tuna_jk_direct(tuna_ctx* ctx, int nD, const double* P, double* J, double* K, double tau);
 int tuna_jk_direct_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK, double tau);
 /* Multi-GPU sharding of the quartet list for tuna_jk_direct*: this context evaluates only its share and
