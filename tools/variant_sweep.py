@@ -15,7 +15,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     ctx.set_basis(*flatten(bfs)); ctx.set_transform(np.eye(len(bfs)))
     P = w.fixed_density(len(bfs))
     best = 1e30
-    for _ in range(3):
+    for _ in range(4):          # with TUNA_B200_GRAPH=1: plain, captured, replayed, replayed
         J, K = ctx.jk_direct(P, 1e-16)
         best = min(best, ctx.last_kernel_ms(3))
     W = np.random.default_rng(5).standard_normal(J.shape[-2:])
@@ -25,7 +25,7 @@ else:
     sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [400, 800]
     # build/*.so come from tools/build_variants.sh (compile-time variants of the shell engine, off in the shipped library)
     libs = {"cur": "tuna_b200/libtuna_b200.so", "wide": "build/lib_wide.so", "asm": "build/lib_asm.so", "tiers": "build/lib_tiers.so", "v3": "build/lib_v3.so"}
-    combos = [("cur", {}), ("wide", {}), ("asm", {}), ("tiers", {}), ("tiers", {"TUNA_B200_REG_TIER": "0"}), ("v3", {}), ("v3", {"TUNA_B200_REG_TIER": "0"})]
+    combos = [("cur", {}), ("cur", {"TUNA_B200_GRAPH": "1"}), ("wide", {}), ("asm", {}), ("tiers", {}), ("tiers", {"TUNA_B200_REG_TIER": "0"}), ("v3", {}), ("v3", {"TUNA_B200_REG_TIER": "0"})]
     ref = {}
     for nbf in sizes:
         for name, env in combos:
