@@ -440,6 +440,39 @@ def bench_one_electron(wl, charges=(7.0, 7.0)):
     return out
 
 
+def parity_at_bench_size(wl, tau, device):
+    """Evidence that the timed kernels compute the reference's numbers AT THE TIMED SIZE (no dense tensor exists there): J/K from a unit-pair
+    density P = e_k e_l^T + e_l e_k^T are single integrals, J_ij = (ij|kl) + (ij|lk), K_ij = (il|kj) + (ik|lj), which the oracle evaluates one
+    by one for sampled (i, j).  The oracle is the checker here, never the thing measured."""
+    import tuna_b200
+    from oracle import tuna_oracle as orc
+    from tuna_b200.basis import flatten
+    from util import pick_function, unit_pair_density
+    bfs = wl["bfs"]
+    fb = orc.FlatBasis.from_reference_objects(bfs)
+    n = fb.ncart
+    Lmax = int(np.asarray(fb.lmn).sum(axis=1).max())
+    k, l = pick_function(fb, 0, Lmax, True, 0), pick_function(fb, 1, max(Lmax - 1, 0), False, 0)
+    ctx = tuna_b200.Context(device)
+    ctx.set_basis(*flatten(bfs))
+    ctx.set_transform(np.eye(n))
+    J, K = ctx.jk_direct(unit_pair_density(n, k, l), tau)
+    rng = np.random.default_rng(5)
+    worst, worst_rel, ok = 0.0, 0.0, True
+    ns = 150
+    for i, j in zip(rng.integers(0, n, ns), rng.integers(0, n, ns)):
+        i, j = int(i), int(j)
+        a, b = orc.eri_single(fb, i, j, k, l), orc.eri_single(fb, i, j, l, k)
+        c, d = orc.eri_single(fb, i, l, k, j), orc.eri_single(fb, i, k, l, j)
+        for got, ref, scale in ((J[i, j], a + b, max(abs(a), abs(b))), (K[i, j], c + d, max(abs(c), abs(d)))):
+            err = abs(got - ref)
+            worst = max(worst, err)
+            ok = ok and err <= 2 * max(1e-12, 1e-13 * scale)
+    ctx.close()
+    return {"what": "direct J/K from a unit-pair density vs single integrals of the oracle, sampled elements", "samples": 2 * ns, "pair": [k, l],
+            "max_abs_diff": worst, "within_tolerance": bool(ok), "tolerance": "2 * max(1e-12, 1e-13 |ERI|) (SURVEY.md 8d)"}
+
+
 def sweep_point(torch, nbf, tau, fp64_peak, device):
     """One extra point of the even-tempered sweep at N=1: device-resident direct Fock builds, CUDA-event timed."""
     import tuna_b200
@@ -567,6 +600,10 @@ def run_ours(args, wl):
         rate = ex["fp64_flops_per_build"] / world / (k_ms * 1e-3) / 1e12
         line["roofline"]["executed"] = dict(ex, tflops=rate, frac_of_fp64_peak=rate / fp64_peak if fp64_peak else None)
     if world == 1:
+        try:
+            line["parity"] = parity_at_bench_size(wl, args.tau, local)
+        except Exception as e:       # evidence only; never allowed to take the line down
+            line["parity"] = {"error": str(e)}
         line["cpu_baseline"] = cpu_reference(wl)
         if not args.no_stored:
             fb = None
