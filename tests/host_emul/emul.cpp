@@ -68,11 +68,15 @@ int emul_eri_fill(int ncart, const double* oz, const int* lmn, const int* nprim,
 
 // ---- shell-quartet engine (shell_jk.cuh) with the serial HostPolicy ------------------------------------------------
 #include "../../tuna_b200/csrc/shell_host.hpp"
+#include "../../tuna_b200/csrc/shell4_host.hpp"
 
 struct HostPolicy {
     static constexpr int G = 1;
     static int lane() { return 0; }
     static void sync() {}
+    static void sync_cta() {}
+    static int cta_thread() { return 0; }
+    static int cta_threads() { return 1; }
     static void atomic_add(double* p, double v) { *p += v; }
 };
 
@@ -171,6 +175,102 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
                 Kout[d * nn + (size_t)i * ncart + j] = ff * (Kf[d * nn + (size_t)i * ncart + j] + Kf[d * nn + (size_t)j * ncart + i]);
             }
     if (stats) { stats[0] = (long long)S.shells.size(); stats[1] = (long long)S.pairA.size(); stats[2] = nitems_total; stats[3] = nskipped; stats[4] = ncls; }
+    return 0;
+}
+
+// ---- generation-4 engine (shell4.cuh) with the serial HostPolicy: same driver, same conventions ---------------------------
+extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
+                              const double* ceff, int nD, const double* P, double* Jout, double* Kout, double tau, long long* stats) {
+    HostBasis B = make_basis(ncart, oz, lmn, nprim, off, exps, ceff);
+    PairTable PT;
+    build_pair_table(B, PT);
+    std::vector<double> boys, herm;
+    build_boys_table(boys);
+    build_hermite_poly_table(herm);
+    std::vector<double> aoQ(PT.npair);
+    for (int64_t a = 0; a < PT.npair; ++a) {
+        PairClass ca{PT.cls[a] & 255, (PT.cls[a] >> 8) & 255, PT.cls[a] >> 16};
+        aoQ[a] = std::sqrt(std::fabs(eri_ao_quartet(PT.pp.data() + PT.ppoff[a] * PP_DOUBLES, PT.npp[a], PT.pp.data() + PT.ppoff[a] * PP_DOUBLES,
+                                                    PT.npp[a], ca, ca, boys.data(), herm.data())));
+    }
+    ShellTab T;
+    build_shell_tab(T);
+    ShellSystem S;
+    if (!detect_shells(B, T, S)) return 1;
+    build_shell_pairs(S, T, PT, aoQ, ncart);
+    const size_t nn = (size_t)ncart * ncart;
+    std::vector<double> Pf(nD * nn), Jf(nD * nn, 0.0), Kf(nD * nn, 0.0);
+    double dmax = 0.0;
+    for (int d = 0; d < nD; ++d)
+        for (int i = 0; i < ncart; ++i)
+            for (int j = 0; j < ncart; ++j) {
+                Pf[d * nn + (size_t)i * ncart + j] = S.fnorm[i] * S.fnorm[j] * P[d * nn + (size_t)i * ncart + j];
+                dmax = std::max(dmax, std::fabs(P[d * nn + (size_t)i * ncart + j]));
+            }
+    std::vector<double> Psym(nD * nn);
+    for (int d = 0; d < nD; ++d)
+        for (int i = 0; i < ncart; ++i)
+            for (int j = 0; j < ncart; ++j) Psym[d * nn + (size_t)i * ncart + j] = Pf[d * nn + (size_t)i * ncart + j] + Pf[d * nn + (size_t)j * ncart + i];
+    ShellData D;
+    D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
+    D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data();
+    D.eri_out = nullptr; D.fnorm = S.fnorm.data();
+    long long nitems_total = 0, nskipped = 0, nint_total = 0, nterm_total = 0;
+    const int ncls = (int)S.classes.size();
+    for (int cb = 0; cb < ncls; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            Shell4Job J;
+            J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
+            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4;
+            J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
+            std::vector<long long> prefix;
+            J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
+            J.item_prefix = prefix.data(); J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
+            Class4Host CH;
+            const char* eb = getenv("TUNA_EMUL_IT_BUDGET");      // small budgets force the multi-chunk path in tests
+            if (eb) build_class4_tables(T, J.La, J.Lb, J.Lc, J.Ld, CH, atoi(eb), atoi(eb)); else build_class4_tables(T, J.La, J.Lb, J.Lc, J.Ld, CH);
+            J.ct = class4_view(CH, HostPtrOf());
+            shell4_job_layout(J, nD);
+            const char* enb = getenv("TUNA_EMUL_NB");
+            const int NBATCH = enb ? atoi(enb) : 2;
+            std::vector<double> sm((size_t)4 * J.total);
+            std::vector<unsigned> tab(CH.ntab);
+            int tab_chunk = -1;
+            Quartet4 hq[4];
+            for (int q = 0; q < 4; ++q) hq[q] = Quartet4{0, 0, 0, 0, 0.0};
+            int nb = 0;
+            auto run_batch = [&]() {
+                if (nb == 0) return;
+                if (NBATCH == 4) shell4_quartets<HostPolicy, 4>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                else if (NBATCH == 2) shell4_quartets<HostPolicy, 2>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                else shell4_quartets<HostPolicy, 1>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                for (int q = 0; q < 4; ++q) hq[q].active = 0;
+                nb = 0;
+            };
+            for (long long item = 0; item < J.nitems; ++item) {
+                int ib = 0, hi = J.nbra;
+                while (hi - ib > 1) { const int mid = (ib + hi) >> 1; if (prefix[mid] <= item) ib = mid; else hi = mid; }
+                const int ik = (int)(item - prefix[ib]);
+                const int AB = J.bra_list[ib], CD = J.ket_list[ik];
+                if (tau > 0.0 && S.pairQ[AB] * S.pairQ[CD] * dmax < tau) { ++nskipped; continue; }
+                double w = 1.0;
+                if (S.pairA[AB] == S.pairB[AB]) w *= 0.5;
+                if (S.pairA[CD] == S.pairB[CD]) w *= 0.5;
+                if (AB == CD) w *= 0.5;
+                hq[nb] = Quartet4{1, AB, CD, 0, w};
+                if (++nb == NBATCH) run_batch();
+            }
+            run_batch();
+            nitems_total += J.nitems; nint_total += CH.nint; nterm_total += CH.terms;
+        }
+    for (int d = 0; d < nD; ++d)
+        for (int i = 0; i < ncart; ++i)
+            for (int j = 0; j < ncart; ++j) {
+                const double ff = S.fnorm[i] * S.fnorm[j];
+                Jout[d * nn + (size_t)i * ncart + j] = ff * (Jf[d * nn + (size_t)i * ncart + j] + Jf[d * nn + (size_t)j * ncart + i]);
+                Kout[d * nn + (size_t)i * ncart + j] = ff * (Kf[d * nn + (size_t)i * ncart + j] + Kf[d * nn + (size_t)j * ncart + i]);
+            }
+    if (stats) { stats[0] = (long long)S.shells.size(); stats[1] = (long long)S.pairA.size(); stats[2] = nitems_total; stats[3] = nskipped; stats[4] = ncls; stats[5] = nint_total; stats[6] = nterm_total; }
     return 0;
 }
 

@@ -83,8 +83,20 @@ def test_quartet_math_vs_oracle(emul, oracle, name):
     assert np.array_equal(out == 0.0, ref == 0.0)
 
 
+ENGINES = {"gen2": "emul_jk_shell", "gen4": "emul_jk_shell4"}
+
+
+def engine_entry(emul, gen):
+    """The serial CPU build of the engine body: shell_jk.cuh (generation 2, still the dense-fill engine) or shell4.cuh (generation 4,
+    the default direct engine).  The compile-time variants only exist for generation 2."""
+    if gen == "gen4" and emul.variant:
+        pytest.skip("variant builds concern generation 2 only")
+    return getattr(emul, ENGINES[gen])
+
+
+@pytest.mark.parametrize("gen", list(ENGINES))
 @pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "et100"])
-def test_shell_engine_vs_oracle(emul, oracle, name):
+def test_shell_engine_vs_oracle(emul, oracle, name, gen):
     """shell_jk.cuh (the direct-mode engine) run serially on the CPU: J/K for two symmetric densities vs the oracle's
     einsums over the oracle's Cartesian tensor, with and without Schwarz screening."""
     if emul.variant and name == "n2_ccpvtz":
@@ -104,7 +116,7 @@ def test_shell_engine_vs_oracle(emul, oracle, name):
     P = (P + P.transpose(0, 2, 1)) / 2
     J, K, stats = np.zeros_like(P), np.zeros_like(P), np.zeros(8, dtype=np.int64)
     for tau in (0.0, 1e-16):
-        rc = emul.emul_jk_shell(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+        rc = engine_entry(emul, gen)(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
                                 fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), 2, P.ctypes.data_as(dp), J.ctypes.data_as(dp),
                                 K.ctypes.data_as(dp), ctypes.c_double(tau), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
         assert rc == 0
@@ -113,8 +125,13 @@ def test_shell_engine_vs_oracle(emul, oracle, name):
             assert np.abs(J[d] - Jr).max() < 1e-11 and np.abs(K[d] - Kr).max() < 1e-11
 
 
-def test_shell_engine_h_shells(emul, oracle):
-    """All shell types up to H, including the multi-chunk (hh|hh) class tables, on a synthetic two-centre basis."""
+@pytest.mark.parametrize("gen,nb,budget", [("gen2", None, None), ("gen4", None, None), ("gen4", "1", "1500"), ("gen4", "4", "700")])
+def test_shell_engine_h_shells(emul, oracle, gen, nb, budget, monkeypatch):
+    """All shell types up to H, including the multi-chunk (hh|hh) class tables, on a synthetic two-centre basis; generation 4 also with
+    one and four quartets per batch and with small chunk budgets (several chunks per class, table reload)."""
+    if nb:
+        monkeypatch.setenv("TUNA_EMUL_NB", nb)
+        monkeypatch.setenv("TUNA_EMUL_IT_BUDGET", budget)
     from tuna_b200 import workloads as w
     from tuna_b200.basis import from_arrays
     shells_a = [(0, [1.3], [1.0]), (1, [0.9], [1.0]), (5, [1.1], [1.0])]
@@ -132,9 +149,9 @@ def test_shell_engine_h_shells(emul, oracle):
     P = np.random.default_rng(1).standard_normal((1, n, n))
     P = (P + P.transpose(0, 2, 1)) / 2
     J, K, stats = np.zeros_like(P), np.zeros_like(P), np.zeros(8, dtype=np.int64)
-    rc = emul.emul_jk_shell(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
-                            fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), 1, P.ctypes.data_as(dp), J.ctypes.data_as(dp),
-                            K.ctypes.data_as(dp), ctypes.c_double(0.0), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    rc = engine_entry(emul, gen)(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                                 fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), 1, P.ctypes.data_as(dp), J.ctypes.data_as(dp),
+                                 K.ctypes.data_as(dp), ctypes.c_double(0.0), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
     assert rc == 0 and stats[0] == 7
     assert np.abs(J[0] - oracle.coulomb(P[0], E)).max() < 1e-11 and np.abs(K[0] - oracle.exchange(P[0], E)).max() < 1e-11
 
@@ -164,7 +181,8 @@ def test_shell_engine_fill_mode_vs_oracle(emul, oracle, name):
     assert np.array_equal(out, out.transpose(1, 0, 2, 3)) and np.array_equal(out, out.transpose(0, 1, 3, 2)) and np.array_equal(out, out.transpose(2, 3, 0, 1))
 
 
-def test_shell_engine_extreme_shells_of_the_headline_basis(emul, oracle):
+@pytest.mark.parametrize("gen", list(ENGINES))
+def test_shell_engine_extreme_shells_of_the_headline_basis(emul, oracle, gen):
     """The tightest and the most diffuse shell of every angular momentum of the ET800 set (s exponent 2.1e5 ... h exponent 1.0) on both
     atoms, unit-pair densities: sampled J/K elements against single integrals of the oracle (no dense tensor needed).  The same check
     runs on the GPU at the full nbf 400 / 800 sizes (tests/test_zz_fullsize.py)."""
@@ -190,9 +208,9 @@ def test_shell_engine_extreme_shells_of_the_headline_basis(emul, oracle):
     off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
     ceff = np.ascontiguousarray(fb.coefs * fb.norms)
     J, K, stats = np.zeros_like(P), np.zeros_like(P), np.zeros(8, dtype=np.int64)
-    rc = emul.emul_jk_shell(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
-                            fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), 2, P.ctypes.data_as(dp), J.ctypes.data_as(dp),
-                            K.ctypes.data_as(dp), ctypes.c_double(1e-16), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    rc = engine_entry(emul, gen)(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                                 fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), 2, P.ctypes.data_as(dp), J.ctypes.data_as(dp),
+                                 K.ctypes.data_as(dp), ctypes.c_double(1e-16), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
     assert rc == 0
     for d, (k, l) in enumerate(pairs):
         assert check_unit_pair_jk(oracle, fb, k, l, J[d], K[d], n_samples=200) < 1e-12

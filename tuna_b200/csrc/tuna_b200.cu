@@ -23,6 +23,7 @@
 #include "pairtable.hpp"
 #include "shell_host.hpp"
 #include "shell_jk.cuh"
+#include "shell4_host.hpp"
 #include "mo_transform.cuh"
 #include "oneel_core.cuh"
 
@@ -112,6 +113,14 @@ struct tuna_ctx {
     static constexpr int NAUX = 6;
     cudaStream_t aux[NAUX] = {};     // class jobs of one build are independent (atomic accumulation): one launch per group size, each on its own stream
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
+    // generation-4 shell engine (shell4.cuh): per-class tables and the job list; the pair data above is shared
+    struct ClassTab4Dev { Class4Host host; Class4Dev view; unsigned char* blob = nullptr; };
+    struct Job4Host { Shell4Job job; int G = 1, threads = 128, gpc = 1, nb = 1; size_t smem = 0; int tab_off = 0, hdr_off = 0; double allowed = 0; };
+    std::map<int, ClassTab4Dev> class_tabs4;     // key La | Lb<<4 | Lc<<8 | Ld<<12 | nD<<16
+    std::vector<Job4Host> jobs4;
+    double shell4_tau = -1.0;
+    int shell4_nD = -1;
+    int engine_gen = 4;             // 4 = shell4.cuh (default), 2 = shell_jk.cuh (TUNA_B200_ENGINE=2; also serves the dense fill)
     CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
     int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
 
@@ -796,8 +805,13 @@ struct DevPolicy {
     static constexpr int G = GG;
     __device__ __forceinline__ static int lane() { return threadIdx.x & (GG - 1); }
     __device__ __forceinline__ static void sync() {
-        if (GG <= 32) __syncwarp(); else __syncthreads();
+        if constexpr (GG > 32) __syncthreads();
+        else if constexpr (GG == 32) __syncwarp();
+        else __syncwarp(((1u << GG) - 1u) << ((threadIdx.x & 31) & ~(GG - 1)));     // only the lanes of this group
     }
+    __device__ __forceinline__ static void sync_cta() { __syncthreads(); }
+    __device__ __forceinline__ static int cta_thread() { return threadIdx.x; }
+    __device__ __forceinline__ static int cta_threads() { return blockDim.x; }
     __device__ __forceinline__ static void atomic_add(double* p, double v) { atomicAdd(p, v); }
 };
 
@@ -927,6 +941,62 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 1
             }
             shell_quartets<DevPolicy<GG>, NB>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
         }
+    }
+    if (done != 0.0) atomicAdd(evaluated, done);
+}
+
+// ---- generation-4 engine: one class job per launch, the descriptor travels as a kernel parameter ------------------------------
+// A CTA work unit (= multi-GPU sharding unit) is J.chunk consecutive shell quartets; the unit's quartets are decoded ONCE (item ->
+// bra / ket pair, Schwarz test, degeneracy weight) into shared-memory headers, then the CTA's groups take them NB at a time.
+#ifndef TUNA_SHELL4_REGS
+#define TUNA_SHELL4_REGS 64
+#endif
+template <int GG, int NB>
+__global__ void __launch_bounds__((GG > 128) ? GG : 128, 65536 / (((GG > 128) ? GG : 128) * TUNA_SHELL4_REGS))
+k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
+             double tau, const unsigned long long* scalars, double* evaluated, int rank, int nranks, int tab_off, int hdr_off) {
+    extern __shared__ double smem_all[];
+    const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
+    unsigned* tab = reinterpret_cast<unsigned*>(smem_all + tab_off);
+    Quartet4* hdr = reinterpret_cast<Quartet4*>(smem_all + hdr_off);
+    const int CH = J.chunk;
+    int& s_ib0 = *reinterpret_cast<int*>(hdr + CH);
+    double* sm = smem_all + (size_t)gid * NB * J.total;
+    const double dmax = __longlong_as_double((long long)scalars[0]);
+    const long long nunit = (J.nitems + CH - 1) / CH;
+    shell4_load_tables<NB>(J.ct, 0, tab, threadIdx.x, blockDim.x);
+    int tab_chunk = 0;
+    double done = 0.0;
+    for (long long gc = (long long)blockIdx.x * nranks + rank; gc < nunit; gc += (long long)gridDim.x * nranks) {
+        const long long first = gc * CH;
+        __syncthreads();                                  // the previous unit's headers are no longer needed (and the tables are in place)
+        if (threadIdx.x == 0) {
+            int lo = 0, hi = J.nbra;                      // invariant: prefix[lo] <= first < prefix[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (J.item_prefix[mid] <= first) lo = mid; else hi = mid;
+            }
+            s_ib0 = lo;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < CH; k += blockDim.x) {
+            const long long item = first + k;
+            Quartet4 h;
+            h.active = 0; h.ab = 0; h.cd = 0; h.pad = 0; h.w = 0.0;
+            if (item < J.nitems) {
+                int ib = s_ib0;
+                while (J.item_prefix[ib + 1] <= item) ++ib;
+                h.ab = J.bra_list[ib]; h.cd = J.ket_list[(int)(item - J.item_prefix[ib])];
+                h.active = !(tau > 0.0 && D.pairQ[h.ab] * D.pairQ[h.cd] * dmax < tau);
+                const bool ab = D.pairA[h.ab] == D.pairB[h.ab], cd = D.pairA[h.cd] == D.pairB[h.cd], dg = h.ab == h.cd;
+                h.w = (ab ? 0.5 : 1.0) * (cd ? 0.5 : 1.0) * (dg ? 0.5 : 1.0);
+                if (h.active) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+            }
+            hdr[k] = h;
+        }
+        __syncthreads();
+        for (int k0 = 0; k0 < CH; k0 += gpc * NB)
+            shell4_quartets<DevPolicy<GG>, NB>(J, D, hdr + k0 + gid * NB, sm, tab, tab_chunk, nD, Pf, Psym, Jf, Kf, ncart);
     }
     if (done != 0.0) atomicAdd(evaluated, done);
 }
@@ -1139,6 +1209,7 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->d_P); dev_free(&ctx->d_J); dev_free(&ctx->d_K);
     dev_free(&ctx->d_Pc); dev_free(&ctx->d_Jc); dev_free(&ctx->d_Kc); dev_free(&ctx->d_tmp); dev_free(&ctx->d_Kpart);
     for (auto& kv : ctx->class_tabs) dev_free(&kv.second.blob);
+    for (auto& kv : ctx->class_tabs4) dev_free(&kv.second.blob);
 #ifdef TUNA_SHELL_WIDE_TERMS
     for (auto& kv : ctx->class_tabs) for (int w = 0; w < 3; ++w) dev_free(&kv.second.wide[w]);
 #endif
@@ -1226,9 +1297,12 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     build_shell_tab(ctx->stab);
     ctx->shell_ready = false;
     ctx->jobs.clear();
+    ctx->jobs4.clear();
     detect_shells(ctx->hb, ctx->stab, ctx->ss);     // ss.ok == false -> direct mode uses the per-component kernel
     const char* eng = getenv("TUNA_B200_DIRECT_ENGINE");
     ctx->direct_engine = (eng && std::string(eng) == "generic") ? 0 : 1;
+    const char* gen = getenv("TUNA_B200_ENGINE");
+    ctx->engine_gen = (gen && atoi(gen) == 2) ? 2 : 4;
     return TUNA_OK;
 }
 
@@ -1966,7 +2040,7 @@ static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int n
 }
 
 // Build (or refresh for a new threshold) the shell-pair data and the job list of the shell-quartet engine.
-static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
+static int ensure_shell_pairs(tuna_ctx* ctx) {
     int rc;
     if (!ctx->shell_ready) {
         if ((rc = ensure_schwarz(ctx))) return rc;
@@ -2005,7 +2079,14 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->shell_ready = true;
         ctx->shell_tau = -1.0;
+        ctx->shell4_tau = -1.0;
     }
+    return TUNA_OK;
+}
+
+static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
+    int rc;
+    if ((rc = ensure_shell_pairs(ctx))) return rc;
     if (ctx->shell_tau != tau || ctx->shell_nD != nD || ctx->shell_fill != fill || ctx->jobs.empty()) {
         ctx->shell_nD = nD;
         ctx->shell_fill = fill;
@@ -2275,6 +2356,218 @@ static int launch_shell_jobs(tuna_ctx* ctx, int nD, const double* Pc, const doub
     return TUNA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// generation-4 engine: per-class tables, job list, launches
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int SHELL4_SMEM_DOUBLES = 27000;       // 211 KB of the 227 KB a CTA may use (tables and headers come on top)
+
+static int shell4_slice_doubles(const Class4Host& C, int nD) {
+    Shell4Job Jt;
+    Jt.La = C.La; Jt.Lb = C.Lb; Jt.Lc = C.Lc; Jt.Ld = C.Ld;
+    Jt.ct.ssize = C.ssize; Jt.ct.itmax = C.itmax; Jt.ct.zrow = C.zrow; Jt.ct.nstage = C.nstage; Jt.ct.nwork = C.nwork;
+    shell4_job_layout(Jt, nD);
+    return Jt.total + (C.ntab + 1) / 2 + 16;
+}
+
+static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int nD, tuna_ctx::ClassTab4Dev** out) {
+    const int key = La | Lb << 4 | Lc << 8 | Ld << 12 | nD << 16;
+    auto it = ctx->class_tabs4.find(key);
+    if (it != ctx->class_tabs4.end()) { *out = &it->second; return TUNA_OK; }
+    tuna_ctx::ClassTab4Dev& E = ctx->class_tabs4[key];
+    {
+        const char* eb = getenv("TUNA_B200_IT_BUDGET");
+        const char* es = getenv("TUNA_B200_S_BUDGET");
+        int itb = eb ? atoi(eb) : S4_IT_BUDGET, sb = es ? atoi(es) : S4_S_BUDGET;
+        build_class4_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb);
+        // a slice that does not fit one CTA is re-cut into more chunks; a slice between half and all of an SM's shared memory is
+        // re-cut so that two CTAs fit (phases 0-2 then run once per chunk)
+        const int tier2 = (225 * 1024 / 2 - 1024 - 64) / 8;
+        for (int pass = 0; pass < 6; ++pass) {
+            const int t0 = shell4_slice_doubles(E.host, nD);
+            const bool too_big = t0 > SHELL4_SMEM_DOUBLES;
+            const char* et = getenv("TUNA_B200_TIER2");
+            const bool tier = t0 > tier2 && !(et && atoi(et) == 0) && pass < 3;
+            if (!too_big && !tier) break;
+            const int nch = (int)E.host.chunk_row0.size() - 1;
+            Class4Host trial;
+            bool found = false;
+            for (int want = nch + 1; want <= nch + 3 && !found; ++want) {
+                build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.nint / want + E.host.nint / (8 * want)), 65000);
+                if ((int)trial.chunk_row0.size() - 1 > nch && (shell4_slice_doubles(trial, nD) <= (too_big ? SHELL4_SMEM_DOUBLES : tier2))) found = true;
+            }
+            if (found) { E.host = trial; if (!too_big) break; }
+            else if (!too_big) break;
+            else if (pass == 5) FAIL(TUNA_ERR_STATE, "shell engine: class does not fit shared memory");
+            else { build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.itmax / 2), std::max(64, E.host.ssize / 2)); E.host = trial; }
+        }
+    }
+    const Class4Host& C = E.host;
+    size_t total = 0;
+    auto reserve = [&](size_t bytes) { size_t o = total; total += (bytes + 15) & ~(size_t)15; return o; };
+    struct Piece { const void* src; size_t bytes, off; };
+    std::vector<Piece> pieces;
+    auto add = [&](const void* src, size_t bytes) { pieces.push_back({src, bytes, reserve(bytes)}); return pieces.back().off; };
+    const size_t o_rt = add(C.t_rt.data(), C.t_rt.size() * 4), o_xy = add(C.t_xy.data(), C.t_xy.size() * 4), o_u = add(C.t_u.data(), C.t_u.size() * 4);
+    const size_t o_s = add(C.t_s.data(), C.t_s.size() * 4), o_s0 = add(C.chunk_s0.data(), C.chunk_s0.size() * 4), o_p4 = add(C.p4.data(), C.p4.size() * 4);
+    const size_t o_t0 = add(C.chunk_t0.data(), C.chunk_t0.size() * 4), o_ni = add(C.chunk_ni.data(), C.chunk_ni.size() * 4);
+    const size_t o_tabs = add(C.tabs.data(), C.tabs.size() * 4), o_acc = add(C.acc.data(), C.acc.size() * 4);
+    const size_t o_pmap = add(C.pmap.data(), C.pmap.size() * 2), o_omap = add(C.omap.data(), C.omap.size() * 2);
+    const size_t o_jp = add(C.jst_ptr.data(), C.jst_ptr.size() * 4), o_jl = add(C.jst_list.data(), C.jst_list.size() * 2), o_jf = add(C.jflush.data(), C.jflush.size() * 4);
+    std::vector<unsigned char> host(total, 0);
+    for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
+    int rc;
+    if ((rc = dev_alloc(ctx, &E.blob, total))) return rc;
+    CK(cudaMemcpyAsync(E.blob, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    struct BlobPtr {
+        unsigned char* base; const Class4Host* C; const size_t* offs;
+    };
+    Class4Dev& V = E.view;
+    V = class4_view(C, HostPtrOf());          // scalars; the pointers are replaced by device addresses below
+    V.t_rt = (const unsigned*)(E.blob + o_rt); V.t_xy = (const unsigned*)(E.blob + o_xy); V.t_u = (const unsigned*)(E.blob + o_u);
+    V.t_s = (const unsigned*)(E.blob + o_s); V.chunk_s0 = (const int*)(E.blob + o_s0); V.p4 = (const unsigned*)(E.blob + o_p4);
+    V.chunk_t0 = (const int*)(E.blob + o_t0); V.chunk_ni = (const int*)(E.blob + o_ni); V.tabs = (const unsigned*)(E.blob + o_tabs);
+    V.acc = (const unsigned*)(E.blob + o_acc); V.pmap = (const unsigned short*)(E.blob + o_pmap); V.omap = (const unsigned short*)(E.blob + o_omap);
+    V.jst_ptr = (const unsigned*)(E.blob + o_jp); V.jst_list = (const unsigned short*)(E.blob + o_jl); V.jflush = (const unsigned*)(E.blob + o_jf);
+    *out = &E;
+    return TUNA_OK;
+}
+
+// Job list of the generation-4 engine for threshold tau and nD densities (pair data shared with generation 2).
+static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
+    int rc;
+    if ((rc = ensure_shell_pairs(ctx))) return rc;
+    if (ctx->shell4_tau == tau && ctx->shell4_nD == nD && !ctx->jobs4.empty()) return TUNA_OK;
+    const ShellSystem& S = ctx->ss;
+    const int ncls = (int)S.classes.size();
+    std::vector<long long> all_prefix;
+    std::vector<size_t> prefix_off;
+    ctx->jobs4.clear();
+    const char* env_div = getenv("TUNA_B200_G_DIV");
+    const char* env_spl = getenv("TUNA_B200_SMEM_PER_LANE");
+    const char* env_nb = getenv("TUNA_B200_NB");
+    const char* env_nbmax = getenv("TUNA_B200_NB_BYTES");
+    const double gdiv = env_div ? atof(env_div) : 8.0;
+    const double smem_per_lane = env_spl ? atof(env_spl) : 256.0;
+    const size_t nb_bytes = env_nbmax ? (size_t)atol(env_nbmax) : 100 * 1024;
+    // static pre-screening uses the weakest density bound the device test can see (not a hard-coded 1e-3)
+    for (int cb = 0; cb < ncls; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            tuna_ctx::Job4Host jh;
+            Shell4Job& J = jh.job;
+            J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
+            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
+            std::vector<long long> prefix;
+            J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
+            if (J.nitems == 0) continue;
+            J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
+            J.bra_list = ctx->d_class_lists + ctx->class_list_off[cb];
+            J.ket_list = ctx->d_class_lists + ctx->class_list_off[ck];
+            prefix_off.push_back(all_prefix.size());
+            all_prefix.insert(all_prefix.end(), prefix.begin(), prefix.end());
+            tuna_ctx::ClassTab4Dev* ctd = nullptr;
+            if ((rc = get_class4_tables(ctx, J.La, J.Lb, J.Lc, J.Ld, nD, &ctd))) return rc;
+            J.ct = ctd->view;
+            shell4_job_layout(J, nD);
+            jh.allowed = (double)ctd->host.allowed;
+            for (int u = 0; u < 6; ++u) J.uniq[u] = ctd->host.uniq[u];
+            int nb = env_nb ? atoi(env_nb) : 2;
+            if (nb != 1 && nb != 2 && nb != 4) nb = 2;
+            while (nb > 1 && (size_t)nb * J.total * 8 > nb_bytes) nb >>= 1;
+            int G = 1;
+            while (G < 256 && G * gdiv < jh.allowed) G *= 2;
+            while (G < 256 && (double)nb * J.total * 8.0 / G > smem_per_lane) G *= 2;
+            while (G < 256 && (size_t)(G <= 32 ? 128 / G : 1) * nb * J.total * 8 > 190 * 1024) G *= 2;
+            if (J.ct.nchunk > 1 && G < 64) G = 64;                 // the table reload of a multi-chunk class synchronises the whole CTA
+            jh.G = G; jh.nb = nb;
+            jh.threads = G <= 32 ? 128 : G;
+            jh.gpc = jh.threads / G;
+            J.chunk = jh.gpc * SHELL_ITEMS_PER_GROUP;
+            const size_t slices = (size_t)jh.gpc * nb * J.total;
+            jh.tab_off = (int)((slices + 1) & ~(size_t)1);
+            jh.hdr_off = jh.tab_off + (J.ct.ntab + 1) / 2;
+            jh.smem = ((size_t)jh.hdr_off + (size_t)J.chunk * sizeof(Quartet4) / 8 + 2) * sizeof(double);
+            if (jh.smem > 226 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 226 KB");
+            ctx->jobs4.push_back(jh);
+        }
+    if ((rc = dev_alloc(ctx, &ctx->d_prefix, std::max<size_t>(all_prefix.size(), 1)))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_prefix, all_prefix.data(), all_prefix.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t j = 0; j < ctx->jobs4.size(); ++j) ctx->jobs4[j].job.item_prefix = ctx->d_prefix + prefix_off[j];
+    std::stable_sort(ctx->jobs4.begin(), ctx->jobs4.end(), [](const tuna_ctx::Job4Host& x, const tuna_ctx::Job4Host& y) {
+        return x.allowed * (double)x.job.nitems > y.allowed * (double)y.job.nitems;
+    });
+    if (const char* dump = getenv("TUNA_B200_DUMP_JOBS")) {       // development aid: the job table in launch order
+        if (FILE* f = fopen(dump, "w")) {
+            fprintf(f, "idx,La,Lb,Lc,Ld,nppAB,nppCD,G,nb,threads,smem,total,nout,nint,itmax,nchunk,nitems,allowed,own\n");
+            int idx = 0;
+            for (const auto& jh : ctx->jobs4)
+                fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%zu,%d,%d,%d,%d,%d,%lld,%.0f,%d\n", idx++, jh.job.La, jh.job.Lb, jh.job.Lc, jh.job.Ld, jh.job.nppAB,
+                        jh.job.nppCD, jh.G, jh.nb, jh.threads, jh.smem, jh.job.total, jh.job.ct.nwork, jh.job.ct.itmax, jh.job.ct.itmax, jh.job.ct.nchunk,
+                        jh.job.nitems, jh.allowed, 1);
+            fclose(f);
+        }
+    }
+    ctx->shell_tau = -1.0;            // d_prefix is shared with the generation-2 job list: that one must be rebuilt before its next use
+    ctx->jobs.clear();
+    ctx->shell4_tau = tau;
+    ctx->shell4_nD = nD;
+    ctx->shell_epoch++;
+    return TUNA_OK;
+}
+
+template <int GG, int NB>
+static cudaError_t launch_shell4_one(tuna_ctx* ctx, const tuna_ctx::Job4Host& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
+                                     double* Jf, double* Kf, double tau, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(k_shell4_one<GG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per device: cheap, so unconditional
+    if (e != cudaSuccess) return e;
+    const long long nunit = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
+    long long blocks = (nunit - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // units owned by this rank
+    if (blocks <= 0) return cudaSuccess;
+    const size_t by_smem = std::max<size_t>(1, (size_t)(228 * 1024) / (jh.smem + 1024));
+    const size_t by_thr = std::max<size_t>(1, 2048 / jh.threads);
+    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * (long long)std::min(by_smem, by_thr) * 2);
+    k_shell4_one<GG, NB><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
+                                                                      ctx->shard_rank, ctx->shard_n, jh.tab_off, jh.hdr_off);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const double* Psym, double* Jc, double* Kc, double tau) {
+    ShellData D;
+    D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
+    D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
+    D.eri_out = nullptr; D.fnorm = ctx->d_fnorm;
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
+    int jn = 0;
+    for (const auto& jh : ctx->jobs4) {
+        cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
+        cudaError_t e;
+#define TUNA_ONE4(GV) (jh.nb == 4 ? launch_shell4_one<GV, 4>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
+                       : jh.nb == 2 ? launch_shell4_one<GV, 2>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
+                                    : launch_shell4_one<GV, 1>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st))
+        switch (jh.G) {
+            case 1: e = TUNA_ONE4(1); break;
+            case 2: e = TUNA_ONE4(2); break;
+            case 4: e = TUNA_ONE4(4); break;
+            case 8: e = TUNA_ONE4(8); break;
+            case 16: e = TUNA_ONE4(16); break;
+            case 32: e = TUNA_ONE4(32); break;
+            case 64: e = TUNA_ONE4(64); break;
+            case 128: e = TUNA_ONE4(128); break;
+            default: e = TUNA_ONE4(256); break;
+        }
+#undef TUNA_ONE4
+        if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell4_one launch: ") + cudaGetErrorString(e));
+    }
+    for (int a = 0; a < tuna_ctx::NAUX; ++a) {
+        CK(cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[a], 0));
+    }
+    return TUNA_OK;
+}
+
 // Dense Cartesian tensor through the shell-quartet engine: every shell quartet once (no screening), canonical AO quartets
 // scattered to their eight images; ctx->d_eri_cart is allocated and zeroed by the caller (parity-forbidden entries stay exact zeros).
 static int shell_fill(tuna_ctx* ctx) {
@@ -2375,7 +2668,8 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     int rc;
     if ((rc = ensure_mats(ctx, nD, nb, nc))) return rc;
     if ((rc = ensure_schwarz(ctx))) return rc;
-    if (shell && (rc = ensure_shell(ctx, tau, nD))) return rc;
+    const bool gen4 = shell && ctx->engine_gen == 4;
+    if (shell && (rc = gen4 ? ensure_shell4(ctx, tau, nD) : ensure_shell(ctx, tau, nD))) return rc;
     const size_t ncc = (size_t)nc * nc;
     const CsrDev& Uin = shell ? ctx->Uft : ctx->Ut;      // the shell engine works with unnormalised components: U' = U diag(f)
     const CsrDev& Uout = shell ? ctx->Uf : ctx->U;
@@ -2396,7 +2690,8 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     if (shell) {
         k_add_transpose_signed<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_Pc, ctx->d_tmp, nD, nc, 0u);   // Psym = P + P^T
         ctx->launches++;
-        if ((rc = launch_shell_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, nullptr))) return rc;
+        if ((rc = gen4 ? launch_shell4_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau)
+                       : launch_shell_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, nullptr))) return rc;
     } else {
         k_jk_direct<<<grid_for(ctx, ctx->task_begin[4] / ctx->shard_n + 1, 128, 16), 128, 0, ctx->stream>>>(
             table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, nc, nD, tau, ctx->d_scalars, ctx->d_scalars + 1,
