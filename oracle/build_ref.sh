@@ -24,3 +24,9 @@ $PY -m cython -3 -X boundscheck=False -X wraparound=False -X cdivision=True -X n
     "$OUT/tuna_integral.c" -o "$OUT/tuna_integral$EXT" -lm
 rm -f "$OUT/tuna_integral.c"
 echo "built $OUT/tuna_integral$EXT"
+# Stage the reference's own Python modules (UNMODIFIED, byte for byte) next to the engine so that the `-m gpu` tests can run the real
+# reference driver (tuna_energy.evaluate_molecular_energy) on the GPU box, where /root/reference does not exist.  Like the .so this
+# copy lives only under the git-ignored oracle/_ref/ and never enters the repository history.
+mkdir -p "$OUT/TUNA"
+cp -f "$REF"/TUNA/*.py "$OUT/TUNA/"
+echo "staged $(ls "$OUT/TUNA" | wc -l) reference modules under $OUT/TUNA"

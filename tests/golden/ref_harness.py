@@ -21,12 +21,23 @@ import numpy as np
 REFERENCE_ROOT = os.environ.get("TUNA_REFERENCE", "/root/reference")
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF_SO_DIR = os.path.join(REPO_ROOT, "oracle", "_ref")
+STAGED_TUNA_DIR = os.path.join(REF_SO_DIR, "TUNA")     # oracle/build_ref.sh stages the unmodified modules here for the GPU box
 
 BOHR_PER_ANGSTROM = 1.8897261259065457
 
 
+def reference_tuna_dir():
+    """The reference's module directory: the read-only tree in the development container, else the copy staged by oracle/build_ref.sh."""
+    live = os.path.join(REFERENCE_ROOT, "TUNA")
+    if os.path.isdir(live):
+        return live
+    if os.path.isfile(os.path.join(STAGED_TUNA_DIR, "tuna_energy.py")):
+        return STAGED_TUNA_DIR
+    return None
+
+
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "TUNA"))
+    return reference_tuna_dir() is not None and any(f.startswith("tuna_integral") and f.endswith(".so") for f in os.listdir(REF_SO_DIR))
 
 
 def load_reference_engine():
@@ -44,7 +55,7 @@ def load_reference():
     if _loaded:
         return _loaded["ns"]
     if not reference_available():
-        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+        raise RuntimeError("reference modules not present (neither " + REFERENCE_ROOT + " nor " + STAGED_TUNA_DIR + ")")
     termcolor = types.ModuleType("termcolor")
     termcolor.colored = lambda s, *a, **k: s
     sys.modules.setdefault("termcolor", termcolor)
@@ -57,7 +68,7 @@ def load_reference():
     pkg.__path__ = []
     sys.modules["tuna_integrals"] = pkg
     sys.modules["tuna_integrals.tuna_integral"] = engine
-    tuna_dir = os.path.join(REFERENCE_ROOT, "TUNA")
+    tuna_dir = reference_tuna_dir()
     if tuna_dir not in sys.path:
         sys.path.insert(0, tuna_dir)
     ns = types.SimpleNamespace()

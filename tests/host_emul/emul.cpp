@@ -228,13 +228,15 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
             J.item_prefix = prefix.data(); J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
             Class4Host CH;
             const char* eb = getenv("TUNA_EMUL_IT_BUDGET");      // small budgets force the multi-chunk path in tests
-            if (eb) build_class4_tables(T, J.La, J.Lb, J.Lc, J.Ld, CH, atoi(eb), atoi(eb)); else build_class4_tables(T, J.La, J.Lb, J.Lc, J.Ld, CH);
+            const char* etm = getenv("TUNA_EMUL_TERM_MAX");       // 0 forces the separable digestion for every class
+            const int tmax = etm ? atoi(etm) : S4_TERM_MAX;
+            if (eb) build_class4_tables(T, J.La, J.Lb, J.Lc, J.Ld, CH, atoi(eb), atoi(eb), tmax); else build_class4_tables(T, J.La, J.Lb, J.Lc, J.Ld, CH, S4_IT_BUDGET, S4_S_BUDGET, tmax);
             J.ct = class4_view(CH, HostPtrOf());
             shell4_job_layout(J, nD);
             const char* enb = getenv("TUNA_EMUL_NB");
             const int NBATCH = enb ? atoi(enb) : 2;
             std::vector<double> sm((size_t)4 * J.total);
-            std::vector<unsigned> tab(CH.ntab);
+            std::vector<unsigned> tab(CH.tab_words + 4);
             int tab_chunk = -1;
             Quartet4 hq[4];
             for (int q = 0; q < 4; ++q) hq[q] = Quartet4{0, 0, 0, 0, 0.0};
@@ -261,7 +263,7 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
                 if (++nb == NBATCH) run_batch();
             }
             run_batch();
-            nitems_total += J.nitems; nint_total += CH.nint; nterm_total += CH.terms;
+            nitems_total += J.nitems; nint_total += CH.nint; nterm_total += CH.nterms;
         }
     for (int d = 0; d < nD; ++d)
         for (int i = 0; i < ncart; ++i)

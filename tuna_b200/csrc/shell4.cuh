@@ -50,6 +50,14 @@ struct Class4Dev {
     unsigned char gsz[4][4];                      //            components in group g
     int ncols[4], pgoff[4];                       // per parity class: gammas (= row length), first Pg staging entry
     Kind4 kind[4];                                // KAC, KAD, KBC, KBD
+    // plan[(kind * 4 + g) * 4 + og] = first outer'' | outer count << 8 | first inner'' << 16 | inner pairs << 24 : the loop bounds of one
+    // accumulator of parity g for outer parity group og (inner group g ^ og), 0 when either group is empty
+    unsigned plan[64];
+    // term mode (light classes, one chunk): the digestion of every accumulator is a list of (integral slot, staged density entry)
+    // pairs kept in SHARED memory as byte offsets (built once per CTA from the 32-bit global list `terms`: slot | entry << 16, padded to
+    // pairs with (zero row, entry 0)); tptr[w] = first pair | pairs << 20.  nterm2 = 0 selects the separable loops above.
+    int nterm2;
+    const unsigned* terms; const unsigned* tptr;
     // work list: acc[2 w] = kind | g << 4 | u << 8 | v << 16 for K (kind 0..3), kind | pc << 4 for J (4 = bra pair function,
     // 5 = ket pair function); acc[2 w + 1] = pair-function index for J.  Sorted by descending work; Out[] is in this order.
     const unsigned* acc;
@@ -76,7 +84,7 @@ struct Shell4Job {
     double uniq[6];
     Class4Dev ct;
     // shared-memory layout of one group (offsets in doubles, each array interleaved over the NB quartets of a batch)
-    int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oRecA, oRecC, oAO, aostride, total;
+    int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oRecA, oRecC, oAO, oPref, aostride, total;
 };
 
 inline void shell4_job_layout(Shell4Job& J, int nD) {
@@ -100,19 +108,48 @@ inline void shell4_job_layout(Shell4Job& J, int nD) {
     if (J.Ld > lmax) lmax = J.Ld;
     J.aostride = (lmax + 1) * (lmax + 2) / 2;
     J.oAO = o; o += (4 * J.aostride * (int)sizeof(int) + 7) / 8;
+    J.oPref = o; o += 1;
     J.total = (o + 1) & ~1;
 }
 
 // Copy the digestion tables of chunk ch into the CTA's table area, scaled to byte offsets of an NB-interleaved slot.
-// (Called by all threads of the CTA; the caller synchronises.)
+// (Called by all threads of the CTA; the caller synchronises.)  Term mode: the area holds the term pairs as byte offsets relative
+// to the group's slice (integral buffer / staged densities of density 0), then tptr.
 template <int NB>
-TUNA_HD void shell4_load_tables(const Class4Dev& CT, int ch, unsigned* tab, int tid, int nthreads) {
+TUNA_HD void shell4_load_tables(const Class4Dev& CT, int ch, unsigned* tab, int tid, int nthreads, int oIt, int oP) {
+    if (CT.nterm2 > 0) {
+        for (int i = tid; i < 2 * CT.nterm2; i += nthreads) {
+            const unsigned t = CT.terms[i];
+            tab[2 * i] = ((unsigned)oIt + (t & 0xffffu)) * (unsigned)(NB * 8);
+            tab[2 * i + 1] = ((unsigned)oP + (t >> 16)) * (unsigned)(NB * 8);
+        }
+        for (int i = tid; i < CT.nwork; i += nthreads) tab[4 * CT.nterm2 + i] = CT.tptr[i];
+        return;
+    }
     const unsigned* src = CT.tabs + (size_t)ch * CT.ntab;
     const int nscaled = CT.jinfo_off;                 // everything before jinfo is a slot number (or S4_ABSENT)
     for (int i = tid; i < CT.ntab; i += nthreads) {
         unsigned v = src[i];
         if (i < nscaled) v = (v == S4_ABSENT) ? (unsigned)CT.itmax * (unsigned)(NB * 8) : v * (unsigned)(NB * 8);
         tab[i] = v;
+    }
+}
+
+// N2 pairs of inner components of one outer component: integral addresses = base + table word, densities contiguous
+template <int NB, int N2>
+TUNA_HD void digest_row4(const char* base, const unsigned* irow, const double* pp, double* s0, double* s1) {
+    unsigned c[2 * N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        const uint2 t = *reinterpret_cast<const uint2*>(irow + 2 * j);
+        c[2 * j] = t.x; c[2 * j + 1] = t.y;
+    }
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        const QVec<NB> i0 = qld<NB>(reinterpret_cast<const double*>(base + c[2 * j])), i1 = qld<NB>(reinterpret_cast<const double*>(base + c[2 * j + 1]));
+        const QVec<NB> p0 = qld<NB>(pp + 2 * j * NB), p1 = qld<NB>(pp + (2 * j + 1) * NB);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) { s0[q] = fma(i0.v[q], p0.v[q], s0[q]); s1[q] = fma(i1.v[q], p1.v[q], s1[q]); }
     }
 }
 
@@ -159,6 +196,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
     double* const Itq = sm + J.oIt * NB; double* const Pstq = sm + J.oP * NB; double* const Outq = sm + J.oOut * NB;
     double* const RAq = sm + J.oRecA * NB; double* const RCq = sm + J.oRecC * NB;
     int* const aoq = reinterpret_cast<int*>(sm + J.oAO * NB);          // [NB][4][aostride]
+    double* const prefq = sm + J.oPref * NB;                           // [NB] prefactor of the current primitive quartet
     const int lane = Pol::lane();
 
     int qa = -1;
@@ -231,7 +269,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
         if (!single) { for (int x = lane; x < CT.chunk_ni[ch] * NB; x += Pol::G) Itq[x] = 0.0; }
         if (tab_chunk != ch) {                            // (only classes with several chunks ever get here)
             Pol::sync_cta();
-            shell4_load_tables<NB>(CT, ch, tab, Pol::cta_thread(), Pol::cta_threads());
+            shell4_load_tables<NB>(CT, ch, tab, Pol::cta_thread(), Pol::cta_threads(), J.oIt, J.oP);
             tab_chunk = ch;
             Pol::sync_cta();
         }
@@ -258,17 +296,17 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                         for (int k = 0; k < m; ++k) { s *= -2.0 * rho; z *= PQz; }
                         Bq[m * NB + q] = f * s;
                         pzq[m * NB + q] = z;
+                        // the prefactor of this primitive quartet, once per quartet (a division and a square root per lane would be
+                        // a third of all instructions of the light classes); read back in phase 4, three barriers later
+                        if (m == 0) {
+                            double wq = w[0];
+#pragma unroll
+                            for (int k = 1; k < NB; ++k) if (q == k) wq = w[k];
+                            prefq[q] = wq * rA[2] * rC[2] * 34.986836655249725 / (p * qq * sqrt(pq));
+                        }
                     }
                 }
                 Pol::sync();
-                // the prefactor of this primitive quartet (lanes read the staged records: one division and square root per
-                // quartet and lane would otherwise be a third of all instructions of the light classes)
-                double pref[NB];
-#pragma unroll
-                for (int q = 0; q < NB; ++q) {
-                    const double p = RAq[q], qq = RCq[q];
-                    pref[q] = w[q] * RAq[2 * NB + q] * RCq[2 * NB + q] * 34.986836655249725 / (p * qq * sqrt(p + qq));
-                }
                 // ---- phase 1: R^n_w (closed form) and the x/y convolution table
                 for (int i = lane; i < CT.n_rt; i += Pol::G) {
                     const unsigned e = CT.t_rt[i];
@@ -349,6 +387,9 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                 Pol::sync();
                 // ---- phase 4: integral assembly, two z combinations per tile
                 {
+                    double pref[NB];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) pref[q] = prefq[q];
                     const uint4* p4 = reinterpret_cast<const uint4*>(CT.p4) + t0;
                     int e = lane;
                     uint4 nxt;
@@ -410,11 +451,55 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             }
         Pol::sync();
         // ---- phase 5: digestion of the chunk, one accumulator per lane; all addressing from the shared-memory tables
-        {
+        if (CT.nterm2 > 0) {
+            // term mode: (integral, density) byte-offset pairs of the accumulator, two terms per 16-byte shared load
+            const char* const smB = reinterpret_cast<const char*>(sm);
+            const unsigned* tptr = tab + 4 * CT.nterm2;
+            for (int wi = lane; wi < nwork; wi += Pol::G) {
+                const unsigned tp = tptr[wi];
+                const unsigned n2 = tp >> 20;
+                if (n2 == 0) continue;
+                const uint4* tl = reinterpret_cast<const uint4*>(tab) + (tp & 0xfffffu);
+                for (int dn = 0; dn < nD; ++dn) {
+                    const char* const pB = smB + dn * nstage * (NB * 8);
+                    double s0[NB], s1[NB];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) { s0[q] = 0.0; s1[q] = 0.0; }
+                    unsigned t = 0;
+                    for (; t + 1 < n2; t += 2) {
+                        const uint4 ta = tl[t], tb = tl[t + 1];
+                        const QVec<NB> i0 = qld<NB>(reinterpret_cast<const double*>(smB + ta.x)), p0 = qld<NB>(reinterpret_cast<const double*>(pB + ta.y));
+                        const QVec<NB> i1 = qld<NB>(reinterpret_cast<const double*>(smB + ta.z)), p1 = qld<NB>(reinterpret_cast<const double*>(pB + ta.w));
+                        const QVec<NB> i2 = qld<NB>(reinterpret_cast<const double*>(smB + tb.x)), p2 = qld<NB>(reinterpret_cast<const double*>(pB + tb.y));
+                        const QVec<NB> i3 = qld<NB>(reinterpret_cast<const double*>(smB + tb.z)), p3 = qld<NB>(reinterpret_cast<const double*>(pB + tb.w));
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            s0[q] = fma(i0.v[q], p0.v[q], s0[q]); s1[q] = fma(i1.v[q], p1.v[q], s1[q]);
+                            s0[q] = fma(i2.v[q], p2.v[q], s0[q]); s1[q] = fma(i3.v[q], p3.v[q], s1[q]);
+                        }
+                    }
+                    if (t < n2) {
+                        const uint4 ta = tl[t];
+                        const QVec<NB> i0 = qld<NB>(reinterpret_cast<const double*>(smB + ta.x)), p0 = qld<NB>(reinterpret_cast<const double*>(pB + ta.y));
+                        const QVec<NB> i1 = qld<NB>(reinterpret_cast<const double*>(smB + ta.z)), p1 = qld<NB>(reinterpret_cast<const double*>(pB + ta.w));
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) { s0[q] = fma(i0.v[q], p0.v[q], s0[q]); s1[q] = fma(i1.v[q], p1.v[q], s1[q]); }
+                    }
+                    QVec<NB> out = qld<NB>(Outq + (dn * nwork + wi) * NB);
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) out.v[q] += s0[q] + s1[q];
+                    qst<NB>(Outq + (dn * nwork + wi) * NB, out);
+                }
+            }
+        } else {
             const char* const ItB = reinterpret_cast<const char*>(Itq);
             const unsigned* jinfo = tab + CT.jinfo_off;
-            for (int wi = lane; wi < nwork; wi += Pol::G) {
-                const unsigned a0w = CT.acc[2 * wi], a1w = CT.acc[2 * wi + 1];
+            int wi = lane;
+            unsigned nx0 = 0u, nx1 = 0u;
+            if (wi < nwork) { nx0 = CT.acc[2 * wi]; nx1 = CT.acc[2 * wi + 1]; }
+            for (; wi < nwork; wi += Pol::G) {
+                const unsigned a0w = nx0, a1w = nx1;
+                if (wi + Pol::G < nwork) { nx0 = CT.acc[2 * (wi + Pol::G)]; nx1 = CT.acc[2 * (wi + Pol::G) + 1]; }
                 const int kd = a0w & 15;
                 for (int dn = 0; dn < nD; ++dn) {
                     const double* Pd = Pstq + dn * nstage * NB;
@@ -424,28 +509,34 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                     if (kd < 4) {
                         const Kind4& K = CT.kind[kd];
                         const int g = (a0w >> 4) & 3, u = (a0w >> 8) & 255, v = (a0w >> 16) & 255;
+                        const int ik = K.inner_ket, padi = K.pad_inner;
                         const unsigned* brow = tab + K.bra_tab + u * K.bra_pitch;
                         const unsigned* krow = tab + K.ket_tab + v * K.ket_pitch;
-                        const unsigned* orow = K.inner_ket ? brow : krow;
-                        const unsigned* irow = K.inner_ket ? krow : brow;
-                        const unsigned char* ogo = CT.pgofs[K.oshell];
-                        const unsigned char* ogs = CT.gsz[K.oshell];
-                        const unsigned char* igo = CT.pgofs[K.ishell];
+                        const unsigned* orow = ik ? brow : krow;
+                        const unsigned* irow = ik ? krow : brow;
+                        const double* Pk = Pd + K.pbase * NB;
+                        const unsigned* plan = CT.plan + (kd * 4 + g) * 4;
+#pragma unroll 1
                         for (int og = 0; og < 4; ++og) {
-                            const int ig = g ^ og;
-                            const int ib = igo[ig], ie = igo[ig + 1];
-                            if (ie == ib) continue;
-                            const int ob = ogo[og], oe = ob + ogs[og];
-                            for (int o = ob; o < oe; ++o) {
-                                const char* base = ItB + orow[o];
-                                const double* pp = Pd + (K.pbase + o * K.pad_inner + ib) * NB;
-                                for (int i = ib; i < ie; i += 2, pp += 2 * NB) {
-                                    const uint2 c2 = *reinterpret_cast<const uint2*>(irow + i);
-                                    const QVec<NB> i0 = qld<NB>(reinterpret_cast<const double*>(base + c2.x));
-                                    const QVec<NB> i1 = qld<NB>(reinterpret_cast<const double*>(base + c2.y));
-                                    const QVec<NB> p0 = qld<NB>(pp), p1 = qld<NB>(pp + NB);
-#pragma unroll
-                                    for (int q = 0; q < NB; ++q) { s0[q] = fma(i0.v[q], p0.v[q], s0[q]); s1[q] = fma(i1.v[q], p1.v[q], s1[q]); }
+                            const unsigned pl = plan[og];
+                            if (pl == 0u) continue;
+                            const int ob = pl & 255, on = (pl >> 8) & 255, ib = (pl >> 16) & 255, n2 = pl >> 24;
+                            const unsigned* ir = irow + ib;
+                            const double* pp = Pk + (ob * padi + ib) * NB;
+                            const unsigned* op = orow + ob;
+                            if (n2 == 3) {
+#pragma unroll 1
+                                for (int o = 0; o < on; ++o, pp += padi * NB) digest_row4<NB, 3>(ItB + op[o], ir, pp, s0, s1);
+                            } else if (n2 == 2) {
+#pragma unroll 1
+                                for (int o = 0; o < on; ++o, pp += padi * NB) digest_row4<NB, 2>(ItB + op[o], ir, pp, s0, s1);
+                            } else if (n2 == 1) {
+#pragma unroll 1
+                                for (int o = 0; o < on; ++o, pp += padi * NB) digest_row4<NB, 1>(ItB + op[o], ir, pp, s0, s1);
+                            } else {
+                                for (int o = 0; o < on; ++o, pp += padi * NB) {
+                                    const char* base = ItB + op[o];
+                                    for (int i = 0; i < n2; ++i) digest_row4<NB, 1>(base, ir + 2 * i, pp + 2 * i * NB, s0, s1);
                                 }
                             }
                         }
@@ -458,12 +549,16 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                             const double* pp = Pd + (CT.nkst + CT.pgoff[pc]) * NB;
                             const int n = CT.ncols[pc];
                             int k = 0;
-                            for (; k + 1 < n; k += 2) {
-                                const QVec<NB> i0 = qld<NB>(ip + k * NB), i1 = qld<NB>(ip + (k + 1) * NB), p0 = qld<NB>(pp + k * NB), p1 = qld<NB>(pp + (k + 1) * NB);
+                            for (; k + 3 < n; k += 4) {
+                                const QVec<NB> i0 = qld<NB>(ip + k * NB), i1 = qld<NB>(ip + (k + 1) * NB), i2 = qld<NB>(ip + (k + 2) * NB), i3 = qld<NB>(ip + (k + 3) * NB);
+                                const QVec<NB> p0 = qld<NB>(pp + k * NB), p1 = qld<NB>(pp + (k + 1) * NB), p2 = qld<NB>(pp + (k + 2) * NB), p3 = qld<NB>(pp + (k + 3) * NB);
 #pragma unroll
-                                for (int q = 0; q < NB; ++q) { s0[q] = fma(i0.v[q], p0.v[q], s0[q]); s1[q] = fma(i1.v[q], p1.v[q], s1[q]); }
+                                for (int q = 0; q < NB; ++q) {
+                                    s0[q] = fma(i0.v[q], p0.v[q], s0[q]); s1[q] = fma(i1.v[q], p1.v[q], s1[q]);
+                                    s0[q] = fma(i2.v[q], p2.v[q], s0[q]); s1[q] = fma(i3.v[q], p3.v[q], s1[q]);
+                                }
                             }
-                            if (k < n) {
+                            for (; k < n; ++k) {
                                 const QVec<NB> i0 = qld<NB>(ip + k * NB), p0 = qld<NB>(pp + k * NB);
 #pragma unroll
                                 for (int q = 0; q < NB; ++q) s0[q] = fma(i0.v[q], p0.v[q], s0[q]);
@@ -477,7 +572,14 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                         const unsigned stride = (unsigned)CT.ncols[pc] * slotb;
                         const char* ip = ItB + row0 + col;
                         const double* pp = Pd + (CT.nkst + CT.ngamma + pb0) * NB;
-                        for (unsigned r = 0; r < nrows; ++r, ip += stride, pp += NB) {
+                        unsigned r = 0;
+                        for (; r + 1 < nrows; r += 2, ip += 2 * stride, pp += 2 * NB) {
+                            const QVec<NB> i0 = qld<NB>(reinterpret_cast<const double*>(ip)), i1 = qld<NB>(reinterpret_cast<const double*>(ip + stride));
+                            const QVec<NB> p0 = qld<NB>(pp), p1 = qld<NB>(pp + NB);
+#pragma unroll
+                            for (int q = 0; q < NB; ++q) { s0[q] = fma(i0.v[q], p0.v[q], s0[q]); s1[q] = fma(i1.v[q], p1.v[q], s1[q]); }
+                        }
+                        if (r < nrows) {
                             const QVec<NB> i0 = qld<NB>(reinterpret_cast<const double*>(ip)), p0 = qld<NB>(pp);
 #pragma unroll
                             for (int q = 0; q < NB; ++q) s0[q] = fma(i0.v[q], p0.v[q], s0[q]);

@@ -20,18 +20,23 @@ struct Class4Host {
     int ncols[4], pgoff[4];
     Kind4 kind[4];
     std::vector<int> chunk_s0, chunk_t0, chunk_ni, chunk_row0;
-    std::vector<unsigned> t_rt, t_xy, t_u, t_s, p4, tabs, acc, jst_ptr, jflush;
+    std::vector<unsigned> t_rt, t_xy, t_u, t_s, p4, tabs, acc, jst_ptr, jflush, terms, tptr;
+    unsigned plan[64];
+    int nterm2 = 0;                        // > 0: term mode (digestion lists in shared memory), pairs of terms
+    int tab_words = 0;                     // words of the CTA's table area in either mode
     std::vector<unsigned short> pmap, omap, jst_list;
     long long allowed = 0;                 // parity-allowed component quartets = integrals per shell quartet
-    long long terms = 0;                   // digestion terms (table statistics)
+    long long nterms = 0;                  // digestion terms (table statistics)
+    bool terms_possible(int term_max) const { return nterms + nwork <= term_max && itmax < 65535 && nstage < 65535; }
     double uniq[6] = {0, 0, 0, 0, 0, 0};   // unique AO quartets a shell quartet stands for, by degeneracy case (as ClassTablesHost)
 };
 
 constexpr int S4_IT_BUDGET = 6144;     // doubles of shared memory for the integral buffer of a chunk
 constexpr int S4_S_BUDGET = 4096;      // doubles for the S slice of a chunk
+constexpr int S4_TERM_MAX = 3072;      // digestion terms up to which a single-chunk class keeps its term lists in shared memory (term mode)
 
 inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld, Class4Host& C, int it_budget = S4_IT_BUDGET,
-                                int s_budget = S4_S_BUDGET) {
+                                int s_budget = S4_S_BUDGET, int term_max = S4_TERM_MAX) {
     C = Class4Host();
     C.La = La; C.Lb = Lb; C.Lc = Lc; C.Ld = Ld;
     const int Lsh[4] = {La, Lb, Lc, Ld};
@@ -186,6 +191,13 @@ inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int L
         }
         C.nkst = pb;
     }
+    for (int k = 0; k < 4; ++k)
+        for (int g = 0; g < 4; ++g)
+            for (int og = 0; og < 4; ++og) {
+                const int os = C.kind[k].oshell, is = C.kind[k].ishell, ig = g ^ og;
+                const int on = C.gsz[os][og], n2 = (C.pgofs[is][ig + 1] - C.pgofs[is][ig]) / 2;
+                C.plan[(k * 4 + g) * 4 + og] = (on == 0 || n2 == 0) ? 0u : ((unsigned)C.pgofs[os][og] | (unsigned)on << 8 | (unsigned)C.pgofs[is][ig] << 16 | (unsigned)n2 << 24);
+            }
     C.pmap.assign(C.nkst, 0xffff);
     for (int k = 0; k < 4; ++k) {
         const Kind4& K = C.kind[k];
@@ -201,6 +213,7 @@ inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int L
 
     // ---- per chunk: row order, slots, S layout, phase 3 / 4 lists, digestion tables ---------------------------------------------
     std::vector<int> beta_chunk(nbeta, -1), beta_pb(nbeta, -1);     // chunk of a beta, its position in the Pb staging order
+    std::vector<int> Rb0;                                            // integral-buffer rows of chunk 0 (term mode needs a single chunk)
     int pb_run = 0;
     C.chunk_s0.push_back(0); C.chunk_t0.push_back(0);
     for (int ch = 0; ch < nchunk; ++ch) {
@@ -225,6 +238,7 @@ inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int L
             }
             tab[C.jinfo_off + 4 * pc + 1] = (unsigned)n;
         }
+        if (ch == 0) Rb0 = Rb;
         C.chunk_ni.push_back(slots);
         C.itmax = std::max(C.itmax, slots);
         C.nint += slots;
@@ -331,15 +345,15 @@ inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int L
                 const int g = T.pg[Lsh[us]][u] ^ T.pg[Lsh[vs]][v];
                 long long cost = 0;
                 for (int og = 0; og < 4; ++og) cost += (long long)C.gsz[ss][og] * C.gsz[ts][g ^ og];
-                C.terms += cost;
+                C.nterms += cost;
                 work.push_back({(unsigned)k | (unsigned)g << 4 | (unsigned)u << 8 | (unsigned)v << 16, 0u, cost, rc(us, u, vs, v), -1, -1});
             }
     }
-    for (int b = 0; b < nbeta; ++b) { work.push_back({4u | (unsigned)betas[b].pc << 4, (unsigned)b, (long long)C.ncols[betas[b].pc], 0xffff, b, -1}); C.terms += C.ncols[betas[b].pc]; }
+    for (int b = 0; b < nbeta; ++b) { work.push_back({4u | (unsigned)betas[b].pc << 4, (unsigned)b, (long long)C.ncols[betas[b].pc], 0xffff, b, -1}); C.nterms += C.ncols[betas[b].pc]; }
     {
         int nb_pc[4] = {0, 0, 0, 0};
         for (int b = 0; b < nbeta; ++b) ++nb_pc[betas[b].pc];
-        for (int g = 0; g < ngamma; ++g) { work.push_back({5u | (unsigned)gammas[g].pc << 4, (unsigned)g, (long long)nb_pc[gammas[g].pc], 0xffff, -1, g}); C.terms += nb_pc[gammas[g].pc]; }
+        for (int g = 0; g < ngamma; ++g) { work.push_back({5u | (unsigned)gammas[g].pc << 4, (unsigned)g, (long long)nb_pc[gammas[g].pc], 0xffff, -1, g}); C.nterms += nb_pc[gammas[g].pc]; }
     }
     // warps should be homogeneous: order by (kind, parity), heavier kinds first
     std::stable_sort(work.begin(), work.end(), [](const Work& x, const Work& y) {
@@ -358,6 +372,51 @@ inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int L
         for (int b = 0; b < nc[1]; ++b) C.jflush.push_back((unsigned)rc(0, a, 1, b) | (unsigned)pos_jb[bidx[a * nc[1] + b]] << 16);
     for (int c = 0; c < nc[2]; ++c)
         for (int d = 0; d < nc[3]; ++d) C.jflush.push_back((unsigned)rc(2, c, 3, d) | (unsigned)pos_jg[gidx[c * nc[3] + d]] << 16);
+
+    // ---- term mode: light single-chunk classes digest through explicit (slot, density entry) lists held in shared memory --------------
+    C.tab_words = C.ntab;
+    if (nchunk == 1 && C.terms_possible(term_max)) {
+        // compact staging: P[d][b], P[c][b], P[d][a], P[c][a] without padding, then Pg and Pb as above
+        const int pbo[4] = {0, nc[3] * nc[1], nc[3] * nc[1] + nc[2] * nc[1], nc[3] * nc[1] + nc[2] * nc[1] + nc[3] * nc[0]};
+        const int nk = pbo[3] + nc[2] * nc[0];
+        C.pmap.assign(nk, 0);
+        for (int d = 0; d < nc[3]; ++d) for (int b = 0; b < nc[1]; ++b) C.pmap[pbo[0] + d * nc[1] + b] = rc(3, d, 1, b);
+        for (int c = 0; c < nc[2]; ++c) for (int b = 0; b < nc[1]; ++b) C.pmap[pbo[1] + c * nc[1] + b] = rc(2, c, 1, b);
+        for (int d = 0; d < nc[3]; ++d) for (int a = 0; a < nc[0]; ++a) C.pmap[pbo[2] + d * nc[0] + a] = rc(3, d, 0, a);
+        for (int c = 0; c < nc[2]; ++c) for (int a = 0; a < nc[0]; ++a) C.pmap[pbo[3] + c * nc[0] + a] = rc(2, c, 0, a);
+        C.nkst = nk;
+        C.nstage = nk + ngamma + nbeta;
+        std::vector<std::vector<unsigned>> lists(C.nwork);
+        auto slot_of = [&](int a, int b, int c, int d) { return (unsigned)(Rb0[bidx[a * nc[1] + b]] + Cg[gidx[c * nc[3] + d]]); };
+        std::vector<int> pos_k[4];
+        for (int k = 0; k < 4; ++k) pos_k[k].assign(nK[k][0] * nK[k][1], -1);
+        for (int w = 0; w < C.nwork; ++w) {
+            const unsigned w0 = work[w].w0;
+            if ((w0 & 15u) < 4u) pos_k[w0 & 15u][((w0 >> 8) & 255u) * nK[w0 & 15u][1] + ((w0 >> 16) & 255u)] = w;
+        }
+        for (int a = 0; a < nc[0]; ++a) for (int b = 0; b < nc[1]; ++b) for (int c = 0; c < nc[2]; ++c) for (int d = 0; d < nc[3]; ++d) {
+            if ((T.pg[La][a] ^ T.pg[Lb][b] ^ T.pg[Lc][c] ^ T.pg[Ld][d]) != 0) continue;
+            const unsigned sl = slot_of(a, b, c, d);
+            lists[pos_k[0][a * nc[2] + c]].push_back(sl | (unsigned)(pbo[0] + d * nc[1] + b) << 16);     // KAC += I P[d][b]
+            lists[pos_k[1][a * nc[3] + d]].push_back(sl | (unsigned)(pbo[1] + c * nc[1] + b) << 16);     // KAD += I P[c][b]
+            lists[pos_k[2][b * nc[2] + c]].push_back(sl | (unsigned)(pbo[2] + d * nc[0] + a) << 16);     // KBC += I P[d][a]
+            lists[pos_k[3][b * nc[3] + d]].push_back(sl | (unsigned)(pbo[3] + c * nc[0] + a) << 16);     // KBD += I P[c][a]
+        }
+        for (int b = 0; b < nbeta; ++b)
+            for (int g = 0; g < ngamma; ++g) {
+                if (betas[b].pc != gammas[g].pc) continue;
+                const unsigned sl = (unsigned)(Rb0[b] + Cg[g]);
+                lists[pos_jb[b]].push_back(sl | (unsigned)(nk + C.pgoff[gammas[g].pc] + Cg[g]) << 16);     // Jb[beta]  += I Pg[gamma]
+                lists[pos_jg[g]].push_back(sl | (unsigned)(nk + ngamma + beta_pb[b]) << 16);               // Jg[gamma] += I Pb[beta]
+            }
+        for (int w = 0; w < C.nwork; ++w) {
+            if (lists[w].size() & 1) lists[w].push_back((unsigned)C.itmax);                                // pad: zero row, density entry 0
+            C.tptr.push_back((unsigned)(C.terms.size() / 2) | (unsigned)(lists[w].size() / 2) << 20);
+            C.terms.insert(C.terms.end(), lists[w].begin(), lists[w].end());
+        }
+        C.nterm2 = (int)C.terms.size() / 2;
+        C.tab_words = 4 * C.nterm2 + C.nwork;
+    }
 
     // ---- statistics ------------------------------------------------------------------------------------------------------------
     for (int a = 0; a < nc[0]; ++a) for (int b = 0; b < nc[1]; ++b) for (int c = 0; c < nc[2]; ++c) for (int d = 0; d < nc[3]; ++d)
@@ -396,6 +455,8 @@ inline Class4Dev class4_view(const Class4Host& C, PtrOf ptr) {
         for (int g = 0; g < 4; ++g) V.gsz[s][g] = C.gsz[s][g];
         V.ncols[s] = C.ncols[s]; V.pgoff[s] = C.pgoff[s]; V.kind[s] = C.kind[s];
     }
+    for (int i = 0; i < 64; ++i) V.plan[i] = C.plan[i];
+    V.nterm2 = C.nterm2; V.terms = ptr(C.terms); V.tptr = ptr(C.tptr);
     V.acc = ptr(C.acc); V.pmap = ptr(C.pmap); V.omap = ptr(C.omap);
     V.jst_ptr = ptr(C.jst_ptr); V.jst_list = ptr(C.jst_list); V.jflush = ptr(C.jflush); V.njfl = (int)C.jflush.size();
     return V;

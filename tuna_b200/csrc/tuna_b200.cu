@@ -964,7 +964,7 @@ k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, co
     double* sm = smem_all + (size_t)gid * NB * J.total;
     const double dmax = __longlong_as_double((long long)scalars[0]);
     const long long nunit = (J.nitems + CH - 1) / CH;
-    shell4_load_tables<NB>(J.ct, 0, tab, threadIdx.x, blockDim.x);
+    shell4_load_tables<NB>(J.ct, 0, tab, threadIdx.x, blockDim.x, J.oIt, J.oP);
     int tab_chunk = 0;
     double done = 0.0;
     for (long long gc = (long long)blockIdx.x * nranks + rank; gc < nunit; gc += (long long)gridDim.x * nranks) {
@@ -1727,7 +1727,7 @@ int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K)
 int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
     if (!ctx) return TUNA_ERR_ARG;
     if (nranks < 1 || rank < 0 || rank >= nranks) FAIL(TUNA_ERR_ARG, "tuna_set_shard: bad rank / nranks");
-    if (ctx->shard_n != nranks) ctx->shell_tau = -1.0;      // the big/small job split depends on the rank count
+    if (ctx->shard_n != nranks) { ctx->shell_tau = -1.0; ctx->shell4_tau = -1.0; }      // work-unit sizes / the big-small job split depend on the rank count
     ctx->shard_rank = rank; ctx->shard_n = nranks;
     return TUNA_OK;
 }
@@ -2366,7 +2366,7 @@ static int shell4_slice_doubles(const Class4Host& C, int nD) {
     Jt.La = C.La; Jt.Lb = C.Lb; Jt.Lc = C.Lc; Jt.Ld = C.Ld;
     Jt.ct.ssize = C.ssize; Jt.ct.itmax = C.itmax; Jt.ct.zrow = C.zrow; Jt.ct.nstage = C.nstage; Jt.ct.nwork = C.nwork;
     shell4_job_layout(Jt, nD);
-    return Jt.total + (C.ntab + 1) / 2 + 16;
+    return Jt.total + (C.tab_words + 1) / 2 + 16;
 }
 
 static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int nD, tuna_ctx::ClassTab4Dev** out) {
@@ -2377,8 +2377,10 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     {
         const char* eb = getenv("TUNA_B200_IT_BUDGET");
         const char* es = getenv("TUNA_B200_S_BUDGET");
+        const char* etm = getenv("TUNA_B200_TERM_MAX");
         int itb = eb ? atoi(eb) : S4_IT_BUDGET, sb = es ? atoi(es) : S4_S_BUDGET;
-        build_class4_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb);
+        const int tmax = etm ? atoi(etm) : S4_TERM_MAX;
+        build_class4_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb, tmax);
         // a slice that does not fit one CTA is re-cut into more chunks; a slice between half and all of an SM's shared memory is
         // re-cut so that two CTAs fit (phases 0-2 then run once per chunk)
         const int tier2 = (225 * 1024 / 2 - 1024 - 64) / 8;
@@ -2392,13 +2394,13 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
             Class4Host trial;
             bool found = false;
             for (int want = nch + 1; want <= nch + 3 && !found; ++want) {
-                build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.nint / want + E.host.nint / (8 * want)), 65000);
+                build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.nint / want + E.host.nint / (8 * want)), 65000, tmax);
                 if ((int)trial.chunk_row0.size() - 1 > nch && (shell4_slice_doubles(trial, nD) <= (too_big ? SHELL4_SMEM_DOUBLES : tier2))) found = true;
             }
             if (found) { E.host = trial; if (!too_big) break; }
             else if (!too_big) break;
             else if (pass == 5) FAIL(TUNA_ERR_STATE, "shell engine: class does not fit shared memory");
-            else { build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.itmax / 2), std::max(64, E.host.ssize / 2)); E.host = trial; }
+            else { build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.itmax / 2), std::max(64, E.host.ssize / 2), tmax); E.host = trial; }
         }
     }
     const Class4Host& C = E.host;
@@ -2413,15 +2415,13 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     const size_t o_tabs = add(C.tabs.data(), C.tabs.size() * 4), o_acc = add(C.acc.data(), C.acc.size() * 4);
     const size_t o_pmap = add(C.pmap.data(), C.pmap.size() * 2), o_omap = add(C.omap.data(), C.omap.size() * 2);
     const size_t o_jp = add(C.jst_ptr.data(), C.jst_ptr.size() * 4), o_jl = add(C.jst_list.data(), C.jst_list.size() * 2), o_jf = add(C.jflush.data(), C.jflush.size() * 4);
+    const size_t o_tm = add(C.terms.data(), C.terms.size() * 4), o_tp = add(C.tptr.data(), C.tptr.size() * 4);
     std::vector<unsigned char> host(total, 0);
     for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
     int rc;
     if ((rc = dev_alloc(ctx, &E.blob, total))) return rc;
     CK(cudaMemcpyAsync(E.blob, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    struct BlobPtr {
-        unsigned char* base; const Class4Host* C; const size_t* offs;
-    };
     Class4Dev& V = E.view;
     V = class4_view(C, HostPtrOf());          // scalars; the pointers are replaced by device addresses below
     V.t_rt = (const unsigned*)(E.blob + o_rt); V.t_xy = (const unsigned*)(E.blob + o_xy); V.t_u = (const unsigned*)(E.blob + o_u);
@@ -2429,6 +2429,7 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     V.chunk_t0 = (const int*)(E.blob + o_t0); V.chunk_ni = (const int*)(E.blob + o_ni); V.tabs = (const unsigned*)(E.blob + o_tabs);
     V.acc = (const unsigned*)(E.blob + o_acc); V.pmap = (const unsigned short*)(E.blob + o_pmap); V.omap = (const unsigned short*)(E.blob + o_omap);
     V.jst_ptr = (const unsigned*)(E.blob + o_jp); V.jst_list = (const unsigned short*)(E.blob + o_jl); V.jflush = (const unsigned*)(E.blob + o_jf);
+    V.terms = (const unsigned*)(E.blob + o_tm); V.tptr = (const unsigned*)(E.blob + o_tp);
     *out = &E;
     return TUNA_OK;
 }
@@ -2482,10 +2483,17 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             jh.G = G; jh.nb = nb;
             jh.threads = G <= 32 ? 128 : G;
             jh.gpc = jh.threads / G;
-            J.chunk = jh.gpc * SHELL_ITEMS_PER_GROUP;
+            {   // items per CTA work unit: enough units to spread over all CTA slots of all ranks eight times, at most 16 per group
+                const size_t by_smem = std::max<size_t>(1, (size_t)(228 * 1024) / ((size_t)jh.gpc * nb * J.total * 8 + 2048));
+                const long long slots = (long long)ctx->sm_count * (long long)std::min<size_t>(by_smem, 2048 / jh.threads) * ctx->shard_n;
+                long long per = J.nitems / std::max<long long>(1, slots * 8 * jh.gpc);
+                per = std::max<long long>(nb, std::min<long long>(per, 16));
+                per = (per + nb - 1) / nb * nb;
+                J.chunk = jh.gpc * (int)per;
+            }
             const size_t slices = (size_t)jh.gpc * nb * J.total;
             jh.tab_off = (int)((slices + 1) & ~(size_t)1);
-            jh.hdr_off = jh.tab_off + (J.ct.ntab + 1) / 2;
+            jh.hdr_off = jh.tab_off + (ctd->host.tab_words + 4 + 1) / 2;
             jh.smem = ((size_t)jh.hdr_off + (size_t)J.chunk * sizeof(Quartet4) / 8 + 2) * sizeof(double);
             if (jh.smem > 226 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 226 KB");
             ctx->jobs4.push_back(jh);
