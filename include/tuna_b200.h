@@ -91,6 +91,12 @@ int tuna_eri_transform(tuna_ctx* ctx, int n, const double* eri_host, int n1, con
                        int so_layout, double* out_host);
 int tuna_eri_transform_dev(tuna_ctx* ctx, int n, const double* d_eri, int n1, const double* dC1, int n2, const double* dC2,
                            int so_layout, double* d_out);
+/* The spin-orbital transformation of the post-HF drivers (TUNA/tuna_ci.py:564-570): the reference spin-blocks the AO tensor on the host,
+ *   ERI_spin_block = np.kron(np.eye(2), np.kron(np.eye(2), ERI_AO).T)            (16 n^4 doubles)
+ * and hands it to transform_ERI_AO_to_SO with spin-blocked coefficients C (2n x n_so).  Here the spin-blocked tensor is formed on the
+ * device from the RESIDENT stored tensor (dimension n = the stored dimension) and transformed in place: C1 (2n x n1), C2 (2n x n2),
+ * output layout as tuna_eri_transform with so_layout. */
+int tuna_eri_transform_spin_blocked(tuna_ctx* ctx, int n1, const double* C1, int n2, const double* C2, int so_layout, double* out_host);
 
 /* One-electron integrals of the basis given to tuna_set_basis, in the Cartesian basis:
  *   tuna_integral.calculate_one_electron_integrals(n_basis, basis_functions, n_atoms, atoms, dipole_origin, num_threads)   pyx:282-445

@@ -221,7 +221,7 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
         for (int ck = 0; ck <= cb; ++ck) {
             Shell4Job J;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
-            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4;
+            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4; J.dbg_skip = 0;
             J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
             std::vector<long long> prefix;
             J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);

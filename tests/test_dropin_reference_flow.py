@@ -88,6 +88,10 @@ class OracleBackedContext:
         T = self.orc.transform_eri_ao_to_so(E, C1, C2)
         return T if so_layout else np.ascontiguousarray(np.einsum("pqrs->prqs", T))
 
+    def eri_transform_spin_blocked(self, C1, C2=None, so_layout=True):
+        G = np.kron(np.eye(2), np.kron(np.eye(2), self.E_sph).T)          # tuna_ci.py:564
+        return self.eri_transform(C1, C2, so_layout, eri=G)
+
     def one_electron(self, atom_z, atom_charge, dipole_origin):
         return self.orc.one_electron(self.fb, atom_z, atom_charge, dipole_origin)
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "tuna_eri_fill_cart", "tuna_eri_cart_to_sph", "tuna_eri_download", "tuna_eri_upload", "tuna_eri_single", "tuna_schwarz",
     "tuna_jk_stored", "tuna_jk_stored_dev", "tuna_jk_direct", "tuna_jk_direct_dev", "tuna_set_shard", "tuna_get_counts",
     "tuna_last_kernel_ms", "tuna_algorithmic_flops", "tuna_fp64_peak_probe", "tuna_eri_transform", "tuna_eri_transform_dev",
-    "tuna_one_electron", "tuna_cross_overlap",
+    "tuna_eri_transform_spin_blocked", "tuna_one_electron", "tuna_cross_overlap",
 ]
 
 _lib = None
@@ -67,6 +67,7 @@ def load() -> ctypes.CDLL:
         "tuna_fp64_peak_probe": (ci, [vp, c_dp]),
         "tuna_eri_transform": (ci, [vp, ci, c_dp, ci, c_dp, ci, c_dp, ci, c_dp]),
         "tuna_eri_transform_dev": (ci, [vp, ci, vp, ci, vp, ci, vp, ci, vp]),
+        "tuna_eri_transform_spin_blocked": (ci, [vp, ci, c_dp, ci, c_dp, ci, c_dp]),
         "tuna_one_electron": (ci, [vp, ci, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
         "tuna_cross_overlap": (ci, [vp] + [ci, c_dp, c_ip, c_ip, c_lp, c_dp, c_dp] * 2 + [c_dp]),
     }
@@ -214,6 +215,21 @@ class Context:
         n1, n2 = C1.shape[1], C2.shape[1]
         out = _host_tensor((n2, n1, n2, n1) if so_layout else (n2, n2, n1, n1))
         self._ck(self._lib.tuna_eri_transform(self._h, n, _dp(eri), n1, _dp(C1), n2, _dp(C2), int(bool(so_layout)), _dp(out)))
+        return out
+
+    def eri_transform_spin_blocked(self, C1, C2=None, so_layout=True):
+        """Spin-orbital transformation of the spin-blocked tensor np.kron(np.eye(2), np.kron(np.eye(2), E).T) (tuna_ci.py:564-570), the
+        spin-blocked tensor (16 n^4 doubles) being formed on the device from the resident stored tensor E.  C1, C2: (2n, n_so)."""
+        C1 = np.ascontiguousarray(C1, dtype=np.float64)
+        C2 = C1 if C2 is None else np.ascontiguousarray(C2, dtype=np.float64)
+        n = self.n_stored
+        if n == 0:
+            raise error_class("tuna_b200: no stored tensor is resident")
+        if C1.ndim != 2 or C2.ndim != 2 or C1.shape[0] != 2 * n or C2.shape[0] != 2 * n:
+            raise error_class(f"tuna_b200: spin-blocked coefficient matrices must have {2 * n} rows, got {C1.shape} and {C2.shape}")
+        n1, n2 = C1.shape[1], C2.shape[1]
+        out = _host_tensor((n2, n1, n2, n1) if so_layout else (n2, n2, n1, n1))
+        self._ck(self._lib.tuna_eri_transform_spin_blocked(self._h, n1, _dp(C1), n2, _dp(C2), int(bool(so_layout)), _dp(out)))
         return out
 
     def eri_transform_dev(self, n, dT, n1, dC1, n2, dC2, so_layout, d_out):

@@ -10,11 +10,10 @@
 // interleaved chemists' layout "prqs"; the spin-orbital layout "pqrs" swaps the two middle indices in the last step's
 // store.  Each step is a tall-skinny FP64 GEMM (rows n^3, inner n, columns n_mo) that reads and writes the tensor once:
 // 2 K M NX flops against 8 NX (K + M) bytes — for K = M = 60 about 15 flop/B, above the FP64 ridge (~5.6 flop/B at
-// 37 TFLOP/s over 6.55 TB/s), so the step is FP64-pipe bound and the tile is sized for the FMA pipe: 128 x 64 outputs per
-// CTA, 8 x 4 per thread, operands staged through shared memory (T tile transposed so that a 16-byte shared load serves
-// two rows).  Measured (ncu, nbf 110): FP64 pipe 53 % active, shared-memory data pipe 74 % — the 8 x 4 register tile is bound by
-// LSU->register bandwidth (12 operand doubles per 32 DFMA); the next step is FP64 tensor-core MMA (mma.sync m8n8k4 f64), which
-// needs 8x fewer operand bytes per flop.
+// 37 TFLOP/s over 6.55 TB/s), so the step is FP64-pipe bound: 128 x 64 outputs per CTA on the FP64 tensor cores
+// (mma.sync m8n8k4 f64, SASS DMMA), operands staged through shared memory.  The round-1 kernel (8 x 4 FMA register tile) was bound
+// by LSU->register bandwidth (ncu, nbf 110: FP64 pipe 53 % active, shared-memory data pipe 74 %); the MMA fragments need 5x fewer
+// operand bytes per flop.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -27,92 +26,9 @@ constexpr int MO_TS = 64;       // output columns (s) per CTA
 constexpr int MO_KC = 16;       // contraction chunk
 constexpr int MO_TXP = MO_TX + 2;
 
-// swap != 0: X = (a, b, c) with dims (d1, d2, d3) is stored at [s][b][a][c] (spin-orbital layout, last step only).
-__global__ void __launch_bounds__(256, 2) k_axis_gemm(const double* __restrict__ T, const double* __restrict__ C, double* __restrict__ Out,
-                                                      long long NX, int K, int M, int swap, int d1, int d2, int d3) {
-    __shared__ __align__(16) double Ts[MO_KC][MO_TXP];      // [l][x]
-    __shared__ __align__(16) double Cs[MO_KC][MO_TS];       // [l][s]
-    const int t = threadIdx.x;
-    // 1-D grid with the column tile fastest: the CTAs that read the same T tile (one per column tile) are scheduled together,
-    // so the tile comes from HBM once and from L2 afterwards (a (x, y) grid re-read the tensor once per column tile: ncu
-    // dram__bytes_read 2.34 GB for an algorithmic 1.17 GB at nbf 110)
-    const int ntile_s = (M + MO_TS - 1) / MO_TS;
-    const long long X0 = (long long)(blockIdx.x / ntile_s) * MO_TX;
-    const int s0 = (int)(blockIdx.x % ntile_s) * MO_TS;
-    const int tx = t & 15, ts = t >> 4;
-    double acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-
-    const int lc = t & 15, lr = t >> 4;       // T tile loader: 16 consecutive l of one row per half-warp (128-byte segments)
-    for (int l0 = 0; l0 < K; l0 += MO_KC) {
-        __syncthreads();
-#pragma unroll
-        for (int pass = 0; pass < MO_TX / 16; ++pass) {
-            const int r = pass * 16 + lr;
-            const long long X = X0 + r;
-            const int l = l0 + lc;
-            Ts[lc][r] = (X < NX && l < K) ? T[X * K + l] : 0.0;
-        }
-#pragma unroll
-        for (int pass = 0; pass < (MO_KC * MO_TS) / 256; ++pass) {
-            const int e = pass * 256 + t, c = e / MO_TS, s = e % MO_TS;
-            const int l = l0 + c;
-            Cs[c][s] = (l < K && s0 + s < M) ? C[(size_t)l * M + s0 + s] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < MO_KC; ++c) {
-            double a[8], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double2 v = *reinterpret_cast<const double2*>(&Ts[c][i * 32 + tx * 2]);
-                a[2 * i] = v.x; a[2 * i + 1] = v.y;
-            }
-            {
-                const double2 v0 = *reinterpret_cast<const double2*>(&Cs[c][ts * 4]);
-                const double2 v1 = *reinterpret_cast<const double2*>(&Cs[c][ts * 4 + 2]);
-                b[0] = v0.x; b[1] = v0.y; b[2] = v1.x; b[3] = v1.y;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-        }
-    }
-    const bool vec = !swap && (NX % 2 == 0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int s = s0 + ts * 4 + j;
-        if (s >= M) continue;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long X = X0 + i * 32 + tx * 2;
-            if (X >= NX) continue;
-            if (vec) {       // X even, NX even: X + 1 < NX and the address is 16-byte aligned
-                *reinterpret_cast<double2*>(Out + (size_t)s * NX + X) = make_double2(acc[2 * i][j], acc[2 * i + 1][j]);
-            } else if (!swap) {
-                Out[(size_t)s * NX + X] = acc[2 * i][j];
-                if (X + 1 < NX) Out[(size_t)s * NX + X + 1] = acc[2 * i + 1][j];
-            } else {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const long long Xh = X + h;
-                    if (Xh >= NX) continue;
-                    const int c3 = (int)(Xh % d3);
-                    const long long ab = Xh / d3;
-                    const int b2 = (int)(ab % d2), a1 = (int)(ab / d2);
-                    Out[(((size_t)s * d2 + b2) * d1 + a1) * d3 + c3] = acc[2 * i + h][j];
-                }
-            }
-        }
-    }
-}
-
-#ifdef TUNA_MO_DMMA
-// Development variant (off by default, NOT yet run on a GPU): the same step on the FP64 tensor cores.  D (8 x 8) += A (8 x 4) B (4 x 8)
+// The step on the FP64 tensor cores (measured on the B200: 16.2 -> 21.2 TFLOP/s at nbf 60 -> 110 against 13.5 -> 16.3 for the 8 x 4 FMA
+// tile it replaced, profiles/r02a_mo_dmma.json).  swap != 0: X = (a, b, c) with dims (d1, d2, d3) is stored at [s][b][a][c] (spin-orbital
+// layout, last step only).  D (8 x 8) += A (8 x 4) B (4 x 8)
 // with mma.sync.aligned.m8n8k4.row.col.f64: rows = X, columns = s, inner = l.  Fragment layout (PTX ISA, m8n8k4 .f64), with
 // g = lane >> 2 and q = lane & 3:  A: a = A[g][q];  B: b = B[q][g];  C/D: c[i] = C[g][2 q + i].
 // CTA tile 128 (X) x 64 (s) as in k_axis_gemm, 8 warps as 4 (X) x 2 (s), 32 x 32 outputs per warp = 4 x 4 MMA tiles: per 4-wide
@@ -125,7 +41,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 2) k_axis_gemm_dmma(const double* __restrict__ T, const double* __restrict__ C, double* __restrict__ Out,
+__global__ void __launch_bounds__(256, 2) k_axis_gemm(const double* __restrict__ T, const double* __restrict__ C, double* __restrict__ Out,
                                                            long long NX, int K, int M, int swap, int d1, int d2, int d3) {
     __shared__ __align__(16) double Ts[MO_KC][MO_TXQ];      // [l][x]
     __shared__ __align__(16) double Cs[MO_KC][MO_TSQ];      // [l][s]
@@ -191,7 +107,6 @@ __global__ void __launch_bounds__(256, 2) k_axis_gemm_dmma(const double* __restr
             }
     }
 }
-#endif
 
 // One step on `stream`: Out[M][NX] (or the swapped layout) from T[NX][K] and C[K][M].
 inline cudaError_t axis_gemm(cudaStream_t stream, const double* T, const double* C, double* Out, long long NX, int K, int M, int swap, int d1,
@@ -200,13 +115,6 @@ inline cudaError_t axis_gemm(cudaStream_t stream, const double* T, const double*
     const int gy = (M + MO_TS - 1) / MO_TS;
     if (gx <= 0 || gy <= 0) return cudaSuccess;
     if (gx * gy > 2147483647LL) return cudaErrorInvalidConfiguration;
-#ifdef TUNA_MO_DMMA
-    static const bool dmma = !(getenv("TUNA_B200_MO_DMMA") && atoi(getenv("TUNA_B200_MO_DMMA")) == 0);
-    if (dmma) {
-        k_axis_gemm_dmma<<<(unsigned)(gx * gy), 256, 0, stream>>>(T, C, Out, NX, K, M, swap, d1, d2, d3);
-        return cudaGetLastError();
-    }
-#endif
     k_axis_gemm<<<(unsigned)(gx * gy), 256, 0, stream>>>(T, C, Out, NX, K, M, swap, d1, d2, d3);
     return cudaGetLastError();
 }

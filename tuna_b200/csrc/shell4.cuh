@@ -80,6 +80,7 @@ struct Shell4Job {
     const long long* item_prefix;
     int nbra, same_class;
     int chunk;
+    int dbg_skip;                   // development aid (TUNA_B200_DBG_SKIP): bit k set -> stage k is skipped (timing experiments only; 0 in production)
     long long nitems;
     double uniq[6];
     Class4Dev ct;
@@ -220,8 +221,9 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
         }
     }
     Pol::sync();
+    const int skip = J.dbg_skip;
     // ---- stage the density blocks (K blocks through pmap, pair-function sums through the CSR) and clear the accumulators
-    for (int dn = 0; dn < nD; ++dn) {
+    for (int dn = 0; dn < nD && !(skip & 1); ++dn) {
         const double* P = Pf + (size_t)dn * ncart * ncart;
         const double* Ps = Psym + (size_t)dn * ncart * ncart;
         double* Pd = Pstq + dn * nstage * NB;
@@ -277,13 +279,13 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             for (int ic = 0; ic < J.nppCD; ++ic) {
                 // ---- phase 0: the two primitive shell-pair records, Boys values scaled by (-2 rho)^m, powers of PQz
 #pragma unroll
-                for (int q = 0; q < NB; ++q) {
+                for (int q = 0; q < NB && !(skip & 2); ++q) {
                     const double* rA = recA[q] + ia * recAsz;
                     const double* rC = recC[q] + ic * recCsz;
                     if (ic == 0) { for (int x = lane; x < recAsz; x += Pol::G) RAq[x * NB + q] = rA[x]; }
                     for (int x = lane; x < recCsz; x += Pol::G) RCq[x * NB + q] = rC[x];
                 }
-                for (int x = lane; x < NB * 32; x += Pol::G) {
+                for (int x = lane; x < NB * 32 && !(skip & 2); x += Pol::G) {
                     const int q = x >> 5, m = x & 31;
                     if (m <= Ltot) {
                         const double* rA = recA[0] + ia * recAsz;
@@ -308,7 +310,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                 }
                 Pol::sync();
                 // ---- phase 1: R^n_w (closed form) and the x/y convolution table
-                for (int i = lane; i < CT.n_rt; i += Pol::G) {
+                for (int i = lane; i < CT.n_rt && !(skip & 4); i += Pol::G) {
                     const unsigned e = CT.t_rt[i];
                     const int wv = (e >> 16) & 255, n = e >> 24;
                     QVec<NB> r;
@@ -322,7 +324,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                     }
                     qst<NB>(Rtq + (e & 0xffffu) * NB, r);
                 }
-                for (int i = lane; i < CT.n_xy; i += Pol::G) {
+                for (int i = lane; i < CT.n_xy && !(skip & 4); i += Pol::G) {
                     const unsigned e = CT.t_xy[i];
                     const int n12 = (e >> 16) & 15, n34 = (e >> 20) & 15, m = e >> 24, px = n12 & 1;
                     const int tlo = (2 * m - n34 > px) ? 2 * m - n34 : px;
@@ -344,7 +346,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                 }
                 Pol::sync();
                 // ---- phase 2: U[v][gz][n] = sum_phi (-1)^phi Ez_CD[gz][phi] R^n_{v+phi}   (the sign rides on the FMA)
-                for (int i = lane; i < CT.n_u; i += Pol::G) {
+                for (int i = lane; i < CT.n_u && !(skip & 8); i += Pol::G) {
                     const unsigned e0w = CT.t_u[2 * i], e1w = CT.t_u[2 * i + 1];
                     const int lz34 = e1w >> 16;
                     const double* e = RCq + (SP_HDR + (e1w & 0xffffu)) * NB;
@@ -368,7 +370,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                 // ---- phase 3: S[block][n][zc] = sum_v Ez_AB[az][bz][v] U[v][gz][n] for the chunk's bra z rows, even blocks only
                 {
                     const int ustride = NGZ * NS;
-                    for (int i = CT.chunk_s0[ch] + lane; i < CT.chunk_s0[ch + 1]; i += Pol::G) {
+                    for (int i = CT.chunk_s0[ch] + lane; i < CT.chunk_s0[ch + 1] && !(skip & 16); i += Pol::G) {
                         const unsigned e0w = CT.t_s[2 * i], e1w = CT.t_s[2 * i + 1];
                         const int lz12 = e1w >> 16;
                         const double* e = RAq + (SP_HDR + (e1w & 0xffffu)) * NB;
@@ -394,6 +396,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                     int e = lane;
                     uint4 nxt;
                     nxt.x = nxt.y = nxt.z = nxt.w = 0u;
+                    if (skip & 32) e = nt;
                     if (e < nt) nxt = p4[e];
                     for (; e < nt; e += Pol::G) {
                         const uint4 tw = nxt;
@@ -451,7 +454,8 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             }
         Pol::sync();
         // ---- phase 5: digestion of the chunk, one accumulator per lane; all addressing from the shared-memory tables
-        if (CT.nterm2 > 0) {
+        if (skip & 64) {
+        } else if (CT.nterm2 > 0) {
             // term mode: (integral, density) byte-offset pairs of the accumulator, two terms per 16-byte shared load
             const char* const smB = reinterpret_cast<const char*>(sm);
             const unsigned* tptr = tab + 4 * CT.nterm2;
@@ -595,7 +599,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
         Pol::sync();
     }
     // ---- flush the shell blocks
-    for (int dn = 0; dn < nD; ++dn) {
+    for (int dn = 0; dn < nD && !(skip & 128); ++dn) {
         double* Kd = Kf + (size_t)dn * ncart * ncart;
         double* Jd = Jf + (size_t)dn * ncart * ncart;
         for (int x = lane; x < nwork; x += Pol::G) {

@@ -1737,6 +1737,24 @@ int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
 // ------------------------------------------------------------------------------------------------
 // AO -> MO / spin-orbital transformation of the dense tensor (tuna_ci.py:143-255); kernel in mo_transform.cuh
 // ------------------------------------------------------------------------------------------------
+// Spin-blocked tensor of TUNA/tuna_ci.py:564, built on the device from the resident tensor E (dimension n):
+//   G = np.kron(np.eye(2), np.kron(np.eye(2), E).T)  =>  G[I][J][K][L] = [I/n == J/n] [K/n == L/n] E[L%n][K%n][J%n][I%n]   (dimension 2n)
+// (NumPy's kron pads eye(2) to four axes, so each kron spin-blocks the LAST two axes; the .T in between reverses all four.)
+__global__ void __launch_bounds__(256) k_spin_block(const double* __restrict__ E, double* __restrict__ G, int n) {
+    const int n2 = 2 * n;
+    const size_t IJ = blockIdx.x;                       // one (I, J) plane per CTA
+    const int I = (int)(IJ / n2), J = (int)(IJ % n2);
+    double* g = G + IJ * (size_t)n2 * n2;
+    const bool on = (I / n) == (J / n);
+    const int i = I % n, j = J % n;
+    for (int kl = threadIdx.x; kl < n2 * n2; kl += blockDim.x) {
+        const int K = kl / n2, L = kl - K * n2;
+        double v = 0.0;
+        if (on && (K / n) == (L / n)) v = E[(((size_t)(L % n) * n + (K % n)) * n + j) * n + i];
+        g[kl] = v;
+    }
+}
+
 static int mo_transform_core(tuna_ctx* ctx, int n, const double* dT, int n1, const double* dC1, int n2, const double* dC2, int so_layout,
                              double* d_out) {
     const size_t N = (size_t)n, N1 = (size_t)n1, N2 = (size_t)n2;
@@ -1801,6 +1819,36 @@ int tuna_eri_transform(tuna_ctx* ctx, int n, const double* eri_host, int n1, con
         e = cudaMemcpyAsync(out_host, dOut, nout * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { ctx->err = std::string("tuna_eri_transform: ") + cudaGetErrorString(e); rc = TUNA_ERR_CUDA; }
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cleanup();
+    return rc;
+}
+
+int tuna_eri_transform_spin_blocked(tuna_ctx* ctx, int n1, const double* C1, int n2, const double* C2, int so_layout, double* out_host) {
+    if (!ctx) return TUNA_ERR_ARG;
+    if (n1 <= 0 || n2 <= 0 || !C1 || !C2 || !out_host) FAIL(TUNA_ERR_ARG, "tuna_eri_transform_spin_blocked: bad arguments");
+    if (!ctx->d_eri_sph || ctx->n_stored <= 0) FAIL(TUNA_ERR_STATE, "tuna_eri_transform_spin_blocked: no stored tensor is resident");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n_stored, N = 2 * n;
+    const size_t N4 = (size_t)N * N * N * N, nout = (size_t)n1 * n1 * n2 * n2;
+    double* dG = nullptr; double* dC = nullptr; double* dOut = nullptr;
+    int rc = dev_alloc(ctx, &dG, N4);
+    if (!rc) rc = dev_alloc(ctx, &dC, (size_t)N * (n1 + n2));
+    if (!rc) rc = dev_alloc(ctx, &dOut, nout);
+    auto cleanup = [&]() { dev_free(&dG); dev_free(&dC); dev_free(&dOut); };
+    if (rc) { cleanup(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(dC, C1, (size_t)N * n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dC + (size_t)N * n1, C2, (size_t)N * n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cleanup(); ctx->err = std::string("tuna_eri_transform_spin_blocked upload: ") + cudaGetErrorString(e); return TUNA_ERR_CUDA; }
+    k_spin_block<<<(unsigned)((size_t)N * N), 256, 0, ctx->stream>>>(ctx->d_eri_sph, dG, n);
+    ctx->launches++;
+    rc = mo_transform_core(ctx, N, dG, n1, dC, n2, dC + (size_t)N * n1, so_layout, dOut);
+    if (!rc) {
+        e = cudaMemcpyAsync(out_host, dOut, nout * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("tuna_eri_transform_spin_blocked: ") + cudaGetErrorString(e); rc = TUNA_ERR_CUDA; }
     } else {
         cudaStreamSynchronize(ctx->stream);
     }
@@ -2412,9 +2460,10 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     const size_t o_rt = add(C.t_rt.data(), C.t_rt.size() * 4), o_xy = add(C.t_xy.data(), C.t_xy.size() * 4), o_u = add(C.t_u.data(), C.t_u.size() * 4);
     const size_t o_s = add(C.t_s.data(), C.t_s.size() * 4), o_s0 = add(C.chunk_s0.data(), C.chunk_s0.size() * 4), o_p4 = add(C.p4.data(), C.p4.size() * 4);
     const size_t o_t0 = add(C.chunk_t0.data(), C.chunk_t0.size() * 4), o_ni = add(C.chunk_ni.data(), C.chunk_ni.size() * 4);
-    const size_t o_tabs = add(C.tabs.data(), C.tabs.size() * 4), o_acc = add(C.acc.data(), C.acc.size() * 4);
     const size_t o_pmap = add(C.pmap.data(), C.pmap.size() * 2), o_omap = add(C.omap.data(), C.omap.size() * 2);
     const size_t o_jp = add(C.jst_ptr.data(), C.jst_ptr.size() * 4), o_jl = add(C.jst_list.data(), C.jst_list.size() * 2), o_jf = add(C.jflush.data(), C.jflush.size() * 4);
+    const size_t o_acc = add(C.acc.data(), C.nterm2 > 0 ? 0 : C.acc.size() * 4);      // (unused in term mode)
+    const size_t o_tabs = add(C.tabs.data(), C.tabs.size() * 4);
     const size_t o_tm = add(C.terms.data(), C.terms.size() * 4), o_tp = add(C.tptr.data(), C.tptr.size() * 4);
     std::vector<unsigned char> host(total, 0);
     for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
@@ -2458,6 +2507,7 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             Shell4Job& J = jh.job;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
             J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
+            { const char* dbg = getenv("TUNA_B200_DBG_SKIP"); J.dbg_skip = dbg ? atoi(dbg) : 0; }
             std::vector<long long> prefix;
             J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
             if (J.nitems == 0) continue;
@@ -2825,18 +2875,24 @@ int tuna_fp64_peak_probe(tuna_ctx* ctx, double* tflops) {
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    // SUSTAINED rate: two warm-up launches, then back-to-back launches timed as one interval of >= 0.5 s (a 2 ms burst overstates what
+    // a second-long Fock build can reach under the power cap)
+    for (int rep = 0; rep < 2; ++rep) k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999);
+    CK(cudaStreamSynchronize(ctx->stream));
     double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
+    int nl = 64;
+    for (int round = 0; round < 4; ++round) {
         CK(cudaEventRecord(e0, ctx->stream));
-        k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999);
+        for (int rep = 0; rep < nl; ++rep) k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999);
         CK(cudaEventRecord(e1, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
-        const double tf = (double)blocks * threads * iters * 8 * 2 / (ms * 1e-3) * 1e-12;
-        if (rep > 0) best = std::max(best, tf);
+        ctx->launches += nl;
+        best = (double)nl * blocks * threads * iters * 8 * 2 / (ms * 1e-3) * 1e-12;
+        if (ms >= 500.0f) break;
+        nl = (int)std::min(4096.0, std::ceil(nl * 600.0 / std::max(ms, 1.0f)));
     }
-    ctx->launches += 5;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     dev_free(&d);
     *tflops = best;

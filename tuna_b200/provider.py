@@ -107,6 +107,76 @@ class ERIHandle:
         return getattr(self.materialise(), name)
 
 
+class SpinBlocked:
+    """Lazy stand-in for the spin-blocking idiom of the reference's post-HF drivers (TUNA/tuna_ci.py:564):
+
+        ERI_spin_block = np.kron(np.eye(2), np.kron(np.eye(2), ERI_AO).T)
+
+    `ERIHandle.__array_function__` turns the inner `np.kron(np.eye(2), handle)` into SpinBlocked(handle, 1), `.T` into stage 2 and the
+    outer kron into stage 3; `transform_ERI_AO_to_SO` recognises stage 3 and builds the 16 n^4 tensor on the device from the resident
+    one.  Anything else that touches the object gets the real ndarray, computed by NumPy exactly as the reference does."""
+
+    __array_priority__ = 100.0
+    ndim = 4
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, handle, stage):
+        self.handle, self.stage = handle, stage
+        self._host = None
+
+    @property
+    def shape(self):
+        n = self.handle.n
+        return {1: (n, n, 2 * n, 2 * n), 2: (2 * n, 2 * n, n, n), 3: (2 * n,) * 4}[self.stage]
+
+    @property
+    def T(self):
+        return SpinBlocked(self.handle, 2) if self.stage == 1 else self.materialise().T
+
+    def materialise(self):
+        if self._host is None:
+            a = np.kron(np.eye(2), self.handle.materialise())
+            if self.stage >= 2:
+                a = a.T
+            if self.stage == 3:
+                a = np.kron(np.eye(2), a)
+            self._host = a
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialise()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func is np.kron and len(args) == 2 and args[1] is self and self.stage == 2 and _is_eye2(args[0]):
+            return SpinBlocked(self.handle, 3)
+        return func(*[a.materialise() if isinstance(a, (SpinBlocked, ERIHandle)) else a for a in args], **kwargs)
+
+    def __getitem__(self, idx):
+        return self.materialise()[idx]
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialise(), name)
+
+
+def _is_eye2(a):
+    return isinstance(a, np.ndarray) and a.shape == (2, 2) and np.array_equal(a, np.eye(2))
+
+
+def _handle_array_function(self, func, types, args, kwargs):
+    """NumPy dispatch on ERIHandle arguments: the spin-blocking kron stays lazy (device-resident stored tensors only); every other
+    function sees the materialised ndarray."""
+    if (func is np.kron and len(args) == 2 and args[1] is self and _is_eye2(args[0]) and self.mode == "stored" and self.basis_kind == "sph"
+            and self.ctx.n_stored == self.n):
+        return SpinBlocked(self, 1)
+    return func(*[a.materialise() if isinstance(a, (SpinBlocked, ERIHandle)) else a for a in args], **kwargs)
+
+
+ERIHandle.__array_function__ = _handle_array_function
+
+
 def _binary(op):
     def f(self, other):
         return getattr(self.materialise(), op)(np.asarray(other) if isinstance(other, ERIHandle) else other)
@@ -305,7 +375,9 @@ def _transform(ERI_AO, C_1, C_2, so_layout, calculation, silent):
         log("\n Transforming integrals on the device (4 steps)... ", calculation, 1, end="", silent=silent)
     C_1 = np.asarray(C_1, dtype=np.float64)
     C_2 = np.asarray(C_2, dtype=np.float64)
-    if isinstance(ERI_AO, ERIHandle) and ERI_AO.mode == "stored" and ERI_AO.basis_kind == "sph" and ERI_AO.ctx.n_stored == ERI_AO.n:
+    if isinstance(ERI_AO, SpinBlocked) and ERI_AO.stage == 3 and ERI_AO.handle.ctx.n_stored == ERI_AO.handle.n and hasattr(ERI_AO.handle.ctx, "eri_transform_spin_blocked"):
+        out = ERI_AO.handle.ctx.eri_transform_spin_blocked(C_1, C_2, so_layout)     # spin-blocked on the device from the resident tensor
+    elif isinstance(ERI_AO, ERIHandle) and ERI_AO.mode == "stored" and ERI_AO.basis_kind == "sph" and ERI_AO.ctx.n_stored == ERI_AO.n:
         out = ERI_AO.ctx.eri_transform(C_1, C_2, so_layout)                     # the tensor is already resident
     else:
         arr = np.asarray(ERI_AO, dtype=np.float64)
