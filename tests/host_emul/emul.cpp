@@ -239,7 +239,7 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
             std::vector<unsigned> tab(CH.tab_words + 4);
             int tab_chunk = -1;
             Quartet4 hq[4];
-            for (int q = 0; q < 4; ++q) hq[q] = Quartet4{0, 0, 0, 0, 0.0};
+            for (int q = 0; q < 4; ++q) { hq[q] = Quartet4(); hq[q].active = 0; }
             int nb = 0;
             auto run_batch = [&]() {
                 if (nb == 0) return;
@@ -259,7 +259,11 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
                 if (S.pairA[AB] == S.pairB[AB]) w *= 0.5;
                 if (S.pairA[CD] == S.pairB[CD]) w *= 0.5;
                 if (AB == CD) w *= 0.5;
-                hq[nb] = Quartet4{1, AB, CD, 0, w};
+                Quartet4 h;
+                h.active = 1; h.shA = S.pairA[AB]; h.shB = S.pairB[AB]; h.shC = S.pairA[CD]; h.shD = S.pairB[CD]; h.pad = 0; h.w = w;
+                h.recA = S.pair_rec[AB]; h.recC = S.pair_rec[CD];
+                h.pA = S.rec[h.recA]; h.zA = S.rec[h.recA + 1]; h.pC = S.rec[h.recC]; h.zC = S.rec[h.recC + 1];
+                hq[nb] = h;
                 if (++nb == NBATCH) run_batch();
             }
             run_batch();

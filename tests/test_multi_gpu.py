@@ -22,7 +22,13 @@ def _run(case, world, port):
            os.path.join(ROOT, "tests", "multi_gpu_case.py"), case]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
-    assert r.returncode == 0 and lines, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    if r.returncode != 0 or not lines:
+        err = r.stderr
+        k = err.find("Traceback")
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"multi_gpu_{case}_{world}.err"), "w") as f:
+            f.write(r.stdout + "\n---- stderr ----\n" + err)
+        raise AssertionError(f"worker failed (rc {r.returncode}): " + (err[k:k + 3000] if k >= 0 else err[-3000:]))
     return json.loads(lines[-1][len("RESULT "):])
 
 

@@ -58,6 +58,11 @@ struct Class4Dev {
     // pairs with (zero row, entry 0)); tptr[w] = first pair | pairs << 20.  nterm2 = 0 selects the separable loops above.
     int nterm2;
     const unsigned* terms; const unsigned* tptr;
+    // term mode flushes every accumulator straight from registers (a single-chunk class completes an accumulator in one pass): no
+    // Out array, no flush phase.  wfl[w] = first | count << 16 | (1u << 31 for a Coulomb target), wlist = (row | col << 8) entries: one
+    // entry for a K accumulator, the component pairs of the pair function for a J accumulator.
+    const unsigned* wfl; const unsigned short* wlist; int nwlist;
+    int nout_sm;                                  // accumulators kept in shared memory: nwork (separable mode) or 0 (term mode)
     // work list: acc[2 w] = kind | g << 4 | u << 8 | v << 16 for K (kind 0..3), kind | pc << 4 for J (4 = bra pair function,
     // 5 = ket pair function); acc[2 w + 1] = pair-function index for J.  Sorted by descending work; Out[] is in this order.
     const unsigned* acc;
@@ -101,7 +106,7 @@ inline void shell4_job_layout(Shell4Job& J, int nD) {
     J.oS = o; o += J.ct.ssize + 2;                    // + slack read by the second lane of a half-filled tile
     J.oIt = o; o += J.ct.itmax + J.ct.zrow;           // integral slots, then the zero row absent bra rows point to
     J.oP = o; o += nD * J.ct.nstage;
-    J.oOut = o; o += nD * J.ct.nwork;
+    J.oOut = o; o += nD * J.ct.nout_sm;
     J.oRecA = o; o += sp_rec_size(J.La, J.Lb);
     J.oRecC = o; o += sp_rec_size(J.Lc, J.Ld);
     int lmax = J.La > J.Lc ? J.La : J.Lc;
@@ -124,7 +129,9 @@ TUNA_HD void shell4_load_tables(const Class4Dev& CT, int ch, unsigned* tab, int 
             tab[2 * i] = ((unsigned)oIt + (t & 0xffffu)) * (unsigned)(NB * 8);
             tab[2 * i + 1] = ((unsigned)oP + (t >> 16)) * (unsigned)(NB * 8);
         }
-        for (int i = tid; i < CT.nwork; i += nthreads) tab[4 * CT.nterm2 + i] = CT.tptr[i];
+        for (int i = tid; i < CT.nwork; i += nthreads) { tab[4 * CT.nterm2 + i] = CT.tptr[i]; tab[4 * CT.nterm2 + CT.nwork + i] = CT.wfl[i]; }
+        unsigned short* wl = reinterpret_cast<unsigned short*>(tab + 4 * CT.nterm2 + 2 * CT.nwork);
+        for (int i = tid; i < CT.nwlist; i += nthreads) wl[i] = CT.wlist[i];
         return;
     }
     const unsigned* src = CT.tabs + (size_t)ch * CT.ntab;
@@ -178,8 +185,10 @@ TUNA_HD void assemble4(const double* xyx, const double* xyy, const double* sp0, 
 
 // Header of one quartet of a batch, decoded once (by one lane) before the group starts on it.
 struct Quartet4 {
-    int active, ab, cd, pad;
-    double w;
+    int active, shA, shB, shC, shD, pad;      // the four shells (A, B of the bra pair, C, D of the ket pair)
+    double w;                                 // degeneracy weight
+    long long recA, recC;                     // offsets of the pairs' first primitive records in ShellData::rec
+    double pA, zA, pC, zC;                    // exponent sum and centre of the FIRST primitive pair of bra and ket (Boys argument without a memory round trip)
 };
 
 // NB shell quartets of one class processed together by one group of Pol::G lanes.  `tab` is the CTA's table area (shared memory on
@@ -210,11 +219,11 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
         act[q] = hq[q].active != 0;
-        const int ab = act[q] ? hq[q].ab : hq[qa].ab, cd = act[q] ? hq[q].cd : hq[qa].cd;
-        w[q] = act[q] ? hq[q].w : 0.0;
-        recA[q] = D.rec + D.pair_rec[ab]; recC[q] = D.rec + D.pair_rec[cd];
+        const Quartet4& h = act[q] ? hq[q] : hq[qa];      // an inactive slot runs on the data of an active one with weight zero
+        w[q] = act[q] ? h.w : 0.0;
+        recA[q] = D.rec + h.recA; recC[q] = D.rec + h.recC;
         int* ao = aoq + q * 4 * aos;
-        const int shA = D.pairA[ab], shB = D.pairB[ab], shC = D.pairA[cd], shD = D.pairB[cd];
+        const int shA = h.shA, shB = h.shB, shC = h.shC, shD = h.shD;
         for (int x = lane; x < aos; x += Pol::G) {
             ao[x] = D.sh_ao[shA * SH_NCMAX + x]; ao[aos + x] = D.sh_ao[shB * SH_NCMAX + x];
             ao[2 * aos + x] = D.sh_ao[shC * SH_NCMAX + x]; ao[3 * aos + x] = D.sh_ao[shD * SH_NCMAX + x];
@@ -259,7 +268,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             qst<NB>(Pd + (CT.nkst + x) * NB, v);
         }
     }
-    for (int x = lane; x < nD * nwork * NB; x += Pol::G) Outq[x] = 0.0;
+    for (int x = lane; x < nD * CT.nout_sm * NB; x += Pol::G) Outq[x] = 0.0;
     for (int x = lane; x < CT.zrow * NB; x += Pol::G) Itq[CT.itmax * NB + x] = 0.0;
     const int recAsz = sp_rec_size(La, Lb), recCsz = sp_rec_size(Lc, Ld);
     const int oExA = SP_HDR + sp_ez_size(La, Lb), oExC = SP_HDR + sp_ez_size(Lc, Ld);
@@ -290,9 +299,13 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                     if (m <= Ltot) {
                         const double* rA = recA[0] + ia * recAsz;
                         const double* rC = recC[0] + ic * recCsz;
+                        int qs = act[0] ? 0 : qa;
 #pragma unroll
-                        for (int k = 1; k < NB; ++k) if (q == k) { rA = recA[k] + ia * recAsz; rC = recC[k] + ic * recCsz; }
-                        const double p = rA[0], qq = rC[0], pq = p + qq, rho = p * qq / pq, PQz = rA[1] - rC[1];
+                        for (int k = 1; k < NB; ++k) if (q == k) { rA = recA[k] + ia * recAsz; rC = recC[k] + ic * recCsz; qs = act[k] ? k : qa; }
+                        double p, qq, PQz;
+                        if (ia == 0 && ic == 0) { p = hq[qs].pA; qq = hq[qs].pC; PQz = hq[qs].zA - hq[qs].zC; }
+                        else { p = rA[0]; qq = rC[0]; PQz = rA[1] - rC[1]; }
+                        const double pq = p + qq, rho = p * qq / pq;
                         const double f = boys_single(D.boys, m, rho * PQz * PQz);
                         double s = 1.0, z = 1.0;
                         for (int k = 0; k < m; ++k) { s *= -2.0 * rho; z *= PQz; }
@@ -459,11 +472,14 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             // term mode: (integral, density) byte-offset pairs of the accumulator, two terms per 16-byte shared load
             const char* const smB = reinterpret_cast<const char*>(sm);
             const unsigned* tptr = tab + 4 * CT.nterm2;
+            const unsigned* wfl = tptr + nwork;
+            const unsigned short* wlist = reinterpret_cast<const unsigned short*>(wfl + nwork);
             for (int wi = lane; wi < nwork; wi += Pol::G) {
                 const unsigned tp = tptr[wi];
                 const unsigned n2 = tp >> 20;
                 if (n2 == 0) continue;
                 const uint4* tl = reinterpret_cast<const uint4*>(tab) + (tp & 0xfffffu);
+                const unsigned fl = wfl[wi];
                 for (int dn = 0; dn < nD; ++dn) {
                     const char* const pB = smB + dn * nstage * (NB * 8);
                     double s0[NB], s1[NB];
@@ -489,10 +505,20 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
 #pragma unroll
                         for (int q = 0; q < NB; ++q) { s0[q] = fma(i0.v[q], p0.v[q], s0[q]); s1[q] = fma(i1.v[q], p1.v[q], s1[q]); }
                     }
-                    QVec<NB> out = qld<NB>(Outq + (dn * nwork + wi) * NB);
+                    if (skip & 128) continue;
+                    double* const M = ((fl >> 31) ? Jf : Kf) + (size_t)dn * ncart * ncart;
+                    const unsigned f0 = fl & 0xffffu, f1 = f0 + ((fl >> 16) & 0x7fffu);
+                    for (unsigned e = f0; e < f1; ++e) {
+                        const unsigned m = wlist[e];
+                        const int ri = ((m >> 5) & 3) * aos + (m & 31), ci = ((m >> 13) & 3) * aos + ((m >> 8) & 31);
 #pragma unroll
-                    for (int q = 0; q < NB; ++q) out.v[q] += s0[q] + s1[q];
-                    qst<NB>(Outq + (dn * nwork + wi) * NB, out);
+                        for (int q = 0; q < NB; ++q) {
+                            const double v = s0[q] + s1[q];
+                            if (!act[q] || v == 0.0) continue;
+                            const int* ao = aoq + q * 4 * aos;
+                            Pol::atomic_add(M + ao[ri] * ncart + ao[ci], v);
+                        }
+                    }
                 }
             }
         } else {
@@ -598,8 +624,8 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
         }
         Pol::sync();
     }
-    // ---- flush the shell blocks
-    for (int dn = 0; dn < nD && !(skip & 128); ++dn) {
+    // ---- flush the shell blocks (separable mode; term mode has flushed from registers)
+    for (int dn = 0; dn < nD && !(skip & 128) && CT.nterm2 == 0; ++dn) {
         double* Kd = Kf + (size_t)dn * ncart * ncart;
         double* Jd = Jf + (size_t)dn * ncart * ncart;
         for (int x = lane; x < nwork; x += Pol::G) {

@@ -24,7 +24,8 @@ struct Class4Host {
     unsigned plan[64];
     int nterm2 = 0;                        // > 0: term mode (digestion lists in shared memory), pairs of terms
     int tab_words = 0;                     // words of the CTA's table area in either mode
-    std::vector<unsigned short> pmap, omap, jst_list;
+    std::vector<unsigned short> pmap, omap, jst_list, wlist;
+    std::vector<unsigned> wfl;
     long long allowed = 0;                 // parity-allowed component quartets = integrals per shell quartet
     long long nterms = 0;                  // digestion terms (table statistics)
     bool terms_possible(int term_max) const { return nterms + nwork <= term_max && itmax < 65535 && nstage < 65535; }
@@ -415,7 +416,16 @@ inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int L
             C.terms.insert(C.terms.end(), lists[w].begin(), lists[w].end());
         }
         C.nterm2 = (int)C.terms.size() / 2;
-        C.tab_words = 4 * C.nterm2 + C.nwork;
+        // flush lists: one target per K accumulator, the component pairs of the pair function for a J accumulator
+        std::vector<std::vector<unsigned short>> fls(C.nwork);
+        for (int w = 0; w < C.nwork; ++w) if (C.omap[w] != 0xffff) fls[w].push_back(C.omap[w]);
+        for (int a = 0; a < nc[0]; ++a) for (int b = 0; b < nc[1]; ++b) fls[pos_jb[bidx[a * nc[1] + b]]].push_back(rc(0, a, 1, b));
+        for (int c = 0; c < nc[2]; ++c) for (int d = 0; d < nc[3]; ++d) fls[pos_jg[gidx[c * nc[3] + d]]].push_back(rc(2, c, 3, d));
+        for (int w = 0; w < C.nwork; ++w) {
+            C.wfl.push_back((unsigned)C.wlist.size() | (unsigned)fls[w].size() << 16 | (C.omap[w] == 0xffff ? 1u << 31 : 0u));
+            C.wlist.insert(C.wlist.end(), fls[w].begin(), fls[w].end());
+        }
+        C.tab_words = 4 * C.nterm2 + 2 * C.nwork + ((int)C.wlist.size() + 1) / 2;
     }
 
     // ---- statistics ------------------------------------------------------------------------------------------------------------
@@ -457,6 +467,7 @@ inline Class4Dev class4_view(const Class4Host& C, PtrOf ptr) {
     }
     for (int i = 0; i < 64; ++i) V.plan[i] = C.plan[i];
     V.nterm2 = C.nterm2; V.terms = ptr(C.terms); V.tptr = ptr(C.tptr);
+    V.wfl = ptr(C.wfl); V.wlist = ptr(C.wlist); V.nwlist = (int)C.wlist.size(); V.nout_sm = C.nterm2 > 0 ? 0 : C.nwork;
     V.acc = ptr(C.acc); V.pmap = ptr(C.pmap); V.omap = ptr(C.omap);
     V.jst_ptr = ptr(C.jst_ptr); V.jst_list = ptr(C.jst_list); V.jflush = ptr(C.jflush); V.njfl = (int)C.jflush.size();
     return V;

@@ -52,6 +52,7 @@ struct tuna_ctx {
     // basis + pair table
     HostBasis hb;
     PairTable pt;
+    bool pairs_ready = false;         // the AO-pair table is built on first use by an ERI / J/K call (one-electron integrals do not need it)
     int ncart = 0;
     int* d_pi = nullptr; int* d_pj = nullptr; int* d_cls = nullptr; int* d_npp = nullptr;
     int64_t* d_ppoff = nullptr;
@@ -160,8 +161,27 @@ static void drop_graphs(tuna_ctx* ctx) {
 
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 
+// No exception may cross the C ABI (include/tuna_b200.h): every entry point that touches std containers is a function-try-block.
+#define TUNA_CATCH                                                                                                     \
+    catch (const std::bad_alloc&) { if (ctx) ctx->err = "host allocation failed"; return TUNA_ERR_NOMEM; }             \
+    catch (const std::exception& e_) { if (ctx) ctx->err = std::string("internal error: ") + e_.what(); return TUNA_ERR_STATE; } \
+    catch (...) { if (ctx) ctx->err = "internal error"; return TUNA_ERR_STATE; }
+
 static int check_pair_symmetry(tuna_ctx* ctx);
 static int shell_fill(tuna_ctx* ctx);
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is PER DEVICE (a process may hold contexts on several GPUs), so the
+// "already done" flag is a bit per device ordinal, one flag word per kernel instantiation.
+template <auto Kernel>
+static cudaError_t opt_in_smem(const tuna_ctx* ctx) {
+    static unsigned long long done = 0;
+    const unsigned long long bit = 1ull << (ctx->device & 63);
+    if (done & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) done |= bit;
+    return e;
+}
+
 
 template <typename T>
 static int dev_alloc(tuna_ctx* ctx, T** p, size_t count) {
@@ -951,8 +971,8 @@ __global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 1
 #ifndef TUNA_SHELL4_REGS
 #define TUNA_SHELL4_REGS 64
 #endif
-template <int GG, int NB>
-__global__ void __launch_bounds__((GG > 128) ? GG : 128, 65536 / (((GG > 128) ? GG : 128) * TUNA_SHELL4_REGS))
+template <int GG, int NB, int REGS = TUNA_SHELL4_REGS>
+__global__ void __launch_bounds__((GG > 128) ? GG : 128, 65536 / (((GG > 128) ? GG : 128) * REGS))
 k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
              double tau, const unsigned long long* scalars, double* evaluated, int rank, int nranks, int tab_off, int hdr_off) {
     extern __shared__ double smem_all[];
@@ -982,15 +1002,20 @@ k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, co
         for (int k = threadIdx.x; k < CH; k += blockDim.x) {
             const long long item = first + k;
             Quartet4 h;
-            h.active = 0; h.ab = 0; h.cd = 0; h.pad = 0; h.w = 0.0;
+            h.active = 0; h.shA = h.shB = h.shC = h.shD = 0; h.pad = 0; h.w = 0.0; h.recA = h.recC = 0; h.pA = h.pC = 1.0; h.zA = h.zC = 0.0;
             if (item < J.nitems) {
                 int ib = s_ib0;
                 while (J.item_prefix[ib + 1] <= item) ++ib;
-                h.ab = J.bra_list[ib]; h.cd = J.ket_list[(int)(item - J.item_prefix[ib])];
-                h.active = !(tau > 0.0 && D.pairQ[h.ab] * D.pairQ[h.cd] * dmax < tau);
-                const bool ab = D.pairA[h.ab] == D.pairB[h.ab], cd = D.pairA[h.cd] == D.pairB[h.cd], dg = h.ab == h.cd;
+                const int pab = J.bra_list[ib], pcd = J.ket_list[(int)(item - J.item_prefix[ib])];
+                h.active = !(tau > 0.0 && D.pairQ[pab] * D.pairQ[pcd] * dmax < tau);
+                h.shA = D.pairA[pab]; h.shB = D.pairB[pab]; h.shC = D.pairA[pcd]; h.shD = D.pairB[pcd];
+                const bool ab = h.shA == h.shB, cd = h.shC == h.shD, dg = pab == pcd;
                 h.w = (ab ? 0.5 : 1.0) * (cd ? 0.5 : 1.0) * (dg ? 0.5 : 1.0);
-                if (h.active) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+                h.recA = D.pair_rec[pab]; h.recC = D.pair_rec[pcd];
+                if (h.active) {
+                    h.pA = D.rec[h.recA]; h.zA = D.rec[h.recA + 1]; h.pC = D.rec[h.recC]; h.zC = D.rec[h.recC + 1];
+                    done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+                }
             }
             hdr[k] = h;
         }
@@ -1147,9 +1172,39 @@ static int ensure_mats(tuna_ctx* ctx, int nD, int n, int ncart) {
     return TUNA_OK;
 }
 
-static int ensure_schwarz(tuna_ctx* ctx) {
-    if (ctx->d_Q) return TUNA_OK;
+// The AO-pair table (host build with OpenMP + one upload) on first use: ERI fill, Schwarz factors, direct J/K, work counters.
+static int ensure_pairs(tuna_ctx* ctx) {
+    if (ctx->pairs_ready) return TUNA_OK;
+    if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "call tuna_set_basis first");
+    try {
+        build_pair_table(ctx->hb, ctx->pt);
+    } catch (const std::bad_alloc&) {
+        FAIL(TUNA_ERR_NOMEM, "host allocation failed while building the pair table");
+    }
+    const PairTable& T = ctx->pt;
     int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_pi, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_pj, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_cls, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_npp, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ppoff, (size_t)T.npair))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_pp, T.pp.size()))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_pi, T.pi.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pj, T.pj.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_cls, T.cls.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_npp, T.npp.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ppoff, T.ppoff.data(), T.npair * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pp, T.pp.data(), T.pp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    count_work(ctx);
+    ctx->pairs_ready = true;
+    return TUNA_OK;
+}
+
+static int ensure_schwarz(tuna_ctx* ctx) {
+    int rc;
+    if ((rc = ensure_pairs(ctx))) return rc;
+    if (ctx->d_Q) return TUNA_OK;
     if ((rc = dev_alloc(ctx, &ctx->d_Q, (size_t)ctx->pt.npair))) return rc;
     k_schwarz<<<grid_for(ctx, ctx->pt.npair, 128, 16), 128, 0, ctx->stream>>>(table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->pt.npair);
     ctx->launches++;
@@ -1243,7 +1298,7 @@ int tuna_set_stream(tuna_ctx* ctx, void* s) {
 }
 
 int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int32_t* lmn, const int32_t* nprim, const int64_t* prim_offset,
-                   const double* exps, const double* coef_eff) {
+                   const double* exps, const double* coef_eff) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (ncart <= 0 || !origins_z || !lmn || !nprim || !prim_offset || !exps || !coef_eff) FAIL(TUNA_ERR_ARG, "tuna_set_basis: null or empty basis");
     CK(cudaSetDevice(ctx->device));
@@ -1268,32 +1323,18 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
         B.ceff.assign(coef_eff, coef_eff + total);
         for (int64_t k = 0; k < total; ++k)
             if (!(B.exps[k] > 0.0)) FAIL(TUNA_ERR_ARG, "tuna_set_basis: non-positive exponent");
-        build_pair_table(B, ctx->pt);
     } catch (const std::bad_alloc&) {
-        FAIL(TUNA_ERR_NOMEM, "host allocation failed while building the pair table");
+        FAIL(TUNA_ERR_NOMEM, "host allocation failed while copying the basis");
     }
     ctx->ncart = ncart;
-    const PairTable& T = ctx->pt;
-    int rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_pi, (size_t)T.npair))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_pj, (size_t)T.npair))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_cls, (size_t)T.npair))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_npp, (size_t)T.npair))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_ppoff, (size_t)T.npair))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_pp, T.pp.size()))) return rc;
-    CK(cudaMemcpyAsync(ctx->d_pi, T.pi.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_pj, T.pj.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_cls, T.cls.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_npp, T.npp.data(), T.npair * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_ppoff, T.ppoff.data(), T.npair * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_pp, T.pp.data(), T.pp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pairs_ready = false;
+    ctx->pt = PairTable();
+    ctx->n_unique = ctx->n_surviving = ctx->n_primq = 0;
     dev_free(&ctx->d_Q);
     dev_free(&ctx->d_eri_cart);
     dev_free(&ctx->d_eri_sph);
     ctx->n_stored = 0;
     ctx->nbf = 0;
-    count_work(ctx);
     build_shell_tab(ctx->stab);
     ctx->shell_ready = false;
     ctx->jobs.clear();
@@ -1304,9 +1345,9 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     const char* gen = getenv("TUNA_B200_ENGINE");
     ctx->engine_gen = (gen && atoi(gen) == 2) ? 2 : 4;
     return TUNA_OK;
-}
+} TUNA_CATCH
 
-int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U) {
+int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_set_transform: call tuna_set_basis first");
     if (nbf <= 0 || !U) FAIL(TUNA_ERR_ARG, "tuna_set_transform: bad arguments");
@@ -1335,14 +1376,15 @@ int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U) {
         for (int a = 0; a < nc; ++a)
             if (u[(size_t)p * nc + a] != (p == a ? 1.0 : 0.0)) { ctx->U_identity = false; break; }
     return TUNA_OK;
-}
+} TUNA_CATCH
 
-int tuna_eri_fill_cart(tuna_ctx* ctx) {
+int tuna_eri_fill_cart(tuna_ctx* ctx) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_eri_fill_cart: call tuna_set_basis first");
     CK(cudaSetDevice(ctx->device));
     const size_t n = ctx->ncart, count = n * n * n * n;
     int rc;
+    if ((rc = ensure_pairs(ctx))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_eri_cart, count))) return rc;
     CK(cudaMemsetAsync(ctx->d_eri_cart, 0, count * sizeof(double), ctx->stream));
     // Shell-quartet engine in fill mode (Boys / R / convolution tables shared by all components of a shell quartet) when the basis
@@ -1363,9 +1405,9 @@ int tuna_eri_fill_cart(tuna_ctx* ctx) {
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[0][1], ctx->stream));
     return TUNA_OK;
-}
+} TUNA_CATCH
 
-int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart) {
+int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (!ctx->d_eri_cart) FAIL(TUNA_ERR_STATE, "tuna_eri_cart_to_sph: no Cartesian tensor resident (call tuna_eri_fill_cart)");
     if (ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_eri_cart_to_sph: call tuna_set_transform first");
@@ -1407,9 +1449,9 @@ int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart) {
     if (rc) { dev_free(&ctx->d_eri_sph); return rc; }
     ctx->n_stored = (int)nb;
     return check_pair_symmetry(ctx);
-}
+} TUNA_CATCH
 
-int tuna_eri_download(tuna_ctx* ctx, int which, double* host_out) {
+int tuna_eri_download(tuna_ctx* ctx, int which, double* host_out) try {
     if (!ctx || !host_out) return TUNA_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const double* src = which == 0 ? ctx->d_eri_cart : ctx->d_eri_sph;
@@ -1418,9 +1460,9 @@ int tuna_eri_download(tuna_ctx* ctx, int which, double* host_out) {
     CK(cudaMemcpyAsync(host_out, src, n * n * n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return TUNA_OK;
-}
+} TUNA_CATCH
 
-int tuna_eri_upload(tuna_ctx* ctx, int n, const double* host_in) {
+int tuna_eri_upload(tuna_ctx* ctx, int n, const double* host_in) try {
     if (!ctx || !host_in || n <= 0) return TUNA_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const size_t count = (size_t)n * n * n * n;
@@ -1431,9 +1473,9 @@ int tuna_eri_upload(tuna_ctx* ctx, int n, const double* host_in) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_stored = n;
     return check_pair_symmetry(ctx);
-}
+} TUNA_CATCH
 
-int tuna_eri_single(tuna_ctx* ctx, int i, int j, int k, int l, double* out) {
+int tuna_eri_single(tuna_ctx* ctx, int i, int j, int k, int l, double* out) try {
     if (!ctx || !out) return TUNA_ERR_ARG;
     const int n = ctx->ncart;
     if (n == 0) FAIL(TUNA_ERR_STATE, "tuna_eri_single: call tuna_set_basis first");
@@ -1463,9 +1505,9 @@ int tuna_eri_single(tuna_ctx* ctx, int i, int j, int k, int l, double* out) {
     CK(cudaStreamSynchronize(ctx->stream));
     dev_free(&d);
     return TUNA_OK;
-}
+} TUNA_CATCH
 
-int tuna_schwarz(tuna_ctx* ctx, double* host_out) {
+int tuna_schwarz(tuna_ctx* ctx, double* host_out) try {
     if (!ctx || !host_out) return TUNA_ERR_ARG;
     if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_schwarz: call tuna_set_basis first");
     CK(cudaSetDevice(ctx->device));
@@ -1480,7 +1522,7 @@ int tuna_schwarz(tuna_ctx* ctx, double* host_out) {
         host_out[(size_t)ctx->pt.pj[a] * n + ctx->pt.pi[a]] = q[a];
     }
     return TUNA_OK;
-}
+} TUNA_CATCH
 
 }  // extern "C"
 
@@ -1506,12 +1548,7 @@ static int check_pair_symmetry(tuna_ctx* ctx) {
 template <int ND, int MT>
 static cudaError_t launch_jk_sym(tuna_ctx* ctx, const double* P, double* Jpart, double* Kslot, int* Krow, int n, int r, int nstage, int kslots,
                                  int ncons, int grid, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_jk_stored_sym<ND, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = opt_in_smem<k_jk_stored_sym<ND, MT>>(ctx); e != cudaSuccess) return e;
     k_jk_stored_sym<ND, MT><<<grid, ncons + 32, smem, ctx->stream>>>(ctx->d_eri_sph, P, Jpart, Kslot, Krow, n, r, nstage, kslots, ncons);
     return cudaGetLastError();
 }
@@ -1583,20 +1620,16 @@ static int jk_stored_sym(tuna_ctx* ctx, int nD, const double* dP, double* dJ, do
 template <int ND>
 static cudaError_t launch_jk_tma(tuna_ctx* ctx, const double* P, double* J, double* Kslot, int* Krow, int n, int r, int R, int q, int nstage,
                                  int kslots, int grid, int threads, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_jk_stored_tma<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = opt_in_smem<k_jk_stored_tma<ND>>(ctx); e != cudaSuccess) return e;
     k_jk_stored_tma<ND><<<grid, threads, smem, ctx->stream>>>(ctx->d_eri_sph, P, J, Kslot, Krow, n, r, R, q, nstage, kslots);
     return cudaGetLastError();
 }
 
-extern "C" int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK) {
+extern "C" int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (!ctx->d_eri_sph || ctx->n_stored == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_stored: no stored tensor resident");
     if (nD <= 0 || !dP) FAIL(TUNA_ERR_ARG, "tuna_jk_stored: bad arguments");
+    CK(cudaSetDevice(ctx->device));
     const int n = ctx->n_stored;
     if (n > 1024) FAIL(TUNA_ERR_ARG, "tuna_jk_stored: stored mode supports n <= 1024");
     int rc;
@@ -1697,11 +1730,11 @@ extern "C" int tuna_jk_stored_dev(tuna_ctx* ctx, int nD, const double* dP, doubl
     }
     CK(cudaEventRecord(ctx->ev[2][1], ctx->stream));
     return TUNA_OK;
-}
+} TUNA_CATCH
 
 extern "C" {
 
-int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K) {
+int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (!ctx->d_eri_sph || ctx->n_stored == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_stored: no stored tensor resident");
     if (nD <= 0 || !P) FAIL(TUNA_ERR_ARG, "tuna_jk_stored: bad arguments");
@@ -1722,7 +1755,7 @@ int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K)
     if (J) std::memcpy(J, hJ, bytes);
     if (K) std::memcpy(K, hK, bytes);
     return TUNA_OK;
-}
+} TUNA_CATCH
 
 int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
     if (!ctx) return TUNA_ERR_ARG;
@@ -1783,7 +1816,7 @@ static int mo_transform_core(tuna_ctx* ctx, int n, const double* dT, int n1, con
 extern "C" {
 
 int tuna_eri_transform_dev(tuna_ctx* ctx, int n, const double* dT, int n1, const double* dC1, int n2, const double* dC2, int so_layout,
-                           double* d_out) {
+                           double* d_out) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (n <= 0 || n1 <= 0 || n2 <= 0 || !dC1 || !dC2 || !d_out) FAIL(TUNA_ERR_ARG, "tuna_eri_transform: bad arguments");
     CK(cudaSetDevice(ctx->device));
@@ -1792,10 +1825,10 @@ int tuna_eri_transform_dev(tuna_ctx* ctx, int n, const double* dT, int n1, const
         dT = ctx->d_eri_sph;
     }
     return mo_transform_core(ctx, n, dT, n1, dC1, n2, dC2, so_layout, d_out);
-}
+} TUNA_CATCH
 
 int tuna_eri_transform(tuna_ctx* ctx, int n, const double* eri_host, int n1, const double* C1, int n2, const double* C2, int so_layout,
-                       double* out_host) {
+                       double* out_host) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (n <= 0 || n1 <= 0 || n2 <= 0 || !C1 || !C2 || !out_host) FAIL(TUNA_ERR_ARG, "tuna_eri_transform: bad arguments");
     CK(cudaSetDevice(ctx->device));
@@ -1824,9 +1857,9 @@ int tuna_eri_transform(tuna_ctx* ctx, int n, const double* eri_host, int n1, con
     }
     cleanup();
     return rc;
-}
+} TUNA_CATCH
 
-int tuna_eri_transform_spin_blocked(tuna_ctx* ctx, int n1, const double* C1, int n2, const double* C2, int so_layout, double* out_host) {
+int tuna_eri_transform_spin_blocked(tuna_ctx* ctx, int n1, const double* C1, int n2, const double* C2, int so_layout, double* out_host) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (n1 <= 0 || n2 <= 0 || !C1 || !C2 || !out_host) FAIL(TUNA_ERR_ARG, "tuna_eri_transform_spin_blocked: bad arguments");
     if (!ctx->d_eri_sph || ctx->n_stored <= 0) FAIL(TUNA_ERR_STATE, "tuna_eri_transform_spin_blocked: no stored tensor is resident");
@@ -1854,7 +1887,7 @@ int tuna_eri_transform_spin_blocked(tuna_ctx* ctx, int n1, const double* C1, int
     }
     cleanup();
     return rc;
-}
+} TUNA_CATCH
 
 }  // extern "C"
 
@@ -1925,7 +1958,7 @@ __global__ void __launch_bounds__(128) k_cross_overlap(BasisDev A, BasisDev B, d
 extern "C" {
 
 int tuna_one_electron(tuna_ctx* ctx, int n_atoms, const double* atom_z, const double* atom_charge, const double* dipole_origin, double* S, double* T,
-                      double* V, double* D, double* Q) {
+                      double* V, double* D, double* Q) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_one_electron: call tuna_set_basis first");
     if (n_atoms <= 0 || !atom_z || !atom_charge || !dipole_origin || !S || !T || !V || !D || !Q) FAIL(TUNA_ERR_ARG, "tuna_one_electron: bad arguments");
@@ -1968,11 +2001,11 @@ int tuna_one_electron(tuna_ctx* ctx, int n_atoms, const double* atom_z, const do
     std::memcpy(D, host.data() + 3 * nn, 3 * nn * sizeof(double));
     std::memcpy(Q, host.data() + 6 * nn, 3 * nn * sizeof(double));
     return TUNA_OK;
-}
+} TUNA_CATCH
 
 int tuna_cross_overlap(tuna_ctx* ctx, int n1, const double* oz1, const int32_t* lmn1, const int32_t* nprim1, const int64_t* off1, const double* exps1,
                        const double* ceff1, int n2, const double* oz2, const int32_t* lmn2, const int32_t* nprim2, const int64_t* off2,
-                       const double* exps2, const double* ceff2, double* S12) {
+                       const double* exps2, const double* ceff2, double* S12) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (n1 <= 0 || n2 <= 0 || !oz1 || !lmn1 || !nprim1 || !off1 || !exps1 || !ceff1 || !oz2 || !lmn2 || !nprim2 || !off2 || !exps2 || !ceff2 || !S12)
         FAIL(TUNA_ERR_ARG, "tuna_cross_overlap: bad arguments");
@@ -1997,7 +2030,7 @@ int tuna_cross_overlap(tuna_ctx* ctx, int n1, const double* oz1, const int32_t* 
     if (rc) return rc;
     if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("tuna_cross_overlap: ") + cudaGetErrorString(e));
     return TUNA_OK;
-}
+} TUNA_CATCH
 
 }  // extern "C"
 
@@ -2273,12 +2306,7 @@ static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
 template <int GG, int NB>
 static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::LaunchGroup& lg, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                 double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_shell_jk<GG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = opt_in_smem<k_shell_jk<GG, NB>>(ctx); e != cudaSuccess) return e;
     const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;      // the dense fill is not sharded
     long long blocks = (lg.nunits - srank + sn - 1) / sn;       // units owned by this rank
     if (blocks <= 0) return cudaSuccess;
@@ -2293,12 +2321,7 @@ static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::LaunchGroup& lg, 
 template <int GG, int NB, int REGS>
 static cudaError_t launch_shell_one_r(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                       double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_shell_jk_one<GG, NB, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = opt_in_smem<k_shell_jk_one<GG, NB, REGS>>(ctx); e != cudaSuccess) return e;
     const long long nchunk = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
     const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;
     long long blocks = (nchunk - srank + sn - 1) / sn;       // chunks owned by this rank
@@ -2326,12 +2349,7 @@ static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, 
 template <int GG, int NB>
 static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                     double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_shell_jk_one<GG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = opt_in_smem<k_shell_jk_one<GG, NB>>(ctx); e != cudaSuccess) return e;
     const long long nchunk = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
     const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;
     long long blocks = (nchunk - srank + sn - 1) / sn;       // chunks owned by this rank
@@ -2413,6 +2431,7 @@ static int shell4_slice_doubles(const Class4Host& C, int nD) {
     Shell4Job Jt;
     Jt.La = C.La; Jt.Lb = C.Lb; Jt.Lc = C.Lc; Jt.Ld = C.Ld;
     Jt.ct.ssize = C.ssize; Jt.ct.itmax = C.itmax; Jt.ct.zrow = C.zrow; Jt.ct.nstage = C.nstage; Jt.ct.nwork = C.nwork;
+    Jt.ct.nout_sm = C.nterm2 > 0 ? 0 : C.nwork;
     shell4_job_layout(Jt, nD);
     return Jt.total + (C.tab_words + 1) / 2 + 16;
 }
@@ -2465,6 +2484,7 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     const size_t o_acc = add(C.acc.data(), C.nterm2 > 0 ? 0 : C.acc.size() * 4);      // (unused in term mode)
     const size_t o_tabs = add(C.tabs.data(), C.tabs.size() * 4);
     const size_t o_tm = add(C.terms.data(), C.terms.size() * 4), o_tp = add(C.tptr.data(), C.tptr.size() * 4);
+    const size_t o_wf = add(C.wfl.data(), C.wfl.size() * 4), o_wl = add(C.wlist.data(), C.wlist.size() * 2);
     std::vector<unsigned char> host(total, 0);
     for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
     int rc;
@@ -2479,6 +2499,7 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     V.acc = (const unsigned*)(E.blob + o_acc); V.pmap = (const unsigned short*)(E.blob + o_pmap); V.omap = (const unsigned short*)(E.blob + o_omap);
     V.jst_ptr = (const unsigned*)(E.blob + o_jp); V.jst_list = (const unsigned short*)(E.blob + o_jl); V.jflush = (const unsigned*)(E.blob + o_jf);
     V.terms = (const unsigned*)(E.blob + o_tm); V.tptr = (const unsigned*)(E.blob + o_tp);
+    V.wfl = (const unsigned*)(E.blob + o_wf); V.wlist = (const unsigned short*)(E.blob + o_wl);
     *out = &E;
     return TUNA_OK;
 }
@@ -2574,21 +2595,32 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
     return TUNA_OK;
 }
 
+template <int GG, int NB, int REGS>
+static cudaError_t launch_shell4_one_r(tuna_ctx* ctx, const tuna_ctx::Job4Host& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
+                                       double* Jf, double* Kf, double tau, cudaStream_t stream, long long blocks) {
+    if (cudaError_t e = opt_in_smem<k_shell4_one<GG, NB, REGS>>(ctx); e != cudaSuccess) return e;
+    k_shell4_one<GG, NB, REGS><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
+                                                                            ctx->shard_rank, ctx->shard_n, jh.tab_off, jh.hdr_off);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
 template <int GG, int NB>
 static cudaError_t launch_shell4_one(tuna_ctx* ctx, const tuna_ctx::Job4Host& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                      double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k_shell4_one<GG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per device: cheap, so unconditional
-    if (e != cudaSuccess) return e;
     const long long nunit = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
     long long blocks = (nunit - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // units owned by this rank
     if (blocks <= 0) return cudaSuccess;
     const size_t by_smem = std::max<size_t>(1, (size_t)(228 * 1024) / (jh.smem + 1024));
     const size_t by_thr = std::max<size_t>(1, 2048 / jh.threads);
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * (long long)std::min(by_smem, by_thr) * 2);
-    k_shell4_one<GG, NB><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
-                                                                      ctx->shard_rank, ctx->shard_n, jh.tab_off, jh.hdr_off);
-    ctx->launches++;
-    return cudaGetLastError();
+    // a class whose shared-memory footprint already limits the SM to two 256-thread CTAs gets the 128-register build (no spills,
+    // more loads in flight in the unrolled digestion); TUNA_B200_REG_TIER=0 forces the 64-register build
+    if constexpr (GG == 256 && NB <= 2) {
+        static const bool tiers = !(getenv("TUNA_B200_REG_TIER") && atoi(getenv("TUNA_B200_REG_TIER")) == 0);
+        if (tiers && by_smem * jh.threads * 128 <= 65536) return launch_shell4_one_r<GG, NB, 128>(ctx, jh, D, nD, Pf, Psym, Jf, Kf, tau, stream, blocks);
+    }
+    return launch_shell4_one_r<GG, NB, TUNA_SHELL4_REGS>(ctx, jh, D, nD, Pf, Psym, Jf, Kf, tau, stream, blocks);
 }
 
 static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const double* Psym, double* Jc, double* Kc, double tau) {
@@ -2774,12 +2806,13 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
 
 extern "C" {
 
-int tuna_jk_direct_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK, double tau) {
+int tuna_jk_direct_dev(tuna_ctx* ctx, int nD, const double* dP, double* dJ, double* dK, double tau) try {
     if (!ctx) return TUNA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
     return jk_direct_core(ctx, nD, dP, 0u, dJ, dK, tau);
-}
+} TUNA_CATCH
 
-int tuna_jk_direct(tuna_ctx* ctx, int nD, const double* P, double* J, double* K, double tau) {
+int tuna_jk_direct(tuna_ctx* ctx, int nD, const double* P, double* J, double* K, double tau) try {
     if (!ctx) return TUNA_ERR_ARG;
     if (ctx->ncart == 0 || ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_jk_direct: basis and transform must be set first");
     if (nD <= 0 || nD > 8 || !P) FAIL(TUNA_ERR_ARG, "tuna_jk_direct: bad arguments (1 <= nD <= 8)");
@@ -2830,11 +2863,12 @@ int tuna_jk_direct(tuna_ctx* ctx, int nD, const double* P, double* J, double* K,
             for (size_t x = 0; x < (size_t)nD * nn; ++x) K[x] += hK[(size_t)nD * nn + x];
     }
     return TUNA_OK;
-}
+} TUNA_CATCH
 
 int tuna_get_counts(const tuna_ctx* c, int64_t counts[8]) {
     if (!c || !counts) return TUNA_ERR_ARG;
     tuna_ctx* ctx = const_cast<tuna_ctx*>(c);
+    if (ctx->ncart > 0 && !ctx->pairs_ready) { cudaSetDevice(ctx->device); if (int rc = ensure_pairs(ctx)) return rc; }
     unsigned long long ev = 0;
     if (ctx->d_scalars) {
         cudaSetDevice(ctx->device);
@@ -2859,8 +2893,10 @@ int tuna_last_kernel_ms(tuna_ctx* ctx, int which, float* ms) {
     return TUNA_OK;
 }
 
-int tuna_algorithmic_flops(const tuna_ctx* ctx, double* eri_flops, double* digest) {
-    if (!ctx) return TUNA_ERR_ARG;
+int tuna_algorithmic_flops(const tuna_ctx* c, double* eri_flops, double* digest) {
+    if (!c) return TUNA_ERR_ARG;
+    tuna_ctx* ctx = const_cast<tuna_ctx*>(c);
+    if (ctx->ncart > 0 && !ctx->pairs_ready) { cudaSetDevice(ctx->device); if (int rc = ensure_pairs(ctx)) return rc; }
     if (eri_flops) *eri_flops = ctx->alg_eri_flops;
     if (digest) *digest = ctx->alg_digest_flops;
     return TUNA_OK;

@@ -48,6 +48,7 @@ class FockBuilder:
 
     def build_device(self):
         """Kernels + collective only: inputs already in HBM (self.dP), result left in self.dJK.  Enqueues on self.stream."""
+        self.ctx.set_stream(self.stream.cuda_stream)      # several builders (e.g. nD = 1 and nD = 2) may share one context
         self.ctx.jk_direct_dev(self.nD, self.dP.data_ptr(), self.dJK[0].data_ptr(), self.dJK[1].data_ptr(), self.tau)
         if self.world > 1:
             with self.torch.cuda.stream(self.stream):

@@ -190,13 +190,35 @@ for _op in ("add", "radd", "sub", "rsub", "mul", "rmul", "truediv", "rtruediv", 
         setattr(ERIHandle, f"__{_op}__", _binary(f"__{_op}__"))
 
 
-def _context_for(bfs):
-    ctx = _lib.Context(_settings["device"])
+_ctx_cache = []        # [(device, key, Context)] most recent first: one-electron integrals, ERIs and J/K of one geometry share a context
+
+
+def _flatten_or_raise(bfs):
     try:
-        oz, lmn, nprim, exps, ceff = flatten(bfs)
+        return flatten(bfs)
     except ValueError as e:
         raise _lib.error_class(f"tuna_b200: {e}")
-    ctx.set_basis(oz, lmn, nprim, exps, ceff)
+
+
+def _context_for(bfs, cached=True):
+    """Context holding this basis.  With cached=True the context of the most recent identical basis (same device, byte-identical flattened
+    arrays) is returned: the reference asks for the one-electron integrals, the two-electron integrals and single quartets of one geometry
+    through separate calls (tuna_kernel.py:425-437), and finite-field / ionisation runs repeat them on the same geometry
+    (tuna_energy.py:361-373).  The library builds the ERI pair table lazily, so a context that only serves one-electron integrals never pays
+    for it.  Cached contexts are never closed here (an ERIHandle may hold them); they are released when the last reference goes."""
+    flat = _flatten_or_raise(bfs)
+    dev = _settings["device"]
+    if cached:
+        key = tuple(np.ascontiguousarray(a).tobytes() for a in flat)
+        for i, (d, k, c) in enumerate(_ctx_cache):
+            if d == dev and k == key and getattr(c, "_h", True):
+                _ctx_cache.insert(0, _ctx_cache.pop(i))
+                return c
+    ctx = _lib.Context(dev)
+    ctx.set_basis(*flat)
+    if cached:
+        _ctx_cache.insert(0, (dev, key, ctx))
+        del _ctx_cache[2:]
     return ctx
 
 
@@ -211,7 +233,7 @@ def calculate_electron_repulsion_integrals(n_basis, ERI_AO, bfs, num_threads):
     out = np.asarray(ERI_AO)
     if out.shape != (n_basis,) * 4 or out.dtype != np.float64:
         raise _lib.error_class("tuna_b200: ERI_AO must be a float64 array of shape (n_basis,)*4")
-    ctx = _context_for(bfs)
+    ctx = _context_for(bfs, cached=False)            # the dense Cartesian tensor is only a transit buffer here: private context, closed below
     ctx.eri_fill_cart()
     if out.flags.c_contiguous:
         ctx.eri_download(0, out)
@@ -223,10 +245,9 @@ def calculate_electron_repulsion_integrals(n_basis, ERI_AO, bfs, num_threads):
 
 def calculate_electron_repulsion_integral(bf_1, bf_2, bf_3, bf_4):
     """(12|34) for four basis functions (pyx:1376-1414)."""
-    ctx = _context_for([bf_1, bf_2, bf_3, bf_4])
-    v = ctx.eri_single(0, 1, 2, 3)
-    ctx.close()
-    return v
+    ctx = _scratch_context()                           # no context per scalar: the scratch context takes the four functions as its basis
+    ctx.set_basis(*_flatten_or_raise([bf_1, bf_2, bf_3, bf_4]))
+    return ctx.eri_single(0, 1, 2, 3)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -411,11 +432,8 @@ def calculate_one_electron_integrals(n_basis, basis_functions, n_atoms, atoms, d
     pos = np.array([np.asarray(a.origin, dtype=np.float64) for a in atoms]).reshape(n_atoms, 3)
     if np.any(pos[:, :2] != 0.0):
         raise _lib.error_class("tuna_b200: all atoms must lie on the z axis")       # as the reference's nuclear integral requires (pyx:783)
-    ctx = _context_for(basis_functions)
-    try:
-        return ctx.one_electron(pos[:, 2], [float(a.charge) for a in atoms], np.asarray(dipole_origin, dtype=np.float64))
-    finally:
-        ctx.close()
+    ctx = _context_for(basis_functions)                # shared with the two-electron call that follows (tuna_kernel.py:425-437)
+    return ctx.one_electron(pos[:, 2], [float(a.charge) for a in atoms], np.asarray(dipole_origin, dtype=np.float64))
 
 
 def calculate_cross_basis_overlap_matrix(n_basis_1, n_basis_2, basis_functions_1, basis_functions_2, num_threads):
