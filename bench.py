@@ -31,12 +31,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "fock_builds_per_s"
 UNIT = "Fock builds/s"
 
-# ncu-counted FP64 work of one direct build, keyed by (workload, densities, tau): 2*DFMA + DMUL + DADD thread instructions
-# summed over the 231 class-job launches of one ET800 build (profiles/r01f_class_metrics.csv; see profiles/README.md).
-EXECUTED_FP64 = {
-    ("et800", 1, 1e-16): {"fp64_flops_per_build": 1.902e12, "warp_instructions_per_build": 6.63e11, "fp64_share_of_thread_instructions": 0.062,
-                          "issue_active_pct": 42.6, "fp64_pipe_active_pct": 6.2, "source": "profiles/r01f_class_metrics.csv (ncu, round 1)"},
-}
+# ncu-counted FP64 work (2*DFMA + DMUL + DADD thread instructions) and DRAM traffic of one direct build, summed over all class-job
+# launches: a property of the code + workload, regenerated from the ncu CSV of the round by tools/executed_from_ncu.py into
+# profiles/executed_fp64.json, keyed "<workload>|<densities>|<tau>".  The RATE below always uses this run's own kernel time.
+def executed_fp64_table():
+    try:
+        with open(os.path.join(ROOT, "profiles", "executed_fp64.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -440,25 +443,33 @@ def bench_one_electron(wl, charges=(7.0, 7.0)):
     return out
 
 
-def parity_at_bench_size(wl, tau, device):
-    """Evidence that the timed kernels compute the reference's numbers AT THE TIMED SIZE (no dense tensor exists there): J/K from a unit-pair
-    density P = e_k e_l^T + e_l e_k^T are single integrals, J_ij = (ij|kl) + (ij|lk), K_ij = (il|kj) + (ik|lj), which the oracle evaluates one
-    by one for sampled (i, j).  The oracle is the checker here, never the thing measured."""
+def parity_at_bench_size(wl, tau, builder, rank, P_timed):
+    """Evidence that the timed kernels compute the reference's numbers AT THE TIMED SIZE and AT THE TIMED RANK COUNT (no dense tensor exists
+    there).  (a) rank 0, single GPU, Cartesian basis: J/K from a unit-pair density P = e_k e_l^T + e_l e_k^T are single integrals,
+    J_ij = (ij|kl) + (ij|lk), K_ij = (il|kj) + (ik|lj), which the oracle evaluates one by one for sampled (i, j).  (b) N > 1: the sharded,
+    all-reduced build of the TIMED density (every rank takes part) against the unsharded build of the same density on rank 0.
+    The oracle is the checker here, never the thing measured."""
     import tuna_b200
     from oracle import tuna_oracle as orc
     from tuna_b200.basis import flatten
     from util import pick_function, unit_pair_density
+    out = None
+    Jn = Kn = None
+    if builder.world > 1:
+        Jn, Kn = builder.build(P_timed)
+    if rank != 0:
+        return None
     bfs = wl["bfs"]
     fb = orc.FlatBasis.from_reference_objects(bfs)
     n = fb.ncart
     Lmax = int(np.asarray(fb.lmn).sum(axis=1).max())
     k, l = pick_function(fb, 0, Lmax, True, 0), pick_function(fb, 1, max(Lmax - 1, 0), False, 0)
-    ctx = tuna_b200.Context(device)
+    ctx = tuna_b200.Context(builder.ctx.device)
     ctx.set_basis(*flatten(bfs))
     ctx.set_transform(np.eye(n))
     J, K = ctx.jk_direct(unit_pair_density(n, k, l), tau)
     rng = np.random.default_rng(5)
-    worst, worst_rel, ok = 0.0, 0.0, True
+    worst, ok = 0.0, True
     ns = 150
     for i, j in zip(rng.integers(0, n, ns), rng.integers(0, n, ns)):
         i, j = int(i), int(j)
@@ -468,9 +479,18 @@ def parity_at_bench_size(wl, tau, device):
             err = abs(got - ref)
             worst = max(worst, err)
             ok = ok and err <= 2 * max(1e-12, 1e-13 * scale)
+    out = {"what": "direct J/K from a unit-pair density vs single integrals of the oracle, sampled elements", "samples": 2 * ns, "pair": [k, l],
+           "max_abs_diff": worst, "within_tolerance": bool(ok), "tolerance": "2 * max(1e-12, 1e-13 |ERI|) (SURVEY.md 8d)", "ranks": builder.world}
+    if builder.world > 1:
+        ctx.set_transform(np.asarray(wl["U"]))
+        J1, K1 = ctx.jk_direct(P_timed, tau)
+        scale = max(1.0, float(np.abs(K1).max()))
+        d = float(max(np.abs(np.asarray(Jn) - J1).max(), np.abs(np.asarray(Kn) - K1).max()))
+        out["sharded_vs_single_gpu"] = {"what": f"all-reduced build over {builder.world} ranks vs the unsharded build of the timed density on rank 0",
+                                        "max_abs_diff": d, "scale": scale, "within_tolerance": bool(d <= 1e-11 * scale), "tolerance": "1e-11 * max(1, max|K|)"}
+        out["within_tolerance"] = bool(out["within_tolerance"] and d <= 1e-11 * scale)
     ctx.close()
-    return {"what": "direct J/K from a unit-pair density vs single integrals of the oracle, sampled elements", "samples": 2 * ns, "pair": [k, l],
-            "max_abs_diff": worst, "within_tolerance": bool(ok), "tolerance": "2 * max(1e-12, 1e-13 |ERI|) (SURVEY.md 8d)"}
+    return out
 
 
 def sweep_point(torch, nbf, tau, fp64_peak, device):
@@ -568,42 +588,50 @@ def run_ours(args, wl):
         sm = tt.clone(); ddist.all_reduce(sm, op=ddist.ReduceOp.SUM)
         e2e_s, evaluated, k_ms = float(mx[0]), int(sm[1].item()), float(mx[2])
     clocks = sampler.stop()
+    try:       # evidence only; never allowed to take the line down (collective: every rank calls it)
+        parity = parity_at_bench_size(wl, args.tau, fb, rank, P if nD > 1 else P[0])
+    except Exception as e:
+        parity = {"error": str(e)}
     if rank != 0:
         if ddist is not None:
             ddist.destroy_process_group()
         return
     c = ctx.counts()
     alg_eri, alg_digest = ctx.algorithmic_flops()
-    alg = alg_eri + alg_digest * nD
+    # screened-out quartets are not work done - the algorithmic count is scaled to the EVALUATED share of the surviving quartets
+    eval_share = evaluated / max(1, c["surviving_quartets"])
+    alg = (alg_eri + alg_digest * nD) * eval_share
     builds_per_s = args.steps / (ms * 1e-3)
-    achieved = alg / world / (k_ms * 1e-3) / 1e12           # this rank's share of the algorithmic flops over its kernel time
+    alg_rate = alg / world / (k_ms * 1e-3) / 1e12           # this rank's share of the algorithmic flops over its kernel time
+    ex = executed_fp64_table().get(f"{wl['name']}|{nD}|{args.tau:g}")
+    ex_rate = ex["fp64_flops_per_build"] / world / (k_ms * 1e-3) / 1e12 if ex else None
+    roofline = {"bound": "fp64", "achieved": ex_rate, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": (ex_rate / fp64_peak) if (ex_rate is not None and fp64_peak) else None,
+                "traffic": ex.get("dram_bytes_per_build") if ex else None,
+                "basis": "EXECUTED FP64 flops of one build (ncu: 2*DFMA + DMUL + DADD thread instructions over all class-job launches, "
+                         "profiles/executed_fp64.json) over this run's kernel time; null when no ncu count exists for this workload",
+                "peak_source": "sustained FP64 DFMA stream measured in this run (tuna_fp64_peak_probe, >= 0.5 s); MEASURED_PEAKS.json has no FP64 entry",
+                "kernel": "k_shell4_one (all class jobs of one build)", "kernel_ms": k_ms,
+                "algorithmic": {"flops_evaluated": alg, "tflops": alg_rate, "frac": alg_rate / fp64_peak if fp64_peak else None, "evaluated_share": eval_share,
+                                "note": "the reference algorithm's flop count F(a,b) (SURVEY.md 8d) + 12 flops/quartet/density of digestion, over the "
+                                        "quartets that survive parity AND Schwarz screening; the engine shares Boys/R/convolution tables among all "
+                                        "components of a shell quartet and therefore executes far fewer flops"}}
+    if ex:
+        roofline["executed"] = ex
     line = {"metric": METRIC, "value": builds_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["description"], "nbf": n, "ncart": wl["ncart"], "mode": "direct", "densities": nD, "schwarz_tau": args.tau,
                        "parallelism": f"quartet list sharded over {world} GPU(s), one all-reduce of J/K per build",
                        "l2": L2_NOTE + "; inputs (pair table, P) are re-read from HBM each step",
-                       "pair_table_setup_s": setup_s},
+                       "pair_table_setup_s": setup_s,
+                       "parity": {"within_tolerance": parity.get("within_tolerance"), "max_abs_diff": parity.get("max_abs_diff"),
+                                  "sharded_max_abs_diff": (parity.get("sharded_vs_single_gpu") or {}).get("max_abs_diff"), "error": parity.get("error")}},
             "eri_quartets_per_s": evaluated * builds_per_s, "surviving_quartets": c["surviving_quartets"], "evaluated_quartets": evaluated,
             "unique_quartets_per_s": c["unique_quartets"] * builds_per_s,
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                         "traffic": None, "peak_source": "FP64 DFMA stream measured in this run (tuna_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry",
-                         "kernel": "k_shell_jk (all class jobs of one build)", "kernel_ms": k_ms, "algorithmic_flops": alg,
-                         "note": "algorithmic = the reference algorithm's flop count F(a,b) (SURVEY.md 8d) + 12 flops/quartet/density of digestion; "
-                                 "the shell engine EXECUTES far fewer FP64 flops (tables shared by all components of a shell quartet): see `executed`"},
+            "roofline": roofline,
             "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(fb.h2d_bytes), "d2h_bytes_per_step": int(fb.d2h_bytes)},
-            "gpu_launches": int(launches), "clocks": clocks}
-    ex = EXECUTED_FP64.get((wl["name"], nD, args.tau))
-    if ex is not None:
-        # "always report the ncu-executed FP64 flop count beside it".  The count is a property of the code + workload
-        # (profiles/r01f_class_metrics.csv, ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on over all class-job
-        # launches of one build); the rate uses THIS run's kernel time.
-        rate = ex["fp64_flops_per_build"] / world / (k_ms * 1e-3) / 1e12
-        line["roofline"]["executed"] = dict(ex, tflops=rate, frac_of_fp64_peak=rate / fp64_peak if fp64_peak else None)
+            "gpu_launches": int(launches), "clocks": clocks, "parity": parity}
     if world == 1:
-        try:
-            line["parity"] = parity_at_bench_size(wl, args.tau, local)
-        except Exception as e:       # evidence only; never allowed to take the line down
-            line["parity"] = {"error": str(e)}
         line["cpu_baseline"] = cpu_reference(wl)
         if not args.no_stored:
             fb = None

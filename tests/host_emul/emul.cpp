@@ -78,6 +78,13 @@ struct HostPolicy {
     static int cta_thread() { return 0; }
     static int cta_threads() { return 1; }
     static void atomic_add(double* p, double v) { *p += v; }
+    static void accumulate(double* M, int idx, double v, long long fix_lo) {
+        if (fix_lo == 0) { M[idx] += v; return; }
+        long long h, l;
+        fixed_split(v, h, l);
+        long long* W = reinterpret_cast<long long*>(M);
+        W[idx] += h; W[fix_lo + idx] += l;
+    }
 };
 
 static double* g_fill_out = nullptr;      // non-null: the driver below runs the engine in fill mode into this dense tensor
@@ -117,7 +124,7 @@ extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const 
     ShellData D;
     D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
     D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data();
-    D.eri_out = g_fill_out; D.fnorm = S.fnorm.data();
+    D.eri_out = g_fill_out; D.fnorm = S.fnorm.data(); D.fix_lo = 0;
     long long nitems_total = 0, nskipped = 0;
     const int ncls = (int)S.classes.size();
     for (int cb = 0; cb < ncls; ++cb)
@@ -215,6 +222,12 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
     D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
     D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data();
     D.eri_out = nullptr; D.fnorm = S.fnorm.data();
+    // TUNA_EMUL_FIXED=1: the reproducible integer accumulation (fixed_split) instead of FP64 adds
+    const bool fixed = getenv("TUNA_EMUL_FIXED") && atoi(getenv("TUNA_EMUL_FIXED")) != 0;
+    std::vector<long long> Jw, Kw;
+    double* Jacc = Jf.data(); double* Kacc = Kf.data();
+    D.fix_lo = 0;
+    if (fixed) { Jw.assign(2 * nD * nn, 0); Kw.assign(2 * nD * nn, 0); Jacc = reinterpret_cast<double*>(Jw.data()); Kacc = reinterpret_cast<double*>(Kw.data()); D.fix_lo = (long long)(nD * nn); }
     long long nitems_total = 0, nskipped = 0, nint_total = 0, nterm_total = 0;
     const int ncls = (int)S.classes.size();
     for (int cb = 0; cb < ncls; ++cb)
@@ -243,9 +256,9 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
             int nb = 0;
             auto run_batch = [&]() {
                 if (nb == 0) return;
-                if (NBATCH == 4) shell4_quartets<HostPolicy, 4>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
-                else if (NBATCH == 2) shell4_quartets<HostPolicy, 2>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
-                else shell4_quartets<HostPolicy, 1>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
+                if (NBATCH == 4) shell4_quartets<HostPolicy, 4>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jacc, Kacc, ncart);
+                else if (NBATCH == 2) shell4_quartets<HostPolicy, 2>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jacc, Kacc, ncart);
+                else shell4_quartets<HostPolicy, 1>(J, D, hq, sm.data(), tab.data(), tab_chunk, nD, Pf.data(), Psym.data(), Jacc, Kacc, ncart);
                 for (int q = 0; q < 4; ++q) hq[q].active = 0;
                 nb = 0;
             };
@@ -269,6 +282,8 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
             run_batch();
             nitems_total += J.nitems; nint_total += CH.nint; nterm_total += CH.nterms;
         }
+    if (fixed)
+        for (size_t x = 0; x < (size_t)nD * nn; ++x) { Jf[x] = fixed_value(Jw[x], Jw[nD * nn + x]); Kf[x] = fixed_value(Kw[x], Kw[nD * nn + x]); }
     for (int d = 0; d < nD; ++d)
         for (int i = 0; i < ncart; ++i)
             for (int j = 0; j < ncart; ++j) {

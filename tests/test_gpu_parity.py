@@ -250,6 +250,33 @@ def test_direct_engines_agree_and_general_density(tb, oracle, name, monkeypatch)
         assert np.abs(a - b).max() < 1e-11 * scale
 
 
+@pytest.mark.parametrize("name", ["ne2_uhf_ccpvqz", "et100"])
+def test_direct_build_is_bitwise_reproducible(tb, name):
+    """North star part 4: J/K of the direct mode do not depend on the order in which the class jobs of six streams and their CTAs arrive.
+    The generation-4 engine accumulates every contribution as two 64-bit integers (fixed_split, csrc/shell_jk.cuh): integer addition is
+    associative, so repeated builds - on the same context and on a fresh one - are bit-identical, and they agree with FP64-atomic
+    accumulation to round-off."""
+    g = load_golden(name)
+    nbf = int(g["nbf"])
+    rng = np.random.default_rng(21)
+    P = rng.standard_normal((2, nbf, nbf))
+    P = (P + P.transpose(0, 2, 1)) / 2
+    ctx = context_for(g)
+    ctx.set_transform(g["U"])
+    J0, K0 = ctx.jk_direct(P, 1e-16)
+    for _ in range(3):
+        J1, K1 = ctx.jk_direct(P, 1e-16)
+        assert np.array_equal(J0, J1) and np.array_equal(K0, K1)
+    ctx2 = context_for(g)
+    ctx2.set_transform(g["U"])
+    J2, K2 = ctx2.jk_direct(P, 1e-16)
+    assert np.array_equal(J0, J2) and np.array_equal(K0, K2)
+    ctx2.set_shard(1, 3)                   # partial builds of a sharded run are reproducible as well
+    Ja, Ka = ctx2.jk_direct(P, 1e-16)
+    Jb, Kb = ctx2.jk_direct(P, 1e-16)
+    assert np.array_equal(Ja, Jb) and np.array_equal(Ka, Kb)
+
+
 def test_high_angular_momentum_h_shells(tb, oracle):
     """A synthetic two-centre basis with every shell type up to H (L = 5, the reference's maximum, tuna_molecule.py:612-618):
     full Cartesian tensor vs the oracle, and the shell-quartet engine (multi-chunk (hh|hh) class tables) vs the stored path."""

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Development builds of the shell engine's compile-time variants (all OFF in the shipped libtuna_b200.so), for A/B timing with
-# tools/variant_sweep.py on a GPU box.  Each is checked for parity on the CPU by tests/test_host_emul.py (same macros, HostPolicy).
+# tools/direct_timing.py on a GPU box.  Each is checked for parity on the CPU by tests/test_host_emul.py (same macros, HostPolicy).
 #   TUNA_SHELL_WIDE_TERMS   phase 5: 8-byte terms with pre-scaled byte offsets, ping-pong quads (no decode, no register copies)
 #   TUNA_SHELL_ASM_UNROLL   phase 4: y operands in registers, m' loop unrolled per trip count
 #   TUNA_SHELL_REG_TIERS    128-register instantiation of k_shell_jk_one for class jobs whose shared memory limits occupancy anyway

@@ -32,7 +32,7 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_sh
 
 M=gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,sm__warps_active.avg.pct_of_peak_sustained_active
 step "ncu FP64 op counters, all class-job launches of one ET800 build"
-TUNA_B200_DUMP_JOBS=$O/${R}_jobs800.csv timeout 240 ncu --metrics $M --clock-control none --csv --log-file $O/${R}_class_metrics.csv -k regex:k_shell_jk -c 245 python tools/variant_sweep.py child 800 > $O/${R}_ncu_c.log 2>&1; step "rc=$?"
+TUNA_B200_DUMP_JOBS=$O/${R}_jobs800.csv timeout 240 ncu --metrics $M --clock-control none --csv --log-file $O/${R}_class_metrics.csv -k regex:k_shell_jk -c 245 python tools/direct_timing.py child 800 > $O/${R}_ncu_c.log 2>&1; step "rc=$?"
 
 step "ncu full capture: stored J/K (Ne2 UHF/cc-pVQZ) and AO->MO GEMM (N2/cc-pVTZ)"
 timeout 150 ncu --set full --clock-control none --import-source on -k regex:"k_jk_stored_sym|k_axis_gemm" -c 6 -f -o $O/${R}_prof_stored_mo python tools/stored_check.py profile > $O/${R}_ncu_t.log 2>&1; step "rc=$?"

@@ -8,7 +8,7 @@ date +%s > $O/${R}_t0
 step() { echo "[$(( $(date +%s) - $(cat $O/${R}_t0) )) s] $*" | tee -a $O/${R}_steps.log; }
 
 step "variant sweep"
-timeout 500 python tools/variant_sweep.py 100,200,400,800 > $O/${R}_variants.log 2>&1; step "rc=$?"
+timeout 500 python tools/direct_timing.py 100,200,400,800 > $O/${R}_variants.log 2>&1; step "rc=$?"
 
 step "fullsize parity (nbf 400 / 800)"
 timeout 400 python -m pytest tests/test_zz_fullsize.py -m gpu -q > $O/${R}_zz.log 2>&1; step "rc=$? $(tail -n 1 $O/${R}_zz.log)"
@@ -21,7 +21,7 @@ timeout 120 python tools/mo_quick.py > $O/${R}_simt_mo.json 2>&1; step "rc=$?"
 step "graph mode parity"
 TUNA_B200_GRAPH=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k direct > $O/${R}_graph.log 2>&1; step "rc=$? $(tail -n 1 $O/${R}_graph.log)"
 
-CMD="python tools/variant_sweep.py child 800"
+CMD="python tools/direct_timing.py child 800"
 for IDX in 116 30 190; do
   step "ncu full capture of class-job launch $IDX"
   TUNA_B200_DUMP_JOBS=$O/${R}_jobs800.csv timeout 240 ncu --set full --clock-control none --import-source on -k regex:k_shell_jk_one -s $IDX -c 1 -f -o $O/${R}_prof_$IDX $CMD > $O/${R}_ncu_$IDX.log 2>&1; step "rc=$?"

@@ -516,7 +516,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                             const double v = s0[q] + s1[q];
                             if (!act[q] || v == 0.0) continue;
                             const int* ao = aoq + q * 4 * aos;
-                            Pol::atomic_add(M + ao[ri] * ncart + ao[ci], v);
+                            Pol::accumulate(M, ao[ri] * ncart + ao[ci], v, D.fix_lo);
                         }
                     }
                 }
@@ -637,7 +637,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             for (int q = 0; q < NB; ++q) {
                 if (!act[q] || v.v[q] == 0.0) continue;
                 const int* ao = aoq + q * 4 * aos;
-                Pol::atomic_add(Kd + ao[ri] * ncart + ao[ci], v.v[q]);
+                Pol::accumulate(Kd, ao[ri] * ncart + ao[ci], v.v[q], D.fix_lo);
             }
         }
         for (int x = lane; x < CT.njfl; x += Pol::G) {
@@ -648,7 +648,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             for (int q = 0; q < NB; ++q) {
                 if (!act[q] || v.v[q] == 0.0) continue;
                 const int* ao = aoq + q * 4 * aos;
-                Pol::atomic_add(Jd + ao[ri] * ncart + ao[ci], v.v[q]);
+                Pol::accumulate(Jd, ao[ri] * ncart + ao[ci], v.v[q], D.fix_lo);
             }
         }
     }

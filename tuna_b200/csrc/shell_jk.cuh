@@ -139,7 +139,23 @@ struct ShellData {
     const double* herm;
     double* eri_out;                        // fill mode: dense Cartesian tensor [ncart^4] (zero-initialised by the caller)
     const double* fnorm;                    // fill mode: per-component norms (the engine works with unnormalised components)
+    long long fix_lo;                       // generation 4, reproducible accumulation: 0 = FP64 atomics into Jf / Kf; otherwise Jf / Kf are 64-bit
+                                            // integer arrays and the low words live fix_lo elements behind the high words (see fixed_add)
 };
+
+// Reproducible J/K accumulation.  Floating-point atomics make the sum depend on the order in which CTAs of six streams arrive; integer
+// addition does not.  A contribution v is split exactly into  v = h * 2^-20 + r,  h = rint(v * 2^20),  and r is rounded to
+// l = rint(r * 2^60) (|l| <= 2^39); h and l are added with 64-bit integer atomics into a high and a low word.  The final value
+// hi * 2^-20 + lo * 2^-60 is independent of the summation order; its error is at most (contributions per element) * 2^-61, i.e. about
+// 2e-14 for the 4e4 shell-pair contributions an element of K receives at nbf 800; |J|, |K| < 2^42 is required (no overflow of hi).
+constexpr double FIX_HI = 1048576.0;                    // 2^20
+constexpr double FIX_LO = 1152921504606846976.0;        // 2^60
+TUNA_HD void fixed_split(double v, long long& h, long long& l) {
+    const double hd = rint(v * FIX_HI);
+    h = (long long)hd;
+    l = (long long)rint(fma(-hd, 1.0 / FIX_HI, v) * FIX_LO);
+}
+TUNA_HD double fixed_value(long long h, long long l) { return (double)h * (1.0 / FIX_HI) + (double)l * (1.0 / FIX_LO); }
 
 inline void shell_job_layout(ShellJob& J, int nD) {
     const int Ltot = J.La + J.Lb + J.Lc + J.Ld, Lab = J.La + J.Lb, Lcd = J.Lc + J.Ld;

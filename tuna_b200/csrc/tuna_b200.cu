@@ -121,6 +121,8 @@ struct tuna_ctx {
     std::vector<Job4Host> jobs4;
     double shell4_tau = -1.0;
     int shell4_nD = -1;
+    long long* d_fix = nullptr; size_t cap_fix = 0;      // reproducible accumulation: [J hi | J lo | K hi | K lo], nD * ncart^2 words each
+    bool deterministic = true;      // order-independent integer accumulation of J/K in the generation-4 engine (TUNA_B200_DETERMINISTIC=0: FP64 atomics)
     int engine_gen = 4;             // 4 = shell4.cuh (default), 2 = shell_jk.cuh (TUNA_B200_ENGINE=2; also serves the dense fill)
     CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
     int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
@@ -833,6 +835,15 @@ struct DevPolicy {
     __device__ __forceinline__ static int cta_thread() { return threadIdx.x; }
     __device__ __forceinline__ static int cta_threads() { return blockDim.x; }
     __device__ __forceinline__ static void atomic_add(double* p, double v) { atomicAdd(p, v); }
+    // M[idx] += v: FP64 atomic (fix_lo == 0) or the order-independent two-word integer accumulation of fixed_split
+    __device__ __forceinline__ static void accumulate(double* M, int idx, double v, long long fix_lo) {
+        if (fix_lo == 0) { atomicAdd(M + idx, v); return; }
+        long long h, l;
+        fixed_split(v, h, l);
+        unsigned long long* W = reinterpret_cast<unsigned long long*>(M);
+        if (h != 0) atomicAdd(W + idx, (unsigned long long)h);
+        if (l != 0) atomicAdd(W + fix_lo + idx, (unsigned long long)l);
+    }
 };
 
 // One group of G lanes per shell quartet.  A launch covers ALL class jobs that use this group size: the work units
@@ -1024,6 +1035,14 @@ k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, co
             shell4_quartets<DevPolicy<GG>, NB>(J, D, hdr + k0 + gid * NB, sm, tab, tab_chunk, nD, Pf, Psym, Jf, Kf, ncart);
     }
     if (done != 0.0) atomicAdd(evaluated, done);
+}
+
+// reproducible accumulation: (hi, lo) integer words -> FP64 (fixed_value), J and K in one launch
+__global__ void k_fixed_to_double(const long long* __restrict__ fix, double* __restrict__ J, double* __restrict__ K, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        J[i] = fixed_value(fix[i], fix[count + i]);
+        K[i] = fixed_value(fix[2 * count + i], fix[3 * count + i]);
+    }
 }
 
 __global__ void k_absmax_scaled(const double* __restrict__ x, const double* __restrict__ finv, int n, int nD, unsigned long long* out) {
@@ -1265,6 +1284,7 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->d_Pc); dev_free(&ctx->d_Jc); dev_free(&ctx->d_Kc); dev_free(&ctx->d_tmp); dev_free(&ctx->d_Kpart);
     for (auto& kv : ctx->class_tabs) dev_free(&kv.second.blob);
     for (auto& kv : ctx->class_tabs4) dev_free(&kv.second.blob);
+    dev_free(&ctx->d_fix);
 #ifdef TUNA_SHELL_WIDE_TERMS
     for (auto& kv : ctx->class_tabs) for (int w = 0; w < 3; ++w) dev_free(&kv.second.wide[w]);
 #endif
@@ -1344,6 +1364,8 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     ctx->direct_engine = (eng && std::string(eng) == "generic") ? 0 : 1;
     const char* gen = getenv("TUNA_B200_ENGINE");
     ctx->engine_gen = (gen && atoi(gen) == 2) ? 2 : 4;
+    const char* det = getenv("TUNA_B200_DETERMINISTIC");
+    ctx->deterministic = !(det && atoi(det) == 0);
     return TUNA_OK;
 } TUNA_CATCH
 
@@ -1976,7 +1998,6 @@ int tuna_one_electron(tuna_ctx* ctx, int n_atoms, const double* atom_z, const do
     if (!rc) rc = dev_alloc(ctx, &d_at, at.size());
     if (!rc) rc = dev_alloc(ctx, &d_out, 9 * nn);
     cudaError_t e = cudaSuccess;
-    std::vector<double> host;
     if (!rc) {
         e = cudaMemcpyAsync(d_at, at.data(), at.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5][0], ctx->stream);
@@ -1986,8 +2007,14 @@ int tuna_one_electron(tuna_ctx* ctx, int n_atoms, const double* atom_z, const do
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[5][1], ctx->stream);
-        host.resize(9 * nn);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), d_out, 9 * nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        // straight into the caller's buffers (page-locked when they come from the Python layer): no staging vector, no second copy
+        double* dst[5] = {S, T, V, D, Q};
+        const size_t cnt[5] = {nn, nn, nn, 3 * nn, 3 * nn};
+        size_t off = 0;
+        for (int k = 0; k < 5; ++k) {
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dst[k], d_out + off, cnt[k] * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+            off += cnt[k];
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     } else {
         cudaStreamSynchronize(ctx->stream);
@@ -1995,11 +2022,6 @@ int tuna_one_electron(tuna_ctx* ctx, int n_atoms, const double* atom_z, const do
     basis_dev_free(B); dev_free(&d_at); dev_free(&d_out);
     if (rc) return rc;
     if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("tuna_one_electron: ") + cudaGetErrorString(e));
-    std::memcpy(S, host.data(), nn * sizeof(double));
-    std::memcpy(T, host.data() + nn, nn * sizeof(double));
-    std::memcpy(V, host.data() + 2 * nn, nn * sizeof(double));
-    std::memcpy(D, host.data() + 3 * nn, 3 * nn * sizeof(double));
-    std::memcpy(Q, host.data() + 6 * nn, 3 * nn * sizeof(double));
     return TUNA_OK;
 } TUNA_CATCH
 
@@ -2369,7 +2391,7 @@ static int launch_shell_jobs(tuna_ctx* ctx, int nD, const double* Pc, const doub
         ShellData D;
         D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
         D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
-        D.eri_out = eri_out; D.fnorm = ctx->d_fnorm;
+        D.eri_out = eri_out; D.fnorm = ctx->d_fnorm; D.fix_lo = 0;
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
         int jn = 0;
@@ -2623,11 +2645,11 @@ static cudaError_t launch_shell4_one(tuna_ctx* ctx, const tuna_ctx::Job4Host& jh
     return launch_shell4_one_r<GG, NB, TUNA_SHELL4_REGS>(ctx, jh, D, nD, Pf, Psym, Jf, Kf, tau, stream, blocks);
 }
 
-static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const double* Psym, double* Jc, double* Kc, double tau) {
+static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const double* Psym, double* Jc, double* Kc, double tau, long long fix_lo) {
     ShellData D;
     D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
     D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
-    D.eri_out = nullptr; D.fnorm = ctx->d_fnorm;
+    D.eri_out = nullptr; D.fnorm = ctx->d_fnorm; D.fix_lo = fix_lo;
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
     int jn = 0;
@@ -2774,14 +2796,31 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
         k_absmax<<<grid_for(ctx, (int64_t)nD * ncc, 256, 4), 256, 0, ctx->stream>>>(ctx->d_Pc, (int64_t)nD * ncc, ctx->d_scalars);
     }
     ctx->launches++;
-    CK(cudaMemsetAsync(ctx->d_Jc, 0, nD * ncc * sizeof(double), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_Kc, 0, nD * ncc * sizeof(double), ctx->stream));
+    const bool fixed = gen4 && ctx->deterministic;
+    const size_t nacc = (size_t)nD * ncc;
+    if (fixed) {
+        if (ctx->cap_fix < 4 * nacc) {
+            ctx->cap_fix = 0;
+            if ((rc = dev_alloc(ctx, &ctx->d_fix, 4 * nacc))) return rc;
+            ctx->cap_fix = 4 * nacc;
+        }
+        CK(cudaMemsetAsync(ctx->d_fix, 0, 4 * nacc * sizeof(long long), ctx->stream));
+    } else {
+        CK(cudaMemsetAsync(ctx->d_Jc, 0, nacc * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_Kc, 0, nacc * sizeof(double), ctx->stream));
+    }
     if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
     if (shell) {
         k_add_transpose_signed<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_Pc, ctx->d_tmp, nD, nc, 0u);   // Psym = P + P^T
         ctx->launches++;
-        if ((rc = gen4 ? launch_shell4_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau)
-                       : launch_shell_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, nullptr))) return rc;
+        if (fixed) {
+            double* Jw = reinterpret_cast<double*>(ctx->d_fix);
+            double* Kw = reinterpret_cast<double*>(ctx->d_fix + 2 * nacc);
+            if ((rc = launch_shell4_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, Jw, Kw, tau, (long long)nacc))) return rc;
+            k_fixed_to_double<<<grid_for(ctx, (int64_t)nacc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_fix, ctx->d_Jc, ctx->d_Kc, nacc);
+            ctx->launches++;
+        } else if ((rc = gen4 ? launch_shell4_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, 0)
+                              : launch_shell_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, nullptr))) return rc;
     } else {
         k_jk_direct<<<grid_for(ctx, ctx->task_begin[4] / ctx->shard_n + 1, 128, 16), 128, 0, ctx->stream>>>(
             table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, nc, nD, tau, ctx->d_scalars, ctx->d_scalars + 1,
