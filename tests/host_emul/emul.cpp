@@ -77,113 +77,13 @@ struct HostPolicy {
     static void sync_cta() {}
     static int cta_thread() { return 0; }
     static int cta_threads() { return 1; }
-    static void atomic_add(double* p, double v) { *p += v; }
     static void accumulate(double* M, int idx, double v, long long fix_lo) {
-        if (fix_lo == 0) { M[idx] += v; return; }
         long long h, l;
         fixed_split(v, h, l);
         long long* W = reinterpret_cast<long long*>(M);
         W[idx] += h; W[fix_lo + idx] += l;
     }
 };
-
-static double* g_fill_out = nullptr;      // non-null: the driver below runs the engine in fill mode into this dense tensor
-
-extern "C" int emul_jk_shell(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
-                             const double* ceff, int nD, const double* P, double* Jout, double* Kout, double tau, long long* stats) {
-    HostBasis B = make_basis(ncart, oz, lmn, nprim, off, exps, ceff);
-    PairTable PT;
-    build_pair_table(B, PT);
-    std::vector<double> boys, herm;
-    build_boys_table(boys);
-    build_hermite_poly_table(herm);
-    std::vector<double> aoQ(PT.npair);
-    for (int64_t a = 0; a < PT.npair; ++a) {
-        PairClass ca{PT.cls[a] & 255, (PT.cls[a] >> 8) & 255, PT.cls[a] >> 16};
-        aoQ[a] = std::sqrt(std::fabs(eri_ao_quartet(PT.pp.data() + PT.ppoff[a] * PP_DOUBLES, PT.npp[a], PT.pp.data() + PT.ppoff[a] * PP_DOUBLES,
-                                                    PT.npp[a], ca, ca, boys.data(), herm.data())));
-    }
-    ShellTab T;
-    build_shell_tab(T);
-    ShellSystem S;
-    if (!detect_shells(B, T, S)) return 1;
-    build_shell_pairs(S, T, PT, aoQ, ncart);
-    const size_t nn = (size_t)ncart * ncart;
-    std::vector<double> Pf(nD * nn), Jf(nD * nn, 0.0), Kf(nD * nn, 0.0);
-    double dmax = 0.0;
-    for (int d = 0; d < nD; ++d)
-        for (int i = 0; i < ncart; ++i)
-            for (int j = 0; j < ncart; ++j) {
-                Pf[d * nn + (size_t)i * ncart + j] = S.fnorm[i] * S.fnorm[j] * P[d * nn + (size_t)i * ncart + j];
-                dmax = std::max(dmax, std::fabs(P[d * nn + (size_t)i * ncart + j]));
-            }
-    std::vector<double> Psym(nD * nn);
-    for (int d = 0; d < nD; ++d)
-        for (int i = 0; i < ncart; ++i)
-            for (int j = 0; j < ncart; ++j) Psym[d * nn + (size_t)i * ncart + j] = Pf[d * nn + (size_t)i * ncart + j] + Pf[d * nn + (size_t)j * ncart + i];
-    ShellData D;
-    D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
-    D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data();
-    D.eri_out = g_fill_out; D.fnorm = S.fnorm.data(); D.fix_lo = 0;
-    long long nitems_total = 0, nskipped = 0;
-    const int ncls = (int)S.classes.size();
-    for (int cb = 0; cb < ncls; ++cb)
-        for (int ck = 0; ck <= cb; ++ck) {
-            ShellJob J;
-            J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
-            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.dbg_skip = 0; J.chunk = 4; J.fill = g_fill_out ? 1 : 0;
-            J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
-            std::vector<long long> prefix;
-            J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
-            J.item_prefix = prefix.data(); J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
-            ClassTablesHost CTH;
-            const char* eb = getenv("TUNA_EMUL_IT_BUDGET");      // small budgets force the multi-chunk path in tests
-            if (eb) build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH, atoi(eb), atoi(eb), g_fill_out != nullptr); else build_class_tables(T, J.La, J.Lb, J.Lc, J.Ld, CTH, SH_IT_BUDGET, SH_S_BUDGET, g_fill_out != nullptr);
-            J.ct = class_tables_view(CTH, HostPtrOf());
-            shell_job_layout(J, nD);
-            const char* enb = getenv("TUNA_EMUL_NB");             // quartets batched per group (1, 2 or 4)
-            const int NBATCH = enb ? atoi(enb) : 2;
-#ifdef TUNA_SHELL_WIDE_TERMS
-            const std::vector<unsigned> wide = scale_wide_terms(CTH.p5wide, NBATCH, J.oP - J.oIt);
-            J.ct.p5w = wide.data();
-#endif
-            std::vector<double> sm((size_t)4 * J.total);
-            bool act[4] = {false, false, false, false};
-            int ABs[4] = {0, 0, 0, 0}, CDs[4] = {0, 0, 0, 0}, nb = 0;
-            double ws[4] = {0.0, 0.0, 0.0, 0.0};
-            auto run_batch = [&]() {
-                if (nb == 0) return;
-                if (NBATCH == 4) shell_quartets<HostPolicy, 4>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
-                else if (NBATCH == 2) shell_quartets<HostPolicy, 2>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
-                else shell_quartets<HostPolicy, 1>(J, D, act, ABs, CDs, ws, sm.data(), nD, Pf.data(), Psym.data(), Jf.data(), Kf.data(), ncart);
-                act[0] = act[1] = act[2] = act[3] = false;
-                nb = 0;
-            };
-            for (long long item = 0; item < J.nitems; ++item) {
-                int ib, ik;
-                shell_item_decode(J, item, ib, ik);
-                const int AB = J.bra_list[ib], CD = J.ket_list[ik];
-                if (tau > 0.0 && S.pairQ[AB] * S.pairQ[CD] * dmax < tau) { ++nskipped; continue; }
-                double w = 1.0;
-                if (S.pairA[AB] == S.pairB[AB]) w *= 0.5;
-                if (S.pairA[CD] == S.pairB[CD]) w *= 0.5;
-                if (AB == CD) w *= 0.5;
-                act[nb] = true; ABs[nb] = AB; CDs[nb] = CD; ws[nb] = w;
-                if (++nb == NBATCH) run_batch();
-            }
-            run_batch();
-            nitems_total += J.nitems;
-        }
-    for (int d = 0; d < nD; ++d)
-        for (int i = 0; i < ncart; ++i)
-            for (int j = 0; j < ncart; ++j) {
-                const double ff = S.fnorm[i] * S.fnorm[j];
-                Jout[d * nn + (size_t)i * ncart + j] = ff * (Jf[d * nn + (size_t)i * ncart + j] + Jf[d * nn + (size_t)j * ncart + i]);
-                Kout[d * nn + (size_t)i * ncart + j] = ff * (Kf[d * nn + (size_t)i * ncart + j] + Kf[d * nn + (size_t)j * ncart + i]);
-            }
-    if (stats) { stats[0] = (long long)S.shells.size(); stats[1] = (long long)S.pairA.size(); stats[2] = nitems_total; stats[3] = nskipped; stats[4] = ncls; }
-    return 0;
-}
 
 // ---- generation-4 engine (shell4.cuh) with the serial HostPolicy: same driver, same conventions ---------------------------
 extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
@@ -221,13 +121,10 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
     ShellData D;
     D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
     D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data();
-    D.eri_out = nullptr; D.fnorm = S.fnorm.data();
-    // TUNA_EMUL_FIXED=1: the reproducible integer accumulation (fixed_split) instead of FP64 adds
-    const bool fixed = getenv("TUNA_EMUL_FIXED") && atoi(getenv("TUNA_EMUL_FIXED")) != 0;
-    std::vector<long long> Jw, Kw;
-    double* Jacc = Jf.data(); double* Kacc = Kf.data();
-    D.fix_lo = 0;
-    if (fixed) { Jw.assign(2 * nD * nn, 0); Kw.assign(2 * nD * nn, 0); Jacc = reinterpret_cast<double*>(Jw.data()); Kacc = reinterpret_cast<double*>(Kw.data()); D.fix_lo = (long long)(nD * nn); }
+    // J/K accumulate as (high, low) 64-bit integer words (fixed_split), exactly as on the device
+    std::vector<long long> Jw(2 * nD * nn, 0), Kw(2 * nD * nn, 0);
+    double* Jacc = reinterpret_cast<double*>(Jw.data()); double* Kacc = reinterpret_cast<double*>(Kw.data());
+    D.fix_lo = (long long)(nD * nn);
     long long nitems_total = 0, nskipped = 0, nint_total = 0, nterm_total = 0;
     const int ncls = (int)S.classes.size();
     for (int cb = 0; cb < ncls; ++cb)
@@ -282,8 +179,7 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
             run_batch();
             nitems_total += J.nitems; nint_total += CH.nint; nterm_total += CH.nterms;
         }
-    if (fixed)
-        for (size_t x = 0; x < (size_t)nD * nn; ++x) { Jf[x] = fixed_value(Jw[x], Jw[nD * nn + x]); Kf[x] = fixed_value(Kw[x], Kw[nD * nn + x]); }
+    for (size_t x = 0; x < (size_t)nD * nn; ++x) { Jf[x] = fixed_value(Jw[x], Jw[nD * nn + x]); Kf[x] = fixed_value(Kw[x], Kw[nD * nn + x]); }
     for (int d = 0; d < nD; ++d)
         for (int i = 0; i < ncart; ++i)
             for (int j = 0; j < ncart; ++j) {
@@ -293,16 +189,6 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
             }
     if (stats) { stats[0] = (long long)S.shells.size(); stats[1] = (long long)S.pairA.size(); stats[2] = nitems_total; stats[3] = nskipped; stats[4] = ncls; stats[5] = nint_total; stats[6] = nterm_total; }
     return 0;
-}
-
-// Dense Cartesian tensor through the shell engine's fill mode (out must be zero-initialised, ncart^4 doubles).
-extern "C" int emul_fill_shell(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
-                               const double* ceff, double* out) {
-    std::vector<double> P((size_t)ncart * ncart, 0.0), Jd((size_t)ncart * ncart), Kd((size_t)ncart * ncart);
-    g_fill_out = out;
-    const int rc = emul_jk_shell(ncart, oz, lmn, nprim, off, exps, ceff, 1, P.data(), Jd.data(), Kd.data(), 0.0, nullptr);
-    g_fill_out = nullptr;
-    return rc;
 }
 
 // ---- one-electron integrals (oneel_core.cuh), serial on the CPU ------------------------------------------------------

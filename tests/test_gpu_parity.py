@@ -35,14 +35,9 @@ def test_h2_known_answers(tb, oracle):
         assert abs(ctx.eri_single(*idx) - val) < 1e-12
 
 
-@pytest.mark.parametrize("engine", ["", "shell", "generic"])
 @pytest.mark.parametrize("name", ["n2_ccpvtz", "co_b3lyp_ccpvtz", "et100"])
-def test_eri_cart_vs_oracle(tb, oracle, name, engine, monkeypatch):
-    """Dense Cartesian tensor by both fill engines (shell-quartet engine in fill mode / per-component kernel) and by the default choice."""
-    if engine:
-        monkeypatch.setenv("TUNA_B200_FILL_ENGINE", engine)
-    else:
-        monkeypatch.delenv("TUNA_B200_FILL_ENGINE", raising=False)
+def test_eri_cart_vs_oracle(tb, oracle, name):
+    """Dense Cartesian tensor (k_eri_fill) against the oracle and the reference's own recorded values."""
     g = load_golden(name)
     ctx = context_for(g)
     ctx.eri_fill_cart()

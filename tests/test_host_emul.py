@@ -12,10 +12,7 @@ from util import load_golden, oracle_basis
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-# "" = the shipped kernel body; the other entries are the development variants kept behind compile-time macros (off in the
-# default build of libtuna_b200.so): their tables and device code are checked here on the CPU before they are ever timed on a GPU.
-VARIANTS = {"": [], "wide_terms": ["-DTUNA_SHELL_WIDE_TERMS"], "asm_unroll": ["-DTUNA_SHELL_ASM_UNROLL"],
-            "all": ["-DTUNA_SHELL_WIDE_TERMS", "-DTUNA_SHELL_ASM_UNROLL"]}
+VARIANTS = {"": []}      # the shipped kernel bodies (no compile-time variants are left)
 
 
 class LazyEmul:
@@ -43,14 +40,7 @@ def emul(request):
     return LazyEmul(request.param)
 
 
-def only_default(emul, *allowed):
-    """The development variants differ only in phases 4/5 of the shell engine: run them on the cheap engine cases."""
-    if emul.variant and allowed != ("*",):
-        pytest.skip("variant builds run the shell-engine subset only")
-
-
 def test_boys_kernel_function(emul, oracle):
-    only_default(emul)
     rng = np.random.default_rng(3)
     Ts = np.concatenate([[0.0, 1e-12, 0.03125, 39.999, 40.0, 40.001, 1e3, 3e6, 1e13], rng.uniform(0, 45, 200), 10 ** rng.uniform(-6, 6, 100)])
     worst = 0.0
@@ -65,7 +55,6 @@ def test_boys_kernel_function(emul, oracle):
 
 @pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "et100"])
 def test_quartet_math_vs_oracle(emul, oracle, name):
-    only_default(emul)
     g = load_golden(name)
     fb = oracle_basis(oracle, g)
     n = fb.ncart
@@ -83,14 +72,11 @@ def test_quartet_math_vs_oracle(emul, oracle, name):
     assert np.array_equal(out == 0.0, ref == 0.0)
 
 
-ENGINES = {"gen2": "emul_jk_shell", "gen4": "emul_jk_shell4"}
+ENGINES = {"gen4": "emul_jk_shell4"}
 
 
 def engine_entry(emul, gen):
-    """The serial CPU build of the engine body: shell_jk.cuh (generation 2, still the dense-fill engine) or shell4.cuh (generation 4,
-    the default direct engine).  The compile-time variants only exist for generation 2."""
-    if gen == "gen4" and emul.variant:
-        pytest.skip("variant builds concern generation 2 only")
+    """The serial CPU build of the engine body (shell4.cuh: same source as the sm_100a kernel, HostPolicy instead of DevPolicy)."""
     return getattr(emul, ENGINES[gen])
 
 
@@ -99,8 +85,6 @@ def engine_entry(emul, gen):
 def test_shell_engine_vs_oracle(emul, oracle, name, gen):
     """shell_jk.cuh (the direct-mode engine) run serially on the CPU: J/K for two symmetric densities vs the oracle's
     einsums over the oracle's Cartesian tensor, with and without Schwarz screening."""
-    if emul.variant and name == "n2_ccpvtz":
-        pytest.skip("variant builds run the shell-engine subset only")
     g = load_golden(name)
     fb = oracle_basis(oracle, g)
     n = fb.ncart
@@ -125,7 +109,7 @@ def test_shell_engine_vs_oracle(emul, oracle, name, gen):
             assert np.abs(J[d] - Jr).max() < 1e-11 and np.abs(K[d] - Kr).max() < 1e-11
 
 
-@pytest.mark.parametrize("gen,nb,budget", [("gen2", None, None), ("gen4", None, None), ("gen4", "1", "1500"), ("gen4", "4", "700")])
+@pytest.mark.parametrize("gen,nb,budget", [("gen4", None, None), ("gen4", "1", "1500"), ("gen4", "4", "700")])
 def test_shell_engine_h_shells(emul, oracle, gen, nb, budget, monkeypatch):
     """All shell types up to H, including the multi-chunk (hh|hh) class tables, on a synthetic two-centre basis; generation 4 also with
     one and four quartets per batch and with small chunk budgets (several chunks per class, table reload)."""
@@ -156,38 +140,11 @@ def test_shell_engine_h_shells(emul, oracle, gen, nb, budget, monkeypatch):
     assert np.abs(J[0] - oracle.coulomb(P[0], E)).max() < 1e-11 and np.abs(K[0] - oracle.exchange(P[0], E)).max() < 1e-11
 
 
-@pytest.mark.parametrize("name", ["h2_631g", "n2_ccpvtz", "et100"])
-def test_shell_engine_fill_mode_vs_oracle(emul, oracle, name):
-    """Fill mode of the shell engine (dense Cartesian tensor for stored mode): element-wise against the oracle, exact zeros for
-    parity-forbidden entries, exact 8-fold symmetry (canonical quartets are scattered to their eight images)."""
-    if emul.variant and name != "h2_631g":
-        pytest.skip("variant builds run the shell-engine subset only")
-    g = load_golden(name)
-    fb = oracle_basis(oracle, g)
-    n = fb.ncart
-    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
-    oz = np.ascontiguousarray(fb.origins[:, 2])
-    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
-    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
-    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
-    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
-    out = np.zeros((n,) * 4)
-    rc = emul.emul_fill_shell(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
-                              fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), out.ctypes.data_as(dp))
-    assert rc == 0
-    ref = oracle.eri_fill(fb)
-    assert np.all(np.abs(out - ref) <= np.maximum(1e-12, 1e-13 * np.abs(ref)))
-    assert np.array_equal(out == 0.0, ref == 0.0)
-    assert np.array_equal(out, out.transpose(1, 0, 2, 3)) and np.array_equal(out, out.transpose(0, 1, 3, 2)) and np.array_equal(out, out.transpose(2, 3, 0, 1))
-
-
 @pytest.mark.parametrize("gen", list(ENGINES))
 def test_shell_engine_extreme_shells_of_the_headline_basis(emul, oracle, gen):
     """The tightest and the most diffuse shell of every angular momentum of the ET800 set (s exponent 2.1e5 ... h exponent 1.0) on both
     atoms, unit-pair densities: sampled J/K elements against single integrals of the oracle (no dense tensor needed).  The same check
     runs on the GPU at the full nbf 400 / 800 sizes (tests/test_zz_fullsize.py)."""
-    if emul.variant not in ("", "all"):
-        pytest.skip("variant builds run the shell-engine subset only")
     from tuna_b200 import workloads as w
     from tuna_b200.basis import from_arrays
     from util import check_unit_pair_jk, pick_function, unit_pair_density

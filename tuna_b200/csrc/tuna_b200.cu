@@ -78,7 +78,6 @@ struct tuna_ctx {
     double* d_Pc = nullptr; double* d_Jc = nullptr; double* d_Kc = nullptr; double* d_tmp = nullptr;  // Cartesian
     double* d_Kpart = nullptr;
     double* d_fnorm = nullptr;        // per-component norms (shell engine fill mode)
-    int shell_fill = 0;               // the cached job list was built for fill mode
     size_t cap_mat = 0, cap_cart = 0, cap_kpart = 0;
     double* h_pin = nullptr; size_t cap_pin = 0;
     unsigned long long* d_scalars = nullptr;   // [0] max|P| bits, [1] evaluated-quartet counter
@@ -94,63 +93,27 @@ struct tuna_ctx {
     ShellTab stab;
     ShellSystem ss;
     bool shell_ready = false;
-    double shell_tau = -1.0;
-    int shell_nD = -1;
     int* d_pairA = nullptr; int* d_pairB = nullptr; long long* d_pair_rec = nullptr; double* d_rec = nullptr; double* d_pairQ = nullptr;
-    int* d_sh_ao = nullptr; int* d_class_lists = nullptr; long long* d_prefix = nullptr; double* d_finv = nullptr;
+    int* d_sh_ao = nullptr; int* d_class_lists = nullptr; double* d_finv = nullptr;
     double* d_eval = nullptr;
     std::vector<size_t> class_list_off;
-    struct JobHost { ShellJob job; int G; size_t smem; double allowed; int threads, gpc, nb = 1; bool own_launch = false; };
-#ifdef TUNA_SHELL_WIDE_TERMS
-    struct ClassTabDev { ClassTablesHost host; ClassTablesDev view; unsigned char* blob = nullptr; unsigned* wide[3] = {nullptr, nullptr, nullptr}; };   // wide[log2 nb]
-#else
-    struct ClassTabDev { ClassTablesHost host; ClassTablesDev view; unsigned char* blob = nullptr; };
-#endif
-    std::map<int, ClassTabDev> class_tabs;      // key La | Lb<<4 | Lc<<8 | Ld<<12
-    std::vector<JobHost> jobs;
-    struct LaunchGroup { int G = 1, nb = 1, threads = 128, njobs = 0, ctas_per_sm = 1; long long nunits = 0; size_t smem = 0, job_slot_off = 0;
-                         ShellJob* d_jobs = nullptr; long long* d_unit_prefix = nullptr; };
-    std::vector<LaunchGroup> groups;      // one launch per group size G covers all class jobs with that G
     static constexpr int NAUX = 6;
-    cudaStream_t aux[NAUX] = {};     // class jobs of one build are independent (atomic accumulation): one launch per group size, each on its own stream
+    cudaStream_t aux[NAUX] = {};     // class jobs of one build are independent (integer-atomic accumulation): launches are dealt round-robin to these streams
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     // generation-4 shell engine (shell4.cuh): per-class tables and the job list; the pair data above is shared
     struct ClassTab4Dev { Class4Host host; Class4Dev view; unsigned char* blob = nullptr; };
     struct Job4Host { Shell4Job job; int G = 1, threads = 128, gpc = 1, nb = 1; size_t smem = 0; int tab_off = 0, hdr_off = 0; double allowed = 0; };
     std::map<int, ClassTab4Dev> class_tabs4;     // key La | Lb<<4 | Lc<<8 | Ld<<12 | nD<<16
-    std::vector<Job4Host> jobs4;
-    double shell4_tau = -1.0;
-    int shell4_nD = -1;
+    // job lists are cached per (threshold, densities per pass, rank count): a build with nD = 5 runs passes of 2, 2 and 1 densities, and
+    // direct SCF alternates between thresholds rarely - none of that may rebuild lists or reallocate inside a Fock build
+    struct JobSet4 { double tau = -1.0; int nD = 0, shard_n = 0; std::vector<Job4Host> jobs; long long* d_prefix = nullptr; };
+    std::vector<JobSet4> jobsets4;
+    int cur_jobset4 = -1;
     long long* d_fix = nullptr; size_t cap_fix = 0;      // reproducible accumulation: [J hi | J lo | K hi | K lo], nD * ncart^2 words each
-    bool deterministic = true;      // order-independent integer accumulation of J/K in the generation-4 engine (TUNA_B200_DETERMINISTIC=0: FP64 atomics)
-    int engine_gen = 4;             // 4 = shell4.cuh (default), 2 = shell_jk.cuh (TUNA_B200_ENGINE=2; also serves the dense fill)
     CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
     int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
 
-    // CUDA-graph replay of a direct J/K pass (TUNA_B200_GRAPH=1; off by default, NOT yet run on a GPU): small systems are bound by
-    // the ~240 launches of a build (nbf 100: 0.78 ms for 24 us of algorithmic work).  The first call with a given argument set runs
-    // normally (module attributes, allocations, job lists), the second is captured - fork/join over the auxiliary streams included -
-    // and every later one is a single cudaGraphLaunch.
-    struct GraphKey {
-        int nD = 0; const double* dP = nullptr; unsigned anti = 0; double* dJ = nullptr; double* dK = nullptr; double tau = 0.0;
-        int srank = 0, sn = 1; unsigned long long epoch = 0;
-        bool operator==(const GraphKey& o) const {
-            return nD == o.nD && dP == o.dP && anti == o.anti && dJ == o.dJ && dK == o.dK && tau == o.tau && srank == o.srank && sn == o.sn && epoch == o.epoch;
-        }
-    };
-    struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
-    bool graph_mode = false, capturing = false, warm_valid = false;
-    GraphKey warm_key;
-    std::vector<GraphEntry> graphs;
-    unsigned long long shell_epoch = 0;      // bumped whenever the job list / pair data behind a captured pass may have changed
 };
-
-static void drop_graphs(tuna_ctx* ctx) {
-    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-    ctx->graphs.clear();
-    ctx->warm_valid = false;
-    ctx->shell_epoch++;
-}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -170,7 +133,6 @@ static void drop_graphs(tuna_ctx* ctx) {
     catch (...) { if (ctx) ctx->err = "internal error"; return TUNA_ERR_STATE; }
 
 static int check_pair_symmetry(tuna_ctx* ctx);
-static int shell_fill(tuna_ctx* ctx);
 
 // Opt-in to more than 48 KB of dynamic shared memory.  The attribute is PER DEVICE (a process may hold contexts on several GPUs), so the
 // "already done" flag is a bit per device ordinal, one flag word per kernel instantiation.
@@ -815,12 +777,8 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters, doub
     if (s == 123.456) out[0] = s;
 }
 
-// ---- shell-quartet engine launch wrapper -----------------------------------------------------------------------
-#ifndef TUNA_SHELL_REGS
-#define TUNA_SHELL_REGS 64
-#endif
-#define TUNA_SHELL_MINB(threads) (65536 / ((threads) * TUNA_SHELL_REGS))
-constexpr int SHELL_ITEMS_PER_GROUP = 4;   // a CTA work unit (= multi-GPU sharding unit) is 4 consecutive shell quartets per group
+// ---- shell-quartet engine (shell4.cuh) ------------------------------------------------------------------------------------
+constexpr int SHELL_ITEMS_PER_GROUP = 4;   // smallest CTA work unit (= multi-GPU sharding unit): shell quartets per group
 
 template <int GG>
 struct DevPolicy {
@@ -834,10 +792,8 @@ struct DevPolicy {
     __device__ __forceinline__ static void sync_cta() { __syncthreads(); }
     __device__ __forceinline__ static int cta_thread() { return threadIdx.x; }
     __device__ __forceinline__ static int cta_threads() { return blockDim.x; }
-    __device__ __forceinline__ static void atomic_add(double* p, double v) { atomicAdd(p, v); }
-    // M[idx] += v: FP64 atomic (fix_lo == 0) or the order-independent two-word integer accumulation of fixed_split
+    // M[idx] += v as the order-independent two-word integer accumulation of fixed_split (no floating-point atomics in the engine)
     __device__ __forceinline__ static void accumulate(double* M, int idx, double v, long long fix_lo) {
-        if (fix_lo == 0) { atomicAdd(M + idx, v); return; }
         long long h, l;
         fixed_split(v, h, l);
         unsigned long long* W = reinterpret_cast<unsigned long long*>(M);
@@ -845,136 +801,6 @@ struct DevPolicy {
         if (l != 0) atomicAdd(W + fix_lo + idx, (unsigned long long)l);
     }
 };
-
-// One group of G lanes per shell quartet.  A launch covers ALL class jobs that use this group size: the work units
-// (job, chunk of J.chunk consecutive shell quartets) of those jobs form one flat list (heaviest jobs first) that the CTAs
-// walk with a grid stride; units are dealt round-robin to ranks (multi-GPU sharding).  The job descriptor of
-// the current unit is copied into shared memory; the bra position of the unit's first item is found once by binary search,
-// the others by walking the per-bra prefix.
-template <int GG, int NB>
-__global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 128) ? GG : 128)) k_shell_jk(const ShellJob* __restrict__ jobs, const long long* __restrict__ unit_prefix,
-                                                                     int njobs, ShellData D, int nD, const double* __restrict__ Pf,
-                                                                     const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
-                                                                     double tau, const unsigned long long* scalars, double* evaluated,
-                                                                     int rank, int nranks, size_t job_slot_off) {
-    extern __shared__ double smem_all[];
-    ShellJob& J = *reinterpret_cast<ShellJob*>(smem_all + job_slot_off);          // behind the group slices
-    int& s_ib0 = *reinterpret_cast<int*>(smem_all + job_slot_off + (sizeof(ShellJob) + 7) / 8);
-    const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
-    const double dmax = __longlong_as_double((long long)scalars[0]);
-    const long long nunits = unit_prefix[njobs];
-    double done = 0.0;
-    for (long long u = (long long)blockIdx.x * nranks + rank; u < nunits; u += (long long)gridDim.x * nranks) {
-        int lo = 0, hi = njobs;                         // job of this unit (uniform in the CTA)
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (unit_prefix[mid] <= u) lo = mid; else hi = mid;
-        }
-        __syncthreads();                                // previous unit is done with J / s_ib0
-        {
-            const int* src = reinterpret_cast<const int*>(jobs + lo);
-            int* dst = reinterpret_cast<int*>(&J);
-            for (int x = threadIdx.x; x < (int)(sizeof(ShellJob) / sizeof(int)); x += blockDim.x) dst[x] = src[x];
-        }
-        __syncthreads();
-        const long long CH = J.chunk;
-        const long long first = (u - unit_prefix[lo]) * CH;
-        if (threadIdx.x == 0) {
-            int ib, ik;
-            shell_item_decode(J, first, ib, ik);
-            s_ib0 = ib;
-        }
-        __syncthreads();
-        const int ib0 = s_ib0;
-        double* sm = smem_all + (size_t)gid * NB * J.total;
-        for (int k0 = 0; k0 < (int)CH; k0 += gpc * NB) {
-            bool active[NB];
-            int AB[NB], CD[NB];
-            double w[NB];
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const int kk = k0 + gid * NB + q;
-                const long long item = first + kk;
-                active[q] = kk < (int)CH && item < J.nitems;
-                AB[q] = 0; CD[q] = 0; w[q] = 1.0;
-                if (active[q]) {
-                    int ib = ib0;
-                    while (J.item_prefix[ib + 1] <= item) ++ib;
-                    AB[q] = J.bra_list[ib]; CD[q] = J.ket_list[(int)(item - J.item_prefix[ib])];
-                    if (tau > 0.0 && D.pairQ[AB[q]] * D.pairQ[CD[q]] * dmax < tau) active[q] = false;
-                    const bool ab = D.pairA[AB[q]] == D.pairB[AB[q]], cd = D.pairA[CD[q]] == D.pairB[CD[q]], dg = AB[q] == CD[q];
-                    if (ab) w[q] *= 0.5;
-                    if (cd) w[q] *= 0.5;
-                    if (dg) w[q] *= 0.5;
-                    if (active[q] && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
-                }
-            }
-            shell_quartets<DevPolicy<GG>, NB>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
-        }
-    }
-    if (done != 0.0) atomicAdd(evaluated, done);
-}
-
-// Single-job variant: the job descriptor travels as a kernel parameter (constant bank / uniform registers instead of shared
-// memory), which is ~25 % faster per quartet; used for class jobs large enough to fill the GPU on their own.
-#ifdef TUNA_SHELL_REG_TIERS
-// Development variant (off by default): a second instantiation with a 128-register budget for class jobs whose shared-memory
-// footprint already limits the SM to few CTAs, so the extra registers cost no occupancy (the 64-register build spills 144 bytes
-// and rematerialises addresses in the hot loops).
-template <int GG, int NB, int REGS>
-__global__ void __launch_bounds__((GG > 128) ? GG : 128, 65536 / (((GG > 128) ? GG : 128) * REGS)) k_shell_jk_one(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
-#else
-template <int GG, int NB>
-__global__ void __launch_bounds__((GG > 128) ? GG : 128, TUNA_SHELL_MINB((GG > 128) ? GG : 128)) k_shell_jk_one(ShellJob J, ShellData D, int nD, const double* __restrict__ Pf,
-#endif
-                                                                         const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
-                                                                         double tau, const unsigned long long* scalars, double* evaluated,
-                                                                         int rank, int nranks) {
-    extern __shared__ double smem_all[];
-    const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
-    int& s_ib0 = *reinterpret_cast<int*>(smem_all + (size_t)gpc * NB * J.total);
-    double* sm = smem_all + (size_t)gid * NB * J.total;
-    const double dmax = __longlong_as_double((long long)scalars[0]);
-    const long long CH = J.chunk;
-    const long long nchunk = (J.nitems + CH - 1) / CH;
-    double done = 0.0;
-    for (long long gc = (long long)blockIdx.x * nranks + rank; gc < nchunk; gc += (long long)gridDim.x * nranks) {
-        const long long first = gc * CH;
-        if (threadIdx.x == 0) {
-            int ib, ik;
-            shell_item_decode(J, first, ib, ik);
-            s_ib0 = ib;
-        }
-        __syncthreads();
-        const int ib0 = s_ib0;
-        __syncthreads();
-        for (int k0 = 0; k0 < (int)CH; k0 += gpc * NB) {
-            bool active[NB];
-            int AB[NB], CD[NB];
-            double w[NB];
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const int kk = k0 + gid * NB + q;
-                const long long item = first + kk;
-                active[q] = kk < (int)CH && item < J.nitems;
-                AB[q] = 0; CD[q] = 0; w[q] = 1.0;
-                if (active[q]) {
-                    int ib = ib0;
-                    while (J.item_prefix[ib + 1] <= item) ++ib;
-                    AB[q] = J.bra_list[ib]; CD[q] = J.ket_list[(int)(item - J.item_prefix[ib])];
-                    if (tau > 0.0 && D.pairQ[AB[q]] * D.pairQ[CD[q]] * dmax < tau) active[q] = false;
-                    const bool ab = D.pairA[AB[q]] == D.pairB[AB[q]], cd = D.pairA[CD[q]] == D.pairB[CD[q]], dg = AB[q] == CD[q];
-                    if (ab) w[q] *= 0.5;
-                    if (cd) w[q] *= 0.5;
-                    if (dg) w[q] *= 0.5;
-                    if (active[q] && (threadIdx.x & (GG - 1)) == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
-                }
-            }
-            shell_quartets<DevPolicy<GG>, NB>(J, D, active, AB, CD, w, sm, nD, Pf, Psym, Jf, Kf, ncart);
-        }
-    }
-    if (done != 0.0) atomicAdd(evaluated, done);
-}
 
 // ---- generation-4 engine: one class job per launch, the descriptor travels as a kernel parameter ------------------------------
 // A CTA work unit (= multi-GPU sharding unit) is J.chunk consecutive shell quartets; the unit's quartets are decoded ONCE (item ->
@@ -1165,7 +991,6 @@ static int ensure_mats(tuna_ctx* ctx, int nD, int n, int ncart) {
     int rc;
     const size_t need = (size_t)nD * n * n;
     if (need > ctx->cap_mat) {
-        drop_graphs(ctx);       // captured passes hold these buffers
         if ((rc = dev_alloc(ctx, &ctx->d_P, need))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_J, need))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_K, need))) return rc;
@@ -1173,7 +998,6 @@ static int ensure_mats(tuna_ctx* ctx, int nD, int n, int ncart) {
     }
     const size_t needc = (size_t)nD * ncart * ncart;
     if (ncart > 0 && needc > ctx->cap_cart) {
-        drop_graphs(ctx);
         if ((rc = dev_alloc(ctx, &ctx->d_Pc, needc))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_Jc, needc))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_Kc, needc))) return rc;
@@ -1249,7 +1073,6 @@ int tuna_ctx_create(int device, tuna_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    { const char* g = getenv("TUNA_B200_GRAPH"); ctx->graph_mode = g && atoi(g) == 1; }
     for (int w = 0; w < 6; ++w)
         for (int s = 0; s < 2; ++s) CK(cudaEventCreate(&ctx->ev[w][s]));
     for (int a = 0; a < tuna_ctx::NAUX; ++a) {
@@ -1282,21 +1105,16 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->d_eri_cart); dev_free(&ctx->d_eri_sph);
     dev_free(&ctx->d_P); dev_free(&ctx->d_J); dev_free(&ctx->d_K);
     dev_free(&ctx->d_Pc); dev_free(&ctx->d_Jc); dev_free(&ctx->d_Kc); dev_free(&ctx->d_tmp); dev_free(&ctx->d_Kpart);
-    for (auto& kv : ctx->class_tabs) dev_free(&kv.second.blob);
     for (auto& kv : ctx->class_tabs4) dev_free(&kv.second.blob);
     dev_free(&ctx->d_fix);
-#ifdef TUNA_SHELL_WIDE_TERMS
-    for (auto& kv : ctx->class_tabs) for (int w = 0; w < 3; ++w) dev_free(&kv.second.wide[w]);
-#endif
-    for (auto& g : ctx->groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
     dev_free(&ctx->d_pairA); dev_free(&ctx->d_pairB); dev_free(&ctx->d_pair_rec); dev_free(&ctx->d_rec);
-    dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_prefix); dev_free(&ctx->d_finv); dev_free(&ctx->d_fnorm);
+    dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_finv);
+    for (auto& js : ctx->jobsets4) dev_free(&js.d_prefix); dev_free(&ctx->d_fnorm);
     dev_free(&ctx->d_eval);
     dev_free(&ctx->Uf.rowptr); dev_free(&ctx->Uf.col); dev_free(&ctx->Uf.val);
     dev_free(&ctx->Uft.rowptr); dev_free(&ctx->Uft.col); dev_free(&ctx->Uft.val);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     dev_free(&ctx->d_mo_ws[0]); dev_free(&ctx->d_mo_ws[1]);
-    drop_graphs(ctx);
     for (int w = 0; w < 6; ++w)
         for (int s = 0; s < 2; ++s) if (ctx->ev[w][s]) cudaEventDestroy(ctx->ev[w][s]);
     for (int a = 0; a < tuna_ctx::NAUX; ++a) {
@@ -1322,7 +1140,6 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     if (!ctx) return TUNA_ERR_ARG;
     if (ncart <= 0 || !origins_z || !lmn || !nprim || !prim_offset || !exps || !coef_eff) FAIL(TUNA_ERR_ARG, "tuna_set_basis: null or empty basis");
     CK(cudaSetDevice(ctx->device));
-    drop_graphs(ctx);
     HostBasis& B = ctx->hb;
     B = HostBasis();
     B.ncart = ncart;
@@ -1357,15 +1174,12 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     ctx->nbf = 0;
     build_shell_tab(ctx->stab);
     ctx->shell_ready = false;
-    ctx->jobs.clear();
-    ctx->jobs4.clear();
+    for (auto& js : ctx->jobsets4) dev_free(&js.d_prefix);
+    ctx->jobsets4.clear();
+    ctx->cur_jobset4 = -1;
     detect_shells(ctx->hb, ctx->stab, ctx->ss);     // ss.ok == false -> direct mode uses the per-component kernel
     const char* eng = getenv("TUNA_B200_DIRECT_ENGINE");
     ctx->direct_engine = (eng && std::string(eng) == "generic") ? 0 : 1;
-    const char* gen = getenv("TUNA_B200_ENGINE");
-    ctx->engine_gen = (gen && atoi(gen) == 2) ? 2 : 4;
-    const char* det = getenv("TUNA_B200_DETERMINISTIC");
-    ctx->deterministic = !(det && atoi(det) == 0);
     return TUNA_OK;
 } TUNA_CATCH
 
@@ -1374,7 +1188,6 @@ int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U) try {
     if (ctx->ncart == 0) FAIL(TUNA_ERR_STATE, "tuna_set_transform: call tuna_set_basis first");
     if (nbf <= 0 || !U) FAIL(TUNA_ERR_ARG, "tuna_set_transform: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    drop_graphs(ctx);
     const int nc = ctx->ncart;
     std::vector<double> u(U, U + (size_t)nbf * nc), ut((size_t)nc * nbf);
     for (int p = 0; p < nbf; ++p)
@@ -1409,18 +1222,6 @@ int tuna_eri_fill_cart(tuna_ctx* ctx) try {
     if ((rc = ensure_pairs(ctx))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_eri_cart, count))) return rc;
     CK(cudaMemsetAsync(ctx->d_eri_cart, 0, count * sizeof(double), ctx->stream));
-    // Shell-quartet engine in fill mode (Boys / R / convolution tables shared by all components of a shell quartet) when the basis
-    // groups into full shells; the per-component kernel otherwise (or with TUNA_B200_FILL_ENGINE=generic).
-    // (The engine also walks the primitive quartets of a shell quartet serially, four barriers each: heavily contracted shells such
-    // as (ss|ss) of cc-pVTZ with 4096 primitive quartets are better served by the per-component kernel, which spreads them over a warp.)
-    const char* fe = getenv("TUNA_B200_FILL_ENGINE");
-    // Measured (B200): the fill is bound by the scattered 8-byte stores of the eight images, not by the integral math - ET100 1.42 ms
-    // (engine) vs 1.39 ms (per-component kernel), N2/cc-pVTZ 15.8 vs 3.8 ms - so the per-component kernel stays the default.
-    const bool want_shell = fe && std::string(fe) == "shell";
-    if (ctx->direct_engine == 1 && ctx->ss.ok && want_shell) {
-        if ((rc = shell_fill(ctx))) return rc;
-        return TUNA_OK;
-    }
     CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
     k_eri_fill<<<grid_for(ctx, ctx->task_begin[4], 128, 16), 128, 0, ctx->stream>>>(table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_eri_cart, ctx->ncart);
     ctx->launches++;
@@ -1782,7 +1583,6 @@ int tuna_jk_stored(tuna_ctx* ctx, int nD, const double* P, double* J, double* K)
 int tuna_set_shard(tuna_ctx* ctx, int rank, int nranks) {
     if (!ctx) return TUNA_ERR_ARG;
     if (nranks < 1 || rank < 0 || rank >= nranks) FAIL(TUNA_ERR_ARG, "tuna_set_shard: bad rank / nranks");
-    if (ctx->shard_n != nranks) { ctx->shell_tau = -1.0; ctx->shell4_tau = -1.0; }      // work-unit sizes / the big-small job split depend on the rank count
     ctx->shard_rank = rank; ctx->shard_n = nranks;
     return TUNA_OK;
 }
@@ -2056,93 +1856,7 @@ int tuna_cross_overlap(tuna_ctx* ctx, int n1, const double* oz1, const int32_t* 
 
 }  // extern "C"
 
-// Per-class work tables: built on the host once per angular class and kept on the device in one blob.
-// Shared-memory doubles of one group that do not depend on the chunking (everything except the S slice and the It buffer).
-static int shell_fixed_doubles(const ShellTab& T, int La, int Lb, int Lc, int Ld, int nD) {
-    const int Lab = La + Lb, Lcd = Lc + Ld, Ltot = Lab + Lcd, NS = Ltot / 2 + 1, NGZ = (Lc + 1) * (Ld + 1);
-    const int nout = T.nc[La] * T.nc[Lc] + T.nc[La] * T.nc[Ld] + T.nc[Lb] * T.nc[Lc] + T.nc[Lb] * T.nc[Ld] + T.nc[La] * T.nc[Lb] + T.nc[Lc] * T.nc[Ld];
-    return 2 * (Ltot + 1) + (Ltot + 1) * NS + (Lab + 1) * (Lcd + 1) * NS + (Lab + 1) * NGZ * NS + 2 * nD * nout + sp_rec_size(La, Lb) + sp_rec_size(Lc, Ld) + 64;
-}
-constexpr int SHELL_SMEM_DOUBLES = 26500;      // 207 KB of the 227 KB a CTA may use
-
-static int get_class_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int nD, bool fill, tuna_ctx::ClassTabDev** out) {
-    const int key = La | Lb << 4 | Lc << 8 | Ld << 12 | nD << 16 | (fill ? 1 << 24 : 0);
-    auto it = ctx->class_tabs.find(key);
-    if (it != ctx->class_tabs.end()) { *out = &it->second; return TUNA_OK; }
-    tuna_ctx::ClassTabDev& E = ctx->class_tabs[key];
-    {
-        const char* eb = getenv("TUNA_B200_IT_BUDGET");
-        const char* es = getenv("TUNA_B200_S_BUDGET");
-        int itb = eb ? atoi(eb) : SH_IT_BUDGET, sb = es ? atoi(es) : SH_S_BUDGET;
-        const int avail = SHELL_SMEM_DOUBLES - shell_fixed_doubles(ctx->stab, La, Lb, Lc, Ld, nD);     // shrink the chunks for big classes
-        if (itb + sb + 2 > avail) { itb = std::max(64, (avail - 2) / 2); sb = std::max(64, avail - 2 - itb); }
-        build_class_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb, fill);
-        // Occupancy tier: a class whose single-quartet slice lands between half and all of the SM's shared memory runs ONE 8-warp CTA
-        // per SM (21 % issue utilisation measured); if splitting the bra z rows into two chunks brings the slice under half, two CTAs
-        // fit (34 %) at the price of running the chunk-independent phases 0-2 twice.
-        const char* et = getenv("TUNA_B200_TIER2");
-        if (!(et && atoi(et) == 0)) {
-            auto slice_doubles = [&](const ClassTablesHost& C) {
-                ShellJob Jt;
-                Jt.La = La; Jt.Lb = Lb; Jt.Lc = Lc; Jt.Ld = Ld;
-                Jt.ct.smax_rows = C.smax_rows; Jt.ct.itmax = C.itmax; Jt.ct.nout = C.nout;
-                shell_job_layout(Jt, nD);
-                return Jt.total;
-            };
-            const int tier2 = (225 * 1024 / 2 - 1024 - 64) / 8;            // doubles per CTA so that two CTAs (+1 KB reserved each) fit
-            const int t0 = slice_doubles(E.host);
-            if (t0 > tier2) {
-                const int NGZ = (Lc + 1) * (Ld + 1), NS = (La + Lb + Lc + Ld) / 2 + 1;
-                const int nch0 = (int)E.host.chunk_bz0.size() - 1, nint0 = E.host.nint;
-                bool found = false;
-                for (int want = 2; want <= std::min(4, nch0 + 2) && !found; ++want)        // balanced cuts, fewest chunks first
-                    for (int pct = 100 / want + 2; pct <= 100 / want + 30 / want + 2 && !found; pct += 3) {      // integrals per bra z row are not uniform
-                        ClassTablesHost trial;
-                        build_class_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, (nint0 * pct) / 100), (La + 1) * (Lb + 1) * NGZ * NS, fill);
-                        if ((int)trial.chunk_bz0.size() - 1 == want && slice_doubles(trial) <= tier2) { E.host = trial; found = true; }
-                    }
-            }
-        }
-    }
-    const ClassTablesHost& C = E.host;
-    size_t total = 0;
-    auto reserve = [&](size_t bytes) { size_t o = total; total += (bytes + 15) & ~(size_t)15; return o; };
-    struct Piece { const void* src; size_t bytes, off; };
-    std::vector<Piece> pieces;
-    auto add = [&](const void* src, size_t bytes) { pieces.push_back({src, bytes, reserve(bytes)}); return pieces.back().off; };
-    const size_t o_bz0 = add(C.chunk_bz0.data(), C.chunk_bz0.size() * 4), o_e0 = add(C.chunk_e0.data(), C.chunk_e0.size() * 4);
-    const size_t o_s0 = add(C.chunk_s0.data(), C.chunk_s0.size() * 4), o_p4 = add(C.p4.data(), C.p4.size() * 4);
-    const size_t o_ptr = add(C.p5ptr.data(), C.p5ptr.size() * 4), o_term = add(C.p5term.data(), C.p5term.size() * 4);
-    const size_t o_off = add(C.p5off.data(), C.p5off.size() * 4), o_pmap = add(C.pmap.data(), C.pmap.size() * 2);
-    const size_t o_omap = add(C.omap.data(), C.omap.size() * 2), o_rt = add(C.t_rt.data(), C.t_rt.size() * 4);
-    const size_t o_xy = add(C.t_xy.data(), C.t_xy.size() * 4), o_u = add(C.t_u.data(), C.t_u.size() * 4), o_s = add(C.t_s.data(), C.t_s.size() * 4);
-    const size_t o_jp = add(C.jst_ptr.data(), C.jst_ptr.size() * 4), o_jl = add(C.jst_list.data(), C.jst_list.size() * 2), o_jf = add(C.jflush.data(), C.jflush.size() * 4);
-    const size_t o_p6 = add(C.p6.data(), C.p6.size() * 4), o_f0 = add(C.chunk_f0.data(), C.chunk_f0.size() * 4);
-    std::vector<unsigned char> host(total, 0);
-    for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
-    int rc;
-    if ((rc = dev_alloc(ctx, &E.blob, total))) return rc;
-    CK(cudaMemcpyAsync(E.blob, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ClassTablesDev& V = E.view;
-    V.nchunk = (int)C.chunk_bz0.size() - 1; V.nout = C.nout; V.itmax = C.itmax; V.smax_rows = C.smax_rows; V.nk = C.nk;
-    V.n_rt = (int)C.t_rt.size(); V.n_xy = (int)C.t_xy.size(); V.n_u = (int)C.t_u.size() / 2;
-    V.chunk_bz0 = (const int*)(E.blob + o_bz0); V.chunk_e0 = (const int*)(E.blob + o_e0); V.chunk_s0 = (const int*)(E.blob + o_s0);
-    V.p4 = (const unsigned*)(E.blob + o_p4); V.p5ptr = (const unsigned*)(E.blob + o_ptr); V.p5term = (const unsigned*)(E.blob + o_term);
-    V.p5off = (const unsigned*)(E.blob + o_off); V.pmap = (const unsigned short*)(E.blob + o_pmap); V.omap = (const unsigned short*)(E.blob + o_omap);
-    V.t_rt = (const unsigned*)(E.blob + o_rt); V.t_xy = (const unsigned*)(E.blob + o_xy); V.t_u = (const unsigned*)(E.blob + o_u);
-    V.t_s = (const unsigned*)(E.blob + o_s);
-    V.njst = (int)C.jst_ptr.size() - 1; V.njfl = (int)C.jflush.size();
-    V.jst_ptr = (const unsigned*)(E.blob + o_jp); V.jst_list = (const unsigned short*)(E.blob + o_jl); V.jflush = (const unsigned*)(E.blob + o_jf);
-    V.p6 = (const unsigned*)(E.blob + o_p6); V.chunk_f0 = (const int*)(E.blob + o_f0);
-#ifdef TUNA_SHELL_WIDE_TERMS
-    V.p5w = nullptr;
-#endif
-    *out = &E;
-    return TUNA_OK;
-}
-
-// Build (or refresh for a new threshold) the shell-pair data and the job list of the shell-quartet engine.
+// Shell-pair data of the shell-quartet engine (built once per geometry).
 static int ensure_shell_pairs(tuna_ctx* ctx) {
     int rc;
     if (!ctx->shell_ready) {
@@ -2181,265 +1895,6 @@ static int ensure_shell_pairs(tuna_ctx* ctx) {
         CK(cudaMemcpyAsync(ctx->d_fnorm, S.fnorm.data(), (size_t)ctx->ncart * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->shell_ready = true;
-        ctx->shell_tau = -1.0;
-        ctx->shell4_tau = -1.0;
-    }
-    return TUNA_OK;
-}
-
-static int ensure_shell(tuna_ctx* ctx, double tau, int nD, int fill = 0) {
-    int rc;
-    if ((rc = ensure_shell_pairs(ctx))) return rc;
-    if (ctx->shell_tau != tau || ctx->shell_nD != nD || ctx->shell_fill != fill || ctx->jobs.empty()) {
-        ctx->shell_nD = nD;
-        ctx->shell_fill = fill;
-        const ShellSystem& S = ctx->ss;
-        const int ncls = (int)S.classes.size();
-        std::vector<long long> all_prefix;
-        std::vector<size_t> prefix_off;
-        ctx->jobs.clear();
-        const char* env_div = getenv("TUNA_B200_G_DIV");
-        const char* env_spl = getenv("TUNA_B200_SMEM_PER_LANE");
-        const double gdiv = env_div ? atof(env_div) : 8.0;
-        const double smem_per_lane = env_spl ? atof(env_spl) : 256.0;
-        for (int cb = 0; cb < ncls; ++cb)
-            for (int ck = 0; ck <= cb; ++ck) {
-                tuna_ctx::JobHost jh;
-                ShellJob& J = jh.job;
-                J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
-                J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
-                { const char* dbg = getenv("TUNA_B200_DBG_SKIP"); J.dbg_skip = dbg ? atoi(dbg) : 0; }
-                J.fill = fill;
-                std::vector<long long> prefix;
-                J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
-                if (J.nitems == 0) continue;
-                J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
-                J.bra_list = ctx->d_class_lists + ctx->class_list_off[cb];
-                J.ket_list = ctx->d_class_lists + ctx->class_list_off[ck];
-                prefix_off.push_back(all_prefix.size());
-                all_prefix.insert(all_prefix.end(), prefix.begin(), prefix.end());
-                tuna_ctx::ClassTabDev* ctd = nullptr;
-                if ((rc = get_class_tables(ctx, J.La, J.Lb, J.Lc, J.Ld, nD, fill != 0, &ctd))) return rc;
-                J.ct = ctd->view;
-                shell_job_layout(J, nD);
-                jh.allowed = (double)ctd->host.allowed;
-                for (int u = 0; u < 6; ++u) J.uniq[u] = ctd->host.uniq[u];
-                // NB quartets are batched per group when two slices fit comfortably; the group size G follows the footprint
-                const char* env_nb = getenv("TUNA_B200_NB");
-                int nb = env_nb ? atoi(env_nb) : 2;
-                if (nb != 1 && nb != 2 && nb != 4) nb = 2;
-                const char* env_nbmax = getenv("TUNA_B200_NB_BYTES");       // batch only while the NB slices stay below this
-                const size_t nb_bytes = env_nbmax ? (size_t)atol(env_nbmax) : 96 * 1024;
-                while (nb > 1 && (size_t)nb * J.total * 8 > nb_bytes) nb >>= 1;
-                int G = 1;
-                while (G < 256 && G * gdiv < jh.allowed) G *= 2;
-                while (G < 256 && (double)nb * J.total * 8.0 / G > smem_per_lane) G *= 2;
-                while (G < 256 && (size_t)(G <= 32 ? 128 / G : 1) * nb * J.total * 8 > 200 * 1024) G *= 2;
-#ifdef TUNA_SHELL_WIDE_TERMS
-                {   // the wide phase-5 table is scaled by 8 nb bytes: one device copy per (class, nb)
-                    const int wi = nb == 4 ? 2 : nb == 2 ? 1 : 0;
-                    if (!ctd->wide[wi]) {
-                        const std::vector<unsigned> w = scale_wide_terms(ctd->host.p5wide, nb, J.oP - J.oIt);
-                        if ((rc = dev_alloc(ctx, &ctd->wide[wi], std::max<size_t>(w.size(), 4)))) return rc;
-                        CK(cudaMemcpyAsync(ctd->wide[wi], w.data(), w.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-                        CK(cudaStreamSynchronize(ctx->stream));
-                    }
-                    J.ct.p5w = ctd->wide[wi];
-                }
-#endif
-                jh.G = G; jh.nb = nb;
-                jh.threads = G <= 32 ? 128 : G;
-                jh.gpc = jh.threads / G;
-                J.chunk = jh.gpc * SHELL_ITEMS_PER_GROUP;
-                jh.smem = ((size_t)jh.gpc * nb * J.total + 2) * sizeof(double);
-                if (jh.smem > 220 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 220 KB");
-                ctx->jobs.push_back(jh);
-            }
-        if ((rc = dev_alloc(ctx, &ctx->d_prefix, std::max<size_t>(all_prefix.size(), 1)))) return rc;
-        for (size_t j = 0; j < ctx->jobs.size(); ++j) ctx->jobs[j].job.item_prefix = reinterpret_cast<const long long*>(prefix_off[j]);   // offset, fixed up below
-        CK(cudaMemcpyAsync(ctx->d_prefix, all_prefix.data(), all_prefix.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        for (auto& jh : ctx->jobs) jh.job.item_prefix = ctx->d_prefix + reinterpret_cast<size_t>(jh.job.item_prefix);
-        // heaviest class jobs first: better packing of the tails across the auxiliary streams
-        std::stable_sort(ctx->jobs.begin(), ctx->jobs.end(), [](const tuna_ctx::JobHost& x, const tuna_ctx::JobHost& y) {
-            return x.allowed * (double)x.job.nitems > y.allowed * (double)y.job.nitems;
-        });
-        // large class jobs get their own launch (descriptor as kernel parameter); the many small ones are grouped by group size
-        // and shared-memory footprint into persistent launches that walk a flat (job, chunk) unit list
-        {
-            const char* et = getenv("TUNA_B200_OWN_LAUNCH_MIN");
-            const double thr = (et ? atof(et) : 5.0e5) * ctx->shard_n;
-            for (auto& jh : ctx->jobs) jh.own_launch = jh.allowed * (double)jh.job.nitems >= thr;
-            if (const char* dump = getenv("TUNA_B200_DUMP_JOBS")) {       // development aid: the job table in launch order
-                if (FILE* f = fopen(dump, "w")) {
-                    fprintf(f, "idx,La,Lb,Lc,Ld,nppAB,nppCD,G,nb,threads,smem,total,nout,nint,itmax,nchunk,nitems,allowed,own\n");
-                    int idx = 0;
-                    for (const auto& jh : ctx->jobs) {
-                        auto ct = ctx->class_tabs.find(jh.job.La | jh.job.Lb << 4 | jh.job.Lc << 8 | jh.job.Ld << 12 | nD << 16 | (fill ? 1 << 24 : 0));
-                        fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%zu,%d,%d,%d,%d,%d,%lld,%.0f,%d\n", idx++, jh.job.La, jh.job.Lb, jh.job.Lc, jh.job.Ld,
-                                jh.job.nppAB, jh.job.nppCD, jh.G, jh.nb, jh.threads, jh.smem, jh.job.total, jh.job.ct.nout,
-                                ct != ctx->class_tabs.end() ? ct->second.host.nint : -1, jh.job.ct.itmax, jh.job.ct.nchunk, jh.job.nitems, jh.allowed,
-                                (int)jh.own_launch);
-                    }
-                    fclose(f);
-                }
-            }
-        }
-        for (auto& g : ctx->groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
-        ctx->groups.clear();
-        for (int nbv = 4; nbv >= 1; nbv >>= 1)
-        for (int G = 256; G >= 1; G >>= 1)
-            for (int bucket = 40; bucket >= 0; --bucket) {       // jobs of similar shared-memory footprint share a launch (occupancy)
-                std::vector<ShellJob> js;
-                std::vector<long long> up(1, 0);
-                size_t max_slices = 0;
-                int threads = 128;
-                for (const auto& jh : ctx->jobs) {
-                    if (jh.G != G || jh.nb != nbv || jh.own_launch) continue;
-                    const size_t slices = (size_t)jh.gpc * jh.nb * jh.job.total;
-                    int b = 0;
-                    while (((size_t)1 << b) < slices) ++b;
-                    b = 2 * b + (slices > ((size_t)3 << (b - 2)) ? 1 : 0);       // half-octave buckets
-                    if (b != bucket) continue;
-                    js.push_back(jh.job);
-                    up.push_back(up.back() + (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk);
-                    max_slices = std::max(max_slices, slices);
-                    threads = jh.threads;
-                }
-                if (js.empty()) continue;
-                tuna_ctx::LaunchGroup lg;
-                lg.G = G; lg.nb = nbv; lg.threads = threads; lg.njobs = (int)js.size(); lg.nunits = up.back();
-                lg.job_slot_off = (max_slices + 1) & ~(size_t)1;
-                lg.smem = (lg.job_slot_off + (sizeof(ShellJob) + 7) / 8 + 2) * sizeof(double);
-                lg.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / lg.smem));
-                if ((rc = dev_alloc(ctx, &lg.d_jobs, js.size()))) return rc;
-                if ((rc = dev_alloc(ctx, &lg.d_unit_prefix, up.size()))) return rc;
-                CK(cudaMemcpyAsync(lg.d_jobs, js.data(), js.size() * sizeof(ShellJob), cudaMemcpyHostToDevice, ctx->stream));
-                CK(cudaMemcpyAsync(lg.d_unit_prefix, up.data(), up.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-                ctx->groups.push_back(lg);
-            }
-        ctx->shell_tau = tau;
-        ctx->shell_epoch++;
-    }
-    return TUNA_OK;
-}
-
-template <int GG, int NB>
-static cudaError_t launch_shell(tuna_ctx* ctx, const tuna_ctx::LaunchGroup& lg, const ShellData& D, int nD, const double* Pf, const double* Psym,
-                                double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    if (cudaError_t e = opt_in_smem<k_shell_jk<GG, NB>>(ctx); e != cudaSuccess) return e;
-    const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;      // the dense fill is not sharded
-    long long blocks = (lg.nunits - srank + sn - 1) / sn;       // units owned by this rank
-    if (blocks <= 0) return cudaSuccess;
-    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * lg.ctas_per_sm);
-    k_shell_jk<GG, NB><<<(int)blocks, lg.threads, lg.smem, stream>>>(lg.d_jobs, lg.d_unit_prefix, lg.njobs, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau,
-                                                                 ctx->d_scalars, ctx->d_eval, srank, sn, lg.job_slot_off);
-    ctx->launches++;
-    return cudaGetLastError();
-}
-
-#ifdef TUNA_SHELL_REG_TIERS
-template <int GG, int NB, int REGS>
-static cudaError_t launch_shell_one_r(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
-                                      double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    if (cudaError_t e = opt_in_smem<k_shell_jk_one<GG, NB, REGS>>(ctx); e != cudaSuccess) return e;
-    const long long nchunk = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
-    const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;
-    long long blocks = (nchunk - srank + sn - 1) / sn;       // chunks owned by this rank
-    if (blocks <= 0) return cudaSuccess;
-    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
-    k_shell_jk_one<GG, NB, REGS><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars,
-                                                                           ctx->d_eval, srank, sn);
-    ctx->launches++;
-    return cudaGetLastError();
-}
-
-template <int GG, int NB>
-static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
-                                    double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    // CTAs per SM allowed by shared memory (1 KB reserved per CTA); the wide-register build is used when that many CTAs of
-    // jh.threads threads still fit 128 registers per thread (TUNA_B200_REG_TIER=0 forces the 64-register build)
-    static const bool tiers = !(getenv("TUNA_B200_REG_TIER") && atoi(getenv("TUNA_B200_REG_TIER")) == 0);
-    const size_t by_smem = std::max<size_t>(1, (size_t)(228 * 1024) / (jh.smem + 1024));
-    if constexpr (GG >= 64 && NB <= 2) {
-        if (tiers && by_smem * jh.threads * 128 <= 65536) return launch_shell_one_r<GG, NB, 128>(ctx, jh, D, nD, Pf, Psym, Jf, Kf, tau, stream);
-    }
-    return launch_shell_one_r<GG, NB, 64>(ctx, jh, D, nD, Pf, Psym, Jf, Kf, tau, stream);
-}
-#else
-template <int GG, int NB>
-static cudaError_t launch_shell_one(tuna_ctx* ctx, const tuna_ctx::JobHost& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
-                                    double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    if (cudaError_t e = opt_in_smem<k_shell_jk_one<GG, NB>>(ctx); e != cudaSuccess) return e;
-    const long long nchunk = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
-    const int srank = D.eri_out ? 0 : ctx->shard_rank, sn = D.eri_out ? 1 : ctx->shard_n;
-    long long blocks = (nchunk - srank + sn - 1) / sn;       // chunks owned by this rank
-    if (blocks <= 0) return cudaSuccess;
-    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 64);
-    k_shell_jk_one<GG, NB><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
-                                                                     srank, sn);
-    ctx->launches++;
-    return cudaGetLastError();
-}
-#endif
-
-// All class jobs of the cached job list: large ones as individual launches, the rest as grouped persistent launches, spread over
-// the auxiliary streams and joined back into ctx->stream.  eri_out != nullptr selects the dense-tensor fill (job list built with fill = 1).
-static int launch_shell_jobs(tuna_ctx* ctx, int nD, const double* Pc, const double* Psym, double* Jc, double* Kc, double tau, double* eri_out) {
-    {
-        ShellData D;
-        D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
-        D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
-        D.eri_out = eri_out; D.fnorm = ctx->d_fnorm; D.fix_lo = 0;
-        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
-        int jn = 0;
-        for (const auto& jh : ctx->jobs) {
-            if (!jh.own_launch) continue;
-            cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
-            cudaError_t e;
-#define TUNA_ONE(GV) (jh.nb == 4 ? launch_shell_one<GV, 4>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
-                      : jh.nb == 2 ? launch_shell_one<GV, 2>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
-                                   : launch_shell_one<GV, 1>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st))
-            switch (jh.G) {
-                case 1: e = TUNA_ONE(1); break;
-                case 2: e = TUNA_ONE(2); break;
-                case 4: e = TUNA_ONE(4); break;
-                case 8: e = TUNA_ONE(8); break;
-                case 16: e = TUNA_ONE(16); break;
-                case 32: e = TUNA_ONE(32); break;
-                case 64: e = TUNA_ONE(64); break;
-                case 128: e = TUNA_ONE(128); break;
-                default: e = TUNA_ONE(256); break;
-            }
-#undef TUNA_ONE
-            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk_one launch: ") + cudaGetErrorString(e));
-        }
-        for (const auto& lg : ctx->groups) {
-            cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
-            cudaError_t e;
-#define TUNA_GRP(GV) (lg.nb == 4 ? launch_shell<GV, 4>(ctx, lg, D, nD, Pc, Psym, Jc, Kc, tau, st) \
-                      : lg.nb == 2 ? launch_shell<GV, 2>(ctx, lg, D, nD, Pc, Psym, Jc, Kc, tau, st) \
-                                   : launch_shell<GV, 1>(ctx, lg, D, nD, Pc, Psym, Jc, Kc, tau, st))
-            switch (lg.G) {
-                case 1: e = TUNA_GRP(1); break;
-                case 2: e = TUNA_GRP(2); break;
-                case 4: e = TUNA_GRP(4); break;
-                case 8: e = TUNA_GRP(8); break;
-                case 16: e = TUNA_GRP(16); break;
-                case 32: e = TUNA_GRP(32); break;
-                case 64: e = TUNA_GRP(64); break;
-                case 128: e = TUNA_GRP(128); break;
-                default: e = TUNA_GRP(256); break;
-            }
-#undef TUNA_GRP
-            if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell_jk launch: ") + cudaGetErrorString(e));
-        }
-        for (int a = 0; a < tuna_ctx::NAUX; ++a) {
-            CK(cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[a], 0));
-        }
     }
     return TUNA_OK;
 }
@@ -2530,12 +1985,18 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
 static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
     int rc;
     if ((rc = ensure_shell_pairs(ctx))) return rc;
-    if (ctx->shell4_tau == tau && ctx->shell4_nD == nD && !ctx->jobs4.empty()) return TUNA_OK;
+    for (size_t i = 0; i < ctx->jobsets4.size(); ++i)
+        if (ctx->jobsets4[i].tau == tau && ctx->jobsets4[i].nD == nD && ctx->jobsets4[i].shard_n == ctx->shard_n) { ctx->cur_jobset4 = (int)i; return TUNA_OK; }
+    if (ctx->jobsets4.size() >= 6) { CK(cudaStreamSynchronize(ctx->stream)); dev_free(&ctx->jobsets4.front().d_prefix); ctx->jobsets4.erase(ctx->jobsets4.begin()); }
+    ctx->jobsets4.emplace_back();
+    ctx->cur_jobset4 = (int)ctx->jobsets4.size() - 1;
+    tuna_ctx::JobSet4& JS = ctx->jobsets4.back();
+    JS.tau = tau; JS.nD = nD; JS.shard_n = ctx->shard_n;
+    std::vector<tuna_ctx::Job4Host>& jobs4 = JS.jobs;
     const ShellSystem& S = ctx->ss;
     const int ncls = (int)S.classes.size();
     std::vector<long long> all_prefix;
     std::vector<size_t> prefix_off;
-    ctx->jobs4.clear();
     const char* env_div = getenv("TUNA_B200_G_DIV");
     const char* env_spl = getenv("TUNA_B200_SMEM_PER_LANE");
     const char* env_nb = getenv("TUNA_B200_NB");
@@ -2589,31 +2050,26 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             jh.hdr_off = jh.tab_off + (ctd->host.tab_words + 4 + 1) / 2;
             jh.smem = ((size_t)jh.hdr_off + (size_t)J.chunk * sizeof(Quartet4) / 8 + 2) * sizeof(double);
             if (jh.smem > 226 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 226 KB");
-            ctx->jobs4.push_back(jh);
+            jobs4.push_back(jh);
         }
-    if ((rc = dev_alloc(ctx, &ctx->d_prefix, std::max<size_t>(all_prefix.size(), 1)))) return rc;
-    CK(cudaMemcpyAsync(ctx->d_prefix, all_prefix.data(), all_prefix.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = dev_alloc(ctx, &JS.d_prefix, std::max<size_t>(all_prefix.size(), 1)))) return rc;
+    CK(cudaMemcpyAsync(JS.d_prefix, all_prefix.data(), all_prefix.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (size_t j = 0; j < ctx->jobs4.size(); ++j) ctx->jobs4[j].job.item_prefix = ctx->d_prefix + prefix_off[j];
-    std::stable_sort(ctx->jobs4.begin(), ctx->jobs4.end(), [](const tuna_ctx::Job4Host& x, const tuna_ctx::Job4Host& y) {
+    for (size_t j = 0; j < jobs4.size(); ++j) jobs4[j].job.item_prefix = JS.d_prefix + prefix_off[j];
+    std::stable_sort(jobs4.begin(), jobs4.end(), [](const tuna_ctx::Job4Host& x, const tuna_ctx::Job4Host& y) {
         return x.allowed * (double)x.job.nitems > y.allowed * (double)y.job.nitems;
     });
     if (const char* dump = getenv("TUNA_B200_DUMP_JOBS")) {       // development aid: the job table in launch order
         if (FILE* f = fopen(dump, "w")) {
             fprintf(f, "idx,La,Lb,Lc,Ld,nppAB,nppCD,G,nb,threads,smem,total,nout,nint,itmax,nchunk,nitems,allowed,own\n");
             int idx = 0;
-            for (const auto& jh : ctx->jobs4)
+            for (const auto& jh : jobs4)
                 fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%zu,%d,%d,%d,%d,%d,%lld,%.0f,%d\n", idx++, jh.job.La, jh.job.Lb, jh.job.Lc, jh.job.Ld, jh.job.nppAB,
                         jh.job.nppCD, jh.G, jh.nb, jh.threads, jh.smem, jh.job.total, jh.job.ct.nwork, jh.job.ct.itmax, jh.job.ct.itmax, jh.job.ct.nchunk,
                         jh.job.nitems, jh.allowed, 1);
             fclose(f);
         }
     }
-    ctx->shell_tau = -1.0;            // d_prefix is shared with the generation-2 job list: that one must be rebuilt before its next use
-    ctx->jobs.clear();
-    ctx->shell4_tau = tau;
-    ctx->shell4_nD = nD;
-    ctx->shell_epoch++;
     return TUNA_OK;
 }
 
@@ -2649,11 +2105,11 @@ static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const dou
     ShellData D;
     D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
     D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
-    D.eri_out = nullptr; D.fnorm = ctx->d_fnorm; D.fix_lo = fix_lo;
+    D.fix_lo = fix_lo;
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
     int jn = 0;
-    for (const auto& jh : ctx->jobs4) {
+    for (const auto& jh : ctx->jobsets4[ctx->cur_jobset4].jobs) {
         cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
         cudaError_t e;
 #define TUNA_ONE4(GV) (jh.nb == 4 ? launch_shell4_one<GV, 4>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
@@ -2680,24 +2136,9 @@ static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const dou
     return TUNA_OK;
 }
 
-// Dense Cartesian tensor through the shell-quartet engine: every shell quartet once (no screening), canonical AO quartets
-// scattered to their eight images; ctx->d_eri_cart is allocated and zeroed by the caller (parity-forbidden entries stay exact zeros).
-static int shell_fill(tuna_ctx* ctx) {
-    int rc;
-    if ((rc = ensure_schwarz(ctx))) return rc;
-    if ((rc = ensure_shell(ctx, 0.0, 1, 1))) return rc;
-    CK(cudaMemsetAsync(ctx->d_scalars, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_eval, 0, sizeof(double), ctx->stream));
-    CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
-    if ((rc = launch_shell_jobs(ctx, 1, nullptr, nullptr, nullptr, nullptr, 0.0, ctx->d_eri_cart))) return rc;
-    CK(cudaEventRecord(ctx->ev[0][1], ctx->stream));
-    return TUNA_OK;
-}
-
 // Core of direct mode on DEVICE buffers: nD densities, bit d of anti_mask marks density d as antisymmetric
 // (its K is Kacc - Kacc^T and its J vanishes); all others must be symmetric.
 static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau);
-static int jk_direct_pass_graphed(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau);
 
 // Densities are processed in passes small enough for the largest class of the basis to fit its J/K blocks in shared memory.
 static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau) {
@@ -2708,66 +2149,17 @@ static int jk_direct_core(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     if (ctx->direct_engine == 1 && ctx->ss.ok) {
         int Lmax = 0;
         for (const auto& sh : ctx->ss.shells) Lmax = std::max(Lmax, sh.L);
-        while (nd_max > 1 && shell_fixed_doubles(ctx->stab, Lmax, Lmax, Lmax, Lmax, nd_max) + 1024 > SHELL_SMEM_DOUBLES) --nd_max;
+        // staged densities + accumulators of the largest class: about 4 (nc + 4)^2 + 8 nc^2 doubles per density next to ~9000 doubles of tables
+        const int nc = ctx->stab.nc[Lmax], per_density = 4 * (nc + 4) * (nc + 4) + 8 * nc * nc;
+        while (nd_max > 1 && nd_max * per_density + 9000 > SHELL4_SMEM_DOUBLES) --nd_max;
     }
     const int npass = (nD + nd_max - 1) / nd_max, per = (nD + npass - 1) / npass;
     const size_t nn = (size_t)ctx->nbf * ctx->nbf;
     for (int d0 = 0; d0 < nD; d0 += per) {
         const int nd = std::min(per, nD - d0);
-        const bool graphed = ctx->graph_mode && ctx->direct_engine == 1 && ctx->ss.ok;
-        int rc = graphed ? jk_direct_pass_graphed(ctx, nd, dP + d0 * nn, (anti_mask >> d0) & ((1u << nd) - 1u), dJ ? dJ + d0 * nn : nullptr, dK ? dK + d0 * nn : nullptr, tau)
-                         : jk_direct_pass(ctx, nd, dP + d0 * nn, (anti_mask >> d0) & ((1u << nd) - 1u), dJ ? dJ + d0 * nn : nullptr, dK ? dK + d0 * nn : nullptr, tau);
+        int rc = jk_direct_pass(ctx, nd, dP + d0 * nn, (anti_mask >> d0) & ((1u << nd) - 1u), dJ ? dJ + d0 * nn : nullptr, dK ? dK + d0 * nn : nullptr, tau);
         if (rc) return rc;
     }
-    return TUNA_OK;
-}
-
-// Graph mode (see tuna_ctx::GraphKey): replay a captured pass, or run / capture it.
-static int jk_direct_pass_graphed(tuna_ctx* ctx, int nD, const double* dP, unsigned anti_mask, double* dJ, double* dK, double tau) {
-    tuna_ctx::GraphKey key;
-    key.nD = nD; key.dP = dP; key.anti = anti_mask; key.dJ = dJ; key.dK = dK; key.tau = tau;
-    key.srank = ctx->shard_rank; key.sn = ctx->shard_n; key.epoch = ctx->shell_epoch;
-    for (auto& g : ctx->graphs)
-        if (g.key == key) {
-            CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));        // in graph mode the "dominant kernel" time covers the whole pass
-            CK(cudaGraphLaunch(g.exec, ctx->stream));
-            CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
-            ctx->launches += g.launches;
-            return TUNA_OK;
-        }
-    if (!(ctx->warm_valid && ctx->warm_key == key)) {                // first sighting: plain run (sets attributes, builds tables)
-        int rc = jk_direct_pass(ctx, nD, dP, anti_mask, dJ, dK, tau);
-        key.epoch = ctx->shell_epoch;                                // the run itself may have rebuilt the job list
-        ctx->warm_key = key; ctx->warm_valid = rc == TUNA_OK;
-        return rc;
-    }
-    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    const int64_t l0 = ctx->launches;
-    ctx->capturing = true;
-    int rc = jk_direct_pass(ctx, nD, dP, anti_mask, dJ, dK, tau);
-    ctx->capturing = false;
-    cudaGraph_t graph = nullptr;
-    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-    const int64_t captured = ctx->launches - l0;
-    ctx->launches = l0;
-    if (rc || e != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        ctx->warm_valid = false;
-        if (rc) return rc;
-        FAIL(TUNA_ERR_CUDA, std::string("graph capture of the direct J/K pass failed: ") + cudaGetErrorString(e));
-    }
-    tuna_ctx::GraphEntry ge;
-    ge.key = key; ge.launches = captured;
-    e = cudaGraphInstantiate(&ge.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-    if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
-    ctx->graphs.push_back(ge);
-    CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
-    CK(cudaGraphLaunch(ge.exec, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
-    ctx->launches += captured;
     return TUNA_OK;
 }
 
@@ -2780,8 +2172,7 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
     int rc;
     if ((rc = ensure_mats(ctx, nD, nb, nc))) return rc;
     if ((rc = ensure_schwarz(ctx))) return rc;
-    const bool gen4 = shell && ctx->engine_gen == 4;
-    if (shell && (rc = gen4 ? ensure_shell4(ctx, tau, nD) : ensure_shell(ctx, tau, nD))) return rc;
+    if (shell && (rc = ensure_shell4(ctx, tau, nD))) return rc;
     const size_t ncc = (size_t)nc * nc;
     const CsrDev& Uin = shell ? ctx->Uft : ctx->Ut;      // the shell engine works with unnormalised components: U' = U diag(f)
     const CsrDev& Uout = shell ? ctx->Uf : ctx->U;
@@ -2796,7 +2187,7 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
         k_absmax<<<grid_for(ctx, (int64_t)nD * ncc, 256, 4), 256, 0, ctx->stream>>>(ctx->d_Pc, (int64_t)nD * ncc, ctx->d_scalars);
     }
     ctx->launches++;
-    const bool fixed = gen4 && ctx->deterministic;
+    const bool fixed = shell;        // the shell engine accumulates order-independently in integers; the per-component kernel uses FP64 atomics
     const size_t nacc = (size_t)nD * ncc;
     if (fixed) {
         if (ctx->cap_fix < 4 * nacc) {
@@ -2809,18 +2200,15 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
         CK(cudaMemsetAsync(ctx->d_Jc, 0, nacc * sizeof(double), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_Kc, 0, nacc * sizeof(double), ctx->stream));
     }
-    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3][0], ctx->stream));
     if (shell) {
         k_add_transpose_signed<<<grid_for(ctx, (int64_t)nD * ncc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_Pc, ctx->d_tmp, nD, nc, 0u);   // Psym = P + P^T
         ctx->launches++;
-        if (fixed) {
-            double* Jw = reinterpret_cast<double*>(ctx->d_fix);
-            double* Kw = reinterpret_cast<double*>(ctx->d_fix + 2 * nacc);
-            if ((rc = launch_shell4_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, Jw, Kw, tau, (long long)nacc))) return rc;
-            k_fixed_to_double<<<grid_for(ctx, (int64_t)nacc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_fix, ctx->d_Jc, ctx->d_Kc, nacc);
-            ctx->launches++;
-        } else if ((rc = gen4 ? launch_shell4_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, 0)
-                              : launch_shell_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, ctx->d_Jc, ctx->d_Kc, tau, nullptr))) return rc;
+        double* Jw = reinterpret_cast<double*>(ctx->d_fix);
+        double* Kw = reinterpret_cast<double*>(ctx->d_fix + 2 * nacc);
+        if ((rc = launch_shell4_jobs(ctx, nD, ctx->d_Pc, ctx->d_tmp, Jw, Kw, tau, (long long)nacc))) return rc;
+        k_fixed_to_double<<<grid_for(ctx, (int64_t)nacc, 256, 8), 256, 0, ctx->stream>>>(ctx->d_fix, ctx->d_Jc, ctx->d_Kc, nacc);
+        ctx->launches++;
     } else {
         k_jk_direct<<<grid_for(ctx, ctx->task_begin[4] / ctx->shard_n + 1, 128, 16), 128, 0, ctx->stream>>>(
             table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_Q, ctx->d_Pc, ctx->d_Jc, ctx->d_Kc, nc, nD, tau, ctx->d_scalars, ctx->d_scalars + 1,
@@ -2828,7 +2216,7 @@ static int jk_direct_pass(tuna_ctx* ctx, int nD, const double* dP, unsigned anti
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3][1], ctx->stream));
     // J = U (Jacc + Jacc^T) U^T,  K = U (Kacc +- Kacc^T) U^T
     for (int which = 0; which < 2; ++which) {
         double* acc = which == 0 ? ctx->d_Jc : ctx->d_Kc;
