@@ -97,7 +97,8 @@ struct tuna_ctx {
     int* d_sh_ao = nullptr; int* d_class_lists = nullptr; double* d_finv = nullptr;
     double* d_eval = nullptr;
     std::vector<size_t> class_list_off;
-    static constexpr int NAUX = 6;
+    static constexpr int NAUX = 16;
+    int naux = 16;                   // streams in use (TUNA_B200_STREAMS, 1..16; measured: 16 helps the launch-bound small systems, neutral at nbf 800)
     cudaStream_t aux[NAUX] = {};     // class jobs of one build are independent (integer-atomic accumulation): launches are dealt round-robin to these streams
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     // generation-4 shell engine (shell4.cuh): per-class tables and the job list; the pair data above is shared
@@ -818,6 +819,7 @@ k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, co
     Quartet4* hdr = reinterpret_cast<Quartet4*>(smem_all + hdr_off);
     const int CH = J.chunk;
     int& s_ib0 = *reinterpret_cast<int*>(hdr + CH);
+
     double* sm = smem_all + (size_t)gid * NB * J.total;
     const double dmax = __longlong_as_double((long long)scalars[0]);
     const long long nunit = (J.nitems + CH - 1) / CH;
@@ -1080,6 +1082,7 @@ int tuna_ctx_create(int device, tuna_ctx** out) {
         CK(cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    if (const char* ns = getenv("TUNA_B200_STREAMS")) ctx->naux = std::max(1, std::min((int)tuna_ctx::NAUX, atoi(ns)));
     std::vector<double> boys, herm;
     build_boys_table(boys);
     build_hermite_poly_table(herm);
@@ -2107,10 +2110,10 @@ static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const dou
     D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm;
     D.fix_lo = fix_lo;
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    for (int a = 0; a < tuna_ctx::NAUX; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
+    for (int a = 0; a < ctx->naux; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
     int jn = 0;
     for (const auto& jh : ctx->jobsets4[ctx->cur_jobset4].jobs) {
-        cudaStream_t st = ctx->aux[jn++ % tuna_ctx::NAUX];
+        cudaStream_t st = ctx->aux[jn++ % ctx->naux];
         cudaError_t e;
 #define TUNA_ONE4(GV) (jh.nb == 4 ? launch_shell4_one<GV, 4>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
                        : jh.nb == 2 ? launch_shell4_one<GV, 2>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
@@ -2129,7 +2132,7 @@ static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const dou
 #undef TUNA_ONE4
         if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell4_one launch: ") + cudaGetErrorString(e));
     }
-    for (int a = 0; a < tuna_ctx::NAUX; ++a) {
+    for (int a = 0; a < ctx->naux; ++a) {
         CK(cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[a], 0));
     }
