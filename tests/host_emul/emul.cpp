@@ -132,6 +132,14 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
             Shell4Job J;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
             J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4; J.dbg_skip = 0;
+            {   // TUNA_EMUL_PSPLIT_TARGET: split contracted shell quartets into work items of bra primitive pairs, as the device launcher does
+                const char* ept = getenv("TUNA_EMUL_PSPLIT_TARGET");
+                const int target = ept ? atoi(ept) : 16;
+                const long long tot = (long long)J.nppAB * J.nppCD;
+                J.psplit = (target > 0 && tot > target) ? (int)std::min<long long>(J.nppAB, (tot + target - 1) / target) : 1;
+                J.clen = (J.nppAB + J.psplit - 1) / J.psplit;
+                J.psplit = (J.nppAB + J.clen - 1) / J.clen;
+            }
             J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
             std::vector<long long> prefix;
             J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
@@ -169,12 +177,14 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
                 if (S.pairA[AB] == S.pairB[AB]) w *= 0.5;
                 if (S.pairA[CD] == S.pairB[CD]) w *= 0.5;
                 if (AB == CD) w *= 0.5;
-                Quartet4 h;
-                h.active = 1; h.shA = S.pairA[AB]; h.shB = S.pairB[AB]; h.shC = S.pairA[CD]; h.shD = S.pairB[CD]; h.pad = 0; h.w = w;
-                h.recA = S.pair_rec[AB]; h.recC = S.pair_rec[CD];
-                h.pA = S.rec[h.recA]; h.zA = S.rec[h.recA + 1]; h.pC = S.rec[h.recC]; h.zC = S.rec[h.recC + 1];
-                hq[nb] = h;
-                if (++nb == NBATCH) run_batch();
+                for (int pchunk = 0; pchunk < J.psplit; ++pchunk) {
+                    Quartet4 h;
+                    h.active = 1; h.shA = S.pairA[AB]; h.shB = S.pairB[AB]; h.shC = S.pairA[CD]; h.shD = S.pairB[CD]; h.ia0 = pchunk * J.clen; h.w = w;
+                    h.recA = S.pair_rec[AB]; h.recC = S.pair_rec[CD];
+                    h.pA = S.rec[h.recA]; h.zA = S.rec[h.recA + 1]; h.pC = S.rec[h.recC]; h.zC = S.rec[h.recC + 1];
+                    hq[nb] = h;
+                    if (++nb == NBATCH) run_batch();
+                }
             }
             run_batch();
             nitems_total += J.nitems; nint_total += CH.nint; nterm_total += CH.nterms;

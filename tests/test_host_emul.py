@@ -109,6 +109,31 @@ def test_shell_engine_vs_oracle(emul, oracle, name, gen):
             assert np.abs(J[d] - Jr).max() < 1e-11 and np.abs(K[d] - Kr).max() < 1e-11
 
 
+@pytest.mark.parametrize("target", ["0", "5", "16"])
+def test_shell_engine_primitive_split(emul, oracle, target, monkeypatch):
+    """Contracted classes: a shell quartet split into work items of bra primitive pairs (each digesting and flushing its partial integrals)
+    gives the same J/K as the unsplit walk (target 0) - N2/cc-pVTZ has shells of up to 8 primitives, i.e. 4096 primitive quartets in (ss|ss)."""
+    monkeypatch.setenv("TUNA_EMUL_PSPLIT_TARGET", target)
+    g = load_golden("n2_ccpvtz")
+    fb = oracle_basis(oracle, g)
+    n = fb.ncart
+    E = oracle.eri_fill(fb)
+    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    oz = np.ascontiguousarray(fb.origins[:, 2])
+    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
+    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
+    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
+    P = np.random.default_rng(4).standard_normal((1, n, n))
+    P = (P + P.transpose(0, 2, 1)) / 2
+    J, K, stats = np.zeros_like(P), np.zeros_like(P), np.zeros(8, dtype=np.int64)
+    rc = emul.emul_jk_shell4(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp), fb.exps.ctypes.data_as(dp),
+                             ceff.ctypes.data_as(dp), 1, P.ctypes.data_as(dp), J.ctypes.data_as(dp), K.ctypes.data_as(dp), ctypes.c_double(0.0),
+                             stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    assert rc == 0
+    assert np.abs(J[0] - oracle.coulomb(P[0], E)).max() < 1e-11 and np.abs(K[0] - oracle.exchange(P[0], E)).max() < 1e-11
+
+
 @pytest.mark.parametrize("gen,nb,budget", [("gen4", None, None), ("gen4", "1", "1500"), ("gen4", "4", "700")])
 def test_shell_engine_h_shells(emul, oracle, gen, nb, budget, monkeypatch):
     """All shell types up to H, including the multi-chunk (hh|hh) class tables, on a synthetic two-centre basis; generation 4 also with

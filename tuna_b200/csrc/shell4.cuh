@@ -81,6 +81,11 @@ struct Class4Dev {
 struct Shell4Job {
     int La, Lb, Lc, Ld;
     int nppAB, nppCD;
+    // Contracted classes: the nppAB * nppCD primitive quartets of a shell quartet are walked serially (phases 0-4 each), which leaves a
+    // handful of lanes busy for thousands of iterations in classes like (ss|ss) of cc-pVQZ.  J and K are linear in the integrals, so a
+    // shell quartet is split into `psplit` work items of `clen` consecutive bra primitive pairs each (clen * psplit >= nppAB); every item
+    // digests and flushes its partial integrals on its own.
+    int psplit, clen;
     const int* bra_list; const int* ket_list;
     const long long* item_prefix;
     int nbra, same_class;
@@ -185,7 +190,7 @@ TUNA_HD void assemble4(const double* xyx, const double* xyy, const double* sp0, 
 
 // Header of one quartet of a batch, decoded once (by one lane) before the group starts on it.
 struct Quartet4 {
-    int active, shA, shB, shC, shD, pad;      // the four shells (A, B of the bra pair, C, D of the ket pair)
+    int active, shA, shB, shC, shD, ia0;      // the four shells (A, B of the bra pair, C, D of the ket pair); first bra primitive pair of this work item
     double w;                                 // degeneracy weight
     long long recA, recC;                     // offsets of the pairs' first primitive records in ShellData::rec
     double pA, zA, pC, zC;                    // exponent sum and centre of the FIRST primitive pair of bra and ket (Boys argument without a memory round trip)
@@ -284,12 +289,21 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             tab_chunk = ch;
             Pol::sync_cta();
         }
-        for (int ia = 0; ia < J.nppAB; ++ia)
+        for (int it = 0; it < J.clen; ++it)
             for (int ic = 0; ic < J.nppCD; ++ic) {
+                // bra primitive pair of every quartet of the batch (a work item past the last primitive pair runs on the last one with weight 0)
+                int iaq[NB];
+                bool pvalid[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int ia = hq[act[q] ? q : qa].ia0 + it;
+                    pvalid[q] = ia < J.nppAB;
+                    iaq[q] = pvalid[q] ? ia : J.nppAB - 1;
+                }
                 // ---- phase 0: the two primitive shell-pair records, Boys values scaled by (-2 rho)^m, powers of PQz
 #pragma unroll
                 for (int q = 0; q < NB && !(skip & 2); ++q) {
-                    const double* rA = recA[q] + ia * recAsz;
+                    const double* rA = recA[q] + iaq[q] * recAsz;
                     const double* rC = recC[q] + ic * recCsz;
                     if (ic == 0) { for (int x = lane; x < recAsz; x += Pol::G) RAq[x * NB + q] = rA[x]; }
                     for (int x = lane; x < recCsz; x += Pol::G) RCq[x * NB + q] = rC[x];
@@ -297,11 +311,12 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                 for (int x = lane; x < NB * 32 && !(skip & 2); x += Pol::G) {
                     const int q = x >> 5, m = x & 31;
                     if (m <= Ltot) {
-                        const double* rA = recA[0] + ia * recAsz;
+                        const double* rA = recA[0] + iaq[0] * recAsz;
                         const double* rC = recC[0] + ic * recCsz;
-                        int qs = act[0] ? 0 : qa;
+                        int qs = act[0] ? 0 : qa, ia = iaq[0];
+                        bool pv = pvalid[0];
 #pragma unroll
-                        for (int k = 1; k < NB; ++k) if (q == k) { rA = recA[k] + ia * recAsz; rC = recC[k] + ic * recCsz; qs = act[k] ? k : qa; }
+                        for (int k = 1; k < NB; ++k) if (q == k) { rA = recA[k] + iaq[k] * recAsz; rC = recC[k] + ic * recCsz; qs = act[k] ? k : qa; ia = iaq[k]; pv = pvalid[k]; }
                         double p, qq, PQz;
                         if (ia == 0 && ic == 0) { p = hq[qs].pA; qq = hq[qs].pC; PQz = hq[qs].zA - hq[qs].zC; }
                         else { p = rA[0]; qq = rC[0]; PQz = rA[1] - rC[1]; }
@@ -317,7 +332,7 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
                             double wq = w[0];
 #pragma unroll
                             for (int k = 1; k < NB; ++k) if (q == k) wq = w[k];
-                            prefq[q] = wq * rA[2] * rC[2] * 34.986836655249725 / (p * qq * sqrt(pq));
+                            prefq[q] = pv ? wq * rA[2] * rC[2] * 34.986836655249725 / (p * qq * sqrt(pq)) : 0.0;
                         }
                     }
                 }

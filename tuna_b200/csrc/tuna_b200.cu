@@ -822,7 +822,8 @@ k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, co
 
     double* sm = smem_all + (size_t)gid * NB * J.total;
     const double dmax = __longlong_as_double((long long)scalars[0]);
-    const long long nunit = (J.nitems + CH - 1) / CH;
+    const long long nwi = J.nitems * J.psplit;          // work items: (shell quartet, chunk of bra primitive pairs)
+    const long long nunit = (nwi + CH - 1) / CH;
     shell4_load_tables<NB>(J.ct, 0, tab, threadIdx.x, blockDim.x, J.oIt, J.oP);
     int tab_chunk = 0;
     double done = 0.0;
@@ -830,20 +831,23 @@ k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, co
         const long long first = gc * CH;
         __syncthreads();                                  // the previous unit's headers are no longer needed (and the tables are in place)
         if (threadIdx.x == 0) {
-            int lo = 0, hi = J.nbra;                      // invariant: prefix[lo] <= first < prefix[hi]
+            const long long first_item = first / J.psplit;
+            int lo = 0, hi = J.nbra;                      // invariant: prefix[lo] <= first_item < prefix[hi]
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (J.item_prefix[mid] <= first) lo = mid; else hi = mid;
+                if (J.item_prefix[mid] <= first_item) lo = mid; else hi = mid;
             }
             s_ib0 = lo;
         }
         __syncthreads();
         for (int k = threadIdx.x; k < CH; k += blockDim.x) {
-            const long long item = first + k;
+            const long long wi = first + k, item = wi / J.psplit;
+            const int pchunk = (int)(wi - item * J.psplit);
             Quartet4 h;
-            h.active = 0; h.shA = h.shB = h.shC = h.shD = 0; h.pad = 0; h.w = 0.0; h.recA = h.recC = 0; h.pA = h.pC = 1.0; h.zA = h.zC = 0.0;
-            if (item < J.nitems) {
+            h.active = 0; h.shA = h.shB = h.shC = h.shD = 0; h.ia0 = 0; h.w = 0.0; h.recA = h.recC = 0; h.pA = h.pC = 1.0; h.zA = h.zC = 0.0;
+            if (wi < nwi) {
                 int ib = s_ib0;
+                h.ia0 = pchunk * J.clen;
                 while (J.item_prefix[ib + 1] <= item) ++ib;
                 const int pab = J.bra_list[ib], pcd = J.ket_list[(int)(item - J.item_prefix[ib])];
                 h.active = !(tau > 0.0 && D.pairQ[pab] * D.pairQ[pcd] * dmax < tau);
@@ -853,7 +857,7 @@ k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, co
                 h.recA = D.pair_rec[pab]; h.recC = D.pair_rec[pcd];
                 if (h.active) {
                     h.pA = D.rec[h.recA]; h.zA = D.rec[h.recA + 1]; h.pC = D.rec[h.recC]; h.zC = D.rec[h.recC + 1];
-                    done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+                    if (pchunk == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
                 }
             }
             hdr[k] = h;
@@ -2014,6 +2018,13 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             Shell4Job& J = jh.job;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
             J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
+            {   // at most ~psplit_target primitive quartets per work item (TUNA_B200_PSPLIT_TARGET, 0 = never split)
+                static const int target = getenv("TUNA_B200_PSPLIT_TARGET") ? atoi(getenv("TUNA_B200_PSPLIT_TARGET")) : 16;
+                const long long tot = (long long)J.nppAB * J.nppCD;
+                J.psplit = (target > 0 && tot > target) ? (int)std::min<long long>(J.nppAB, (tot + target - 1) / target) : 1;
+                J.clen = (J.nppAB + J.psplit - 1) / J.psplit;
+                J.psplit = (J.nppAB + J.clen - 1) / J.clen;
+            }
             { const char* dbg = getenv("TUNA_B200_DBG_SKIP"); J.dbg_skip = dbg ? atoi(dbg) : 0; }
             std::vector<long long> prefix;
             J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
@@ -2043,7 +2054,7 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             {   // items per CTA work unit: enough units to spread over all CTA slots of all ranks eight times, at most 16 per group
                 const size_t by_smem = std::max<size_t>(1, (size_t)(228 * 1024) / ((size_t)jh.gpc * nb * J.total * 8 + 2048));
                 const long long slots = (long long)ctx->sm_count * (long long)std::min<size_t>(by_smem, 2048 / jh.threads) * ctx->shard_n;
-                long long per = J.nitems / std::max<long long>(1, slots * 8 * jh.gpc);
+                long long per = J.nitems * J.psplit / std::max<long long>(1, slots * 8 * jh.gpc);
                 per = std::max<long long>(nb, std::min<long long>(per, 16));
                 per = (per + nb - 1) / nb * nb;
                 J.chunk = jh.gpc * (int)per;
@@ -2089,7 +2100,7 @@ static cudaError_t launch_shell4_one_r(tuna_ctx* ctx, const tuna_ctx::Job4Host& 
 template <int GG, int NB>
 static cudaError_t launch_shell4_one(tuna_ctx* ctx, const tuna_ctx::Job4Host& jh, const ShellData& D, int nD, const double* Pf, const double* Psym,
                                      double* Jf, double* Kf, double tau, cudaStream_t stream) {
-    const long long nunit = (jh.job.nitems + jh.job.chunk - 1) / jh.job.chunk;
+    const long long nunit = (jh.job.nitems * jh.job.psplit + jh.job.chunk - 1) / jh.job.chunk;
     long long blocks = (nunit - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // units owned by this rank
     if (blocks <= 0) return cudaSuccess;
     const size_t by_smem = std::max<size_t>(1, (size_t)(228 * 1024) / (jh.smem + 1024));
