@@ -96,6 +96,7 @@ struct Shell4Job {
     Class4Dev ct;
     // shared-memory layout of one group (offsets in doubles, each array interleaved over the NB quartets of a batch)
     int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oRecA, oRecC, oAO, oPref, aostride, total;
+    int tab_off, hdr_off;           // CTA-level areas behind the group slices (doubles): digestion tables, quartet headers
 };
 
 inline void shell4_job_layout(Shell4Job& J, int nD) {

@@ -103,11 +103,13 @@ struct tuna_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     // generation-4 shell engine (shell4.cuh): per-class tables and the job list; the pair data above is shared
     struct ClassTab4Dev { Class4Host host; Class4Dev view; unsigned char* blob = nullptr; };
-    struct Job4Host { Shell4Job job; int G = 1, threads = 128, gpc = 1, nb = 1; size_t smem = 0; int tab_off = 0, hdr_off = 0; double allowed = 0; };
+    struct Job4Host { Shell4Job job; int G = 1, threads = 128, gpc = 1, nb = 1; size_t smem = 0; double allowed = 0; bool own_launch = true; };
     std::map<int, ClassTab4Dev> class_tabs4;     // key La | Lb<<4 | Lc<<8 | Ld<<12 | nD<<16
     // job lists are cached per (threshold, densities per pass, rank count): a build with nD = 5 runs passes of 2, 2 and 1 densities, and
     // direct SCF alternates between thresholds rarely - none of that may rebuild lists or reallocate inside a Fock build
-    struct JobSet4 { double tau = -1.0; int nD = 0, shard_n = 0; std::vector<Job4Host> jobs; long long* d_prefix = nullptr; };
+    struct Group4 { int G = 1, threads = 128, njobs = 0, job_off = 0, ctas_per_sm = 1; long long nunits = 0; size_t smem = 0;
+                    Shell4Job* d_jobs = nullptr; long long* d_unit_prefix = nullptr; };      // light jobs of one group size in one persistent launch
+    struct JobSet4 { double tau = -1.0; int nD = 0, shard_n = 0; std::vector<Job4Host> jobs; std::vector<Group4> groups; long long* d_prefix = nullptr; };
     std::vector<JobSet4> jobsets4;
     int cur_jobset4 = -1;
     long long* d_fix = nullptr; size_t cap_fix = 0;      // reproducible accumulation: [J hi | J lo | K hi | K lo], nD * ncart^2 words each
@@ -809,62 +811,106 @@ struct DevPolicy {
 #ifndef TUNA_SHELL4_REGS
 #define TUNA_SHELL4_REGS 64
 #endif
+// One CTA work unit: decode the unit's work items ONCE (item -> bra / ket pair, Schwarz test, degeneracy weight, record offsets) into the
+// shared-memory headers, then let the CTA's groups take them NB at a time.
+template <int GG, int NB>
+__device__ __forceinline__ void shell4_unit(const Shell4Job& J, const ShellData& D, long long unit, int nD, const double* __restrict__ Pf,
+                                            const double* __restrict__ Psym, double* Jf, double* Kf, int ncart, double tau, double dmax,
+                                            double* smem_all, int& tab_chunk, double& done) {
+    const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
+    unsigned* tab = reinterpret_cast<unsigned*>(smem_all + J.tab_off);
+    Quartet4* hdr = reinterpret_cast<Quartet4*>(smem_all + J.hdr_off);
+    const int CH = J.chunk;
+    int& s_ib0 = *reinterpret_cast<int*>(hdr + CH);
+    double* sm = smem_all + (size_t)gid * NB * J.total;
+    const long long nwi = J.nitems * J.psplit;          // work items: (shell quartet, chunk of bra primitive pairs)
+    const long long first = unit * CH;
+    __syncthreads();                                  // the previous unit's headers are no longer needed (and the tables are in place)
+    if (threadIdx.x == 0) {
+        const long long first_item = first / J.psplit;
+        int lo = 0, hi = J.nbra;                      // invariant: prefix[lo] <= first_item < prefix[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (J.item_prefix[mid] <= first_item) lo = mid; else hi = mid;
+        }
+        s_ib0 = lo;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < CH; k += blockDim.x) {
+        const long long wi = first + k, item = wi / J.psplit;
+        const int pchunk = (int)(wi - item * J.psplit);
+        Quartet4 h;
+        h.active = 0; h.shA = h.shB = h.shC = h.shD = 0; h.ia0 = 0; h.w = 0.0; h.recA = h.recC = 0; h.pA = h.pC = 1.0; h.zA = h.zC = 0.0;
+        if (wi < nwi) {
+            int ib = s_ib0;
+            h.ia0 = pchunk * J.clen;
+            while (J.item_prefix[ib + 1] <= item) ++ib;
+            const int pab = J.bra_list[ib], pcd = J.ket_list[(int)(item - J.item_prefix[ib])];
+            h.active = !(tau > 0.0 && D.pairQ[pab] * D.pairQ[pcd] * dmax < tau);
+            h.shA = D.pairA[pab]; h.shB = D.pairB[pab]; h.shC = D.pairA[pcd]; h.shD = D.pairB[pcd];
+            const bool ab = h.shA == h.shB, cd = h.shC == h.shD, dg = pab == pcd;
+            h.w = (ab ? 0.5 : 1.0) * (cd ? 0.5 : 1.0) * (dg ? 0.5 : 1.0);
+            h.recA = D.pair_rec[pab]; h.recC = D.pair_rec[pcd];
+            if (h.active) {
+                h.pA = D.rec[h.recA]; h.zA = D.rec[h.recA + 1]; h.pC = D.rec[h.recC]; h.zC = D.rec[h.recC + 1];
+                if (pchunk == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
+            }
+        }
+        hdr[k] = h;
+    }
+    __syncthreads();
+    for (int k0 = 0; k0 < CH; k0 += gpc * NB)
+        shell4_quartets<DevPolicy<GG>, NB>(J, D, hdr + k0 + gid * NB, sm, tab, tab_chunk, nD, Pf, Psym, Jf, Kf, ncart);
+}
+
+// Heavy class jobs: one job per launch, the descriptor travels as a kernel parameter (constant bank / uniform registers).  A CTA work
+// unit (= multi-GPU sharding unit) is J.chunk consecutive work items.
 template <int GG, int NB, int REGS = TUNA_SHELL4_REGS>
 __global__ void __launch_bounds__((GG > 128) ? GG : 128, 65536 / (((GG > 128) ? GG : 128) * REGS))
 k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf, double* Kf, int ncart,
-             double tau, const unsigned long long* scalars, double* evaluated, int rank, int nranks, int tab_off, int hdr_off) {
+             double tau, const unsigned long long* scalars, double* evaluated, int rank, int nranks) {
     extern __shared__ double smem_all[];
-    const int gpc = blockDim.x / GG, gid = threadIdx.x / GG;
-    unsigned* tab = reinterpret_cast<unsigned*>(smem_all + tab_off);
-    Quartet4* hdr = reinterpret_cast<Quartet4*>(smem_all + hdr_off);
-    const int CH = J.chunk;
-    int& s_ib0 = *reinterpret_cast<int*>(hdr + CH);
-
-    double* sm = smem_all + (size_t)gid * NB * J.total;
     const double dmax = __longlong_as_double((long long)scalars[0]);
-    const long long nwi = J.nitems * J.psplit;          // work items: (shell quartet, chunk of bra primitive pairs)
-    const long long nunit = (nwi + CH - 1) / CH;
-    shell4_load_tables<NB>(J.ct, 0, tab, threadIdx.x, blockDim.x, J.oIt, J.oP);
+    const long long nunit = (J.nitems * J.psplit + J.chunk - 1) / J.chunk;
+    shell4_load_tables<NB>(J.ct, 0, reinterpret_cast<unsigned*>(smem_all + J.tab_off), threadIdx.x, blockDim.x, J.oIt, J.oP);
     int tab_chunk = 0;
     double done = 0.0;
-    for (long long gc = (long long)blockIdx.x * nranks + rank; gc < nunit; gc += (long long)gridDim.x * nranks) {
-        const long long first = gc * CH;
-        __syncthreads();                                  // the previous unit's headers are no longer needed (and the tables are in place)
-        if (threadIdx.x == 0) {
-            const long long first_item = first / J.psplit;
-            int lo = 0, hi = J.nbra;                      // invariant: prefix[lo] <= first_item < prefix[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (J.item_prefix[mid] <= first_item) lo = mid; else hi = mid;
-            }
-            s_ib0 = lo;
+    for (long long gc = (long long)blockIdx.x * nranks + rank; gc < nunit; gc += (long long)gridDim.x * nranks)
+        shell4_unit<GG, NB>(J, D, gc, nD, Pf, Psym, Jf, Kf, ncart, tau, dmax, smem_all, tab_chunk, done);
+    if (done != 0.0) atomicAdd(evaluated, done);
+}
+
+// Light class jobs: ALL jobs of one launch geometry (group size, quartets per batch) in ONE persistent launch.  Small systems are bound by
+// the launch count (N2/cc-pVTZ: 231 class jobs of ~10 us each).  The work units of the jobs form one flat list (unit_prefix); a CTA walks
+// it with a grid stride (dealt round-robin to ranks like the single-job kernel) and keeps the descriptor of its current job in shared
+// memory, reloading descriptor and digestion tables when it crosses into the next job.
+template <int GG, int NB>
+__global__ void __launch_bounds__((GG > 128) ? GG : 128, 65536 / (((GG > 128) ? GG : 128) * TUNA_SHELL4_REGS))
+k_shell4_multi(const Shell4Job* __restrict__ jobs, const long long* __restrict__ unit_prefix, int njobs, int job_off, ShellData D, int nD,
+               const double* __restrict__ Pf, const double* __restrict__ Psym, double* Jf, double* Kf, int ncart, double tau,
+               const unsigned long long* scalars, double* evaluated, int rank, int nranks) {
+    extern __shared__ double smem_all[];
+    Shell4Job& J = *reinterpret_cast<Shell4Job*>(smem_all + job_off);          // behind the largest job's areas
+    const double dmax = __longlong_as_double((long long)scalars[0]);
+    const long long nunits = unit_prefix[njobs];
+    int cur = -1, tab_chunk = -1;
+    double done = 0.0;
+    for (long long u = (long long)blockIdx.x * nranks + rank; u < nunits; u += (long long)gridDim.x * nranks) {
+        int lo = 0, hi = njobs;                         // job of this unit (uniform in the CTA)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (unit_prefix[mid] <= u) lo = mid; else hi = mid;
         }
-        __syncthreads();
-        for (int k = threadIdx.x; k < CH; k += blockDim.x) {
-            const long long wi = first + k, item = wi / J.psplit;
-            const int pchunk = (int)(wi - item * J.psplit);
-            Quartet4 h;
-            h.active = 0; h.shA = h.shB = h.shC = h.shD = 0; h.ia0 = 0; h.w = 0.0; h.recA = h.recC = 0; h.pA = h.pC = 1.0; h.zA = h.zC = 0.0;
-            if (wi < nwi) {
-                int ib = s_ib0;
-                h.ia0 = pchunk * J.clen;
-                while (J.item_prefix[ib + 1] <= item) ++ib;
-                const int pab = J.bra_list[ib], pcd = J.ket_list[(int)(item - J.item_prefix[ib])];
-                h.active = !(tau > 0.0 && D.pairQ[pab] * D.pairQ[pcd] * dmax < tau);
-                h.shA = D.pairA[pab]; h.shB = D.pairB[pab]; h.shC = D.pairA[pcd]; h.shD = D.pairB[pcd];
-                const bool ab = h.shA == h.shB, cd = h.shC == h.shD, dg = pab == pcd;
-                h.w = (ab ? 0.5 : 1.0) * (cd ? 0.5 : 1.0) * (dg ? 0.5 : 1.0);
-                h.recA = D.pair_rec[pab]; h.recC = D.pair_rec[pcd];
-                if (h.active) {
-                    h.pA = D.rec[h.recA]; h.zA = D.rec[h.recA + 1]; h.pC = D.rec[h.recC]; h.zC = D.rec[h.recC + 1];
-                    if (pchunk == 0) done += J.uniq[dg ? (ab ? 5 : 4) : (ab ? (cd ? 3 : 1) : (cd ? 2 : 0))];
-                }
-            }
-            hdr[k] = h;
+        if (lo != cur) {
+            __syncthreads();                            // everybody is done with the previous job's descriptor and tables
+            const int* src = reinterpret_cast<const int*>(jobs + lo);
+            int* dst = reinterpret_cast<int*>(&J);
+            for (int x = threadIdx.x; x < (int)(sizeof(Shell4Job) / sizeof(int)); x += blockDim.x) dst[x] = src[x];
+            __syncthreads();
+            shell4_load_tables<NB>(J.ct, 0, reinterpret_cast<unsigned*>(smem_all + J.tab_off), threadIdx.x, blockDim.x, J.oIt, J.oP);
+            cur = lo; tab_chunk = 0;
         }
-        __syncthreads();
-        for (int k0 = 0; k0 < CH; k0 += gpc * NB)
-            shell4_quartets<DevPolicy<GG>, NB>(J, D, hdr + k0 + gid * NB, sm, tab, tab_chunk, nD, Pf, Psym, Jf, Kf, ncart);
+        shell4_unit<GG, NB>(J, D, u - unit_prefix[lo], nD, Pf, Psym, Jf, Kf, ncart, tau, dmax, smem_all, tab_chunk, done);
     }
     if (done != 0.0) atomicAdd(evaluated, done);
 }
@@ -1181,7 +1227,7 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     ctx->nbf = 0;
     build_shell_tab(ctx->stab);
     ctx->shell_ready = false;
-    for (auto& js : ctx->jobsets4) dev_free(&js.d_prefix);
+    for (auto& js : ctx->jobsets4) { dev_free(&js.d_prefix); for (auto& g : js.groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); } }
     ctx->jobsets4.clear();
     ctx->cur_jobset4 = -1;
     detect_shells(ctx->hb, ctx->stab, ctx->ss);     // ss.ok == false -> direct mode uses the per-component kernel
@@ -1994,7 +2040,12 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
     if ((rc = ensure_shell_pairs(ctx))) return rc;
     for (size_t i = 0; i < ctx->jobsets4.size(); ++i)
         if (ctx->jobsets4[i].tau == tau && ctx->jobsets4[i].nD == nD && ctx->jobsets4[i].shard_n == ctx->shard_n) { ctx->cur_jobset4 = (int)i; return TUNA_OK; }
-    if (ctx->jobsets4.size() >= 6) { CK(cudaStreamSynchronize(ctx->stream)); dev_free(&ctx->jobsets4.front().d_prefix); ctx->jobsets4.erase(ctx->jobsets4.begin()); }
+    if (ctx->jobsets4.size() >= 6) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        dev_free(&ctx->jobsets4.front().d_prefix);
+        for (auto& g : ctx->jobsets4.front().groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
+        ctx->jobsets4.erase(ctx->jobsets4.begin());
+    }
     ctx->jobsets4.emplace_back();
     ctx->cur_jobset4 = (int)ctx->jobsets4.size() - 1;
     tuna_ctx::JobSet4& JS = ctx->jobsets4.back();
@@ -2060,9 +2111,9 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
                 J.chunk = jh.gpc * (int)per;
             }
             const size_t slices = (size_t)jh.gpc * nb * J.total;
-            jh.tab_off = (int)((slices + 1) & ~(size_t)1);
-            jh.hdr_off = jh.tab_off + (ctd->host.tab_words + 4 + 1) / 2;
-            jh.smem = ((size_t)jh.hdr_off + (size_t)J.chunk * sizeof(Quartet4) / 8 + 2) * sizeof(double);
+            J.tab_off = (int)((slices + 1) & ~(size_t)1);
+            J.hdr_off = J.tab_off + (ctd->host.tab_words + 4 + 1) / 2;
+            jh.smem = ((size_t)J.hdr_off + (size_t)J.chunk * sizeof(Quartet4) / 8 + 2) * sizeof(double);
             if (jh.smem > 226 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 226 KB");
             jobs4.push_back(jh);
         }
@@ -2073,6 +2124,44 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
     std::stable_sort(jobs4.begin(), jobs4.end(), [](const tuna_ctx::Job4Host& x, const tuna_ctx::Job4Host& y) {
         return x.allowed * (double)x.job.nitems > y.allowed * (double)y.job.nitems;
     });
+    // light class jobs (two quartets per batch, little work) share one persistent launch per group size; the others get their own launch
+    {
+        // a job that cannot fill the GPU once with its own work units (TUNA_B200_OWN_LAUNCH_UNITS per SM and rank, default 2) is "light":
+        // measured, the shared-memory descriptor of the grouped kernel costs ~25 % per quartet, so jobs with plenty of units keep their
+        // own launch (even-tempered sweep), while the hundreds of tiny class jobs of a contracted basis collapse into a few launches
+        // (N2/cc-pVTZ 231 -> 19 launches, 3.0 -> 1.5 ms per direct build)
+        const char* et = getenv("TUNA_B200_OWN_LAUNCH_UNITS");
+        const double per_sm = et ? atof(et) : 2.0;
+        for (auto& jh : jobs4) {
+            const double units = (double)((jh.job.nitems * jh.job.psplit + jh.job.chunk - 1) / jh.job.chunk);
+            jh.own_launch = jh.nb != 2 || units >= per_sm * ctx->sm_count * ctx->shard_n;
+        }
+        for (int G = 256; G >= 1; G >>= 1) {
+            std::vector<Shell4Job> js;
+            std::vector<long long> up(1, 0);
+            size_t max_smem = 0;
+            int threads = 128;
+            for (const auto& jh : jobs4) {
+                if (jh.own_launch || jh.G != G) continue;
+                js.push_back(jh.job);
+                up.push_back(up.back() + (jh.job.nitems * jh.job.psplit + jh.job.chunk - 1) / jh.job.chunk);
+                max_smem = std::max(max_smem, jh.smem);
+                threads = jh.threads;
+            }
+            if (js.size() < 2) { for (auto& jh : jobs4) if (!jh.own_launch && jh.G == G) jh.own_launch = true; continue; }
+            tuna_ctx::Group4 g;
+            g.G = G; g.threads = threads; g.njobs = (int)js.size(); g.nunits = up.back();
+            g.job_off = (int)(((max_smem + 7) / 8 + 1) & ~(size_t)1);
+            g.smem = (size_t)g.job_off * 8 + sizeof(Shell4Job) + 16;
+            g.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / threads, (228 * 1024) / (g.smem + 1024)));
+            if ((rc = dev_alloc(ctx, &g.d_jobs, js.size()))) return rc;
+            if ((rc = dev_alloc(ctx, &g.d_unit_prefix, up.size()))) return rc;
+            CK(cudaMemcpyAsync(g.d_jobs, js.data(), js.size() * sizeof(Shell4Job), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(g.d_unit_prefix, up.data(), up.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            JS.groups.push_back(g);
+        }
+    }
     if (const char* dump = getenv("TUNA_B200_DUMP_JOBS")) {       // development aid: the job table in launch order
         if (FILE* f = fopen(dump, "w")) {
             fprintf(f, "idx,La,Lb,Lc,Ld,nppAB,nppCD,G,nb,threads,smem,total,nout,nint,itmax,nchunk,nitems,allowed,own\n");
@@ -2080,7 +2169,7 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             for (const auto& jh : jobs4)
                 fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%zu,%d,%d,%d,%d,%d,%lld,%.0f,%d\n", idx++, jh.job.La, jh.job.Lb, jh.job.Lc, jh.job.Ld, jh.job.nppAB,
                         jh.job.nppCD, jh.G, jh.nb, jh.threads, jh.smem, jh.job.total, jh.job.ct.nwork, jh.job.ct.itmax, jh.job.ct.itmax, jh.job.ct.nchunk,
-                        jh.job.nitems, jh.allowed, 1);
+                        jh.job.nitems, jh.allowed, (int)jh.own_launch);
             fclose(f);
         }
     }
@@ -2092,7 +2181,7 @@ static cudaError_t launch_shell4_one_r(tuna_ctx* ctx, const tuna_ctx::Job4Host& 
                                        double* Jf, double* Kf, double tau, cudaStream_t stream, long long blocks) {
     if (cudaError_t e = opt_in_smem<k_shell4_one<GG, NB, REGS>>(ctx); e != cudaSuccess) return e;
     k_shell4_one<GG, NB, REGS><<<(int)blocks, jh.threads, jh.smem, stream>>>(jh.job, D, nD, Pf, Psym, Jf, Kf, ctx->ncart, tau, ctx->d_scalars, ctx->d_eval,
-                                                                            ctx->shard_rank, ctx->shard_n, jh.tab_off, jh.hdr_off);
+                                                                            ctx->shard_rank, ctx->shard_n);
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -2124,6 +2213,7 @@ static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const dou
     for (int a = 0; a < ctx->naux; ++a) CK(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_fork, 0));
     int jn = 0;
     for (const auto& jh : ctx->jobsets4[ctx->cur_jobset4].jobs) {
+        if (!jh.own_launch) continue;
         cudaStream_t st = ctx->aux[jn++ % ctx->naux];
         cudaError_t e;
 #define TUNA_ONE4(GV) (jh.nb == 4 ? launch_shell4_one<GV, 4>(ctx, jh, D, nD, Pc, Psym, Jc, Kc, tau, st) \
@@ -2142,6 +2232,33 @@ static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const dou
         }
 #undef TUNA_ONE4
         if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell4_one launch: ") + cudaGetErrorString(e));
+    }
+    for (const auto& g : ctx->jobsets4[ctx->cur_jobset4].groups) {
+        cudaStream_t st = ctx->aux[jn++ % ctx->naux];
+        long long blocks = (g.nunits - ctx->shard_rank + ctx->shard_n - 1) / ctx->shard_n;       // units owned by this rank
+        if (blocks <= 0) continue;
+        blocks = std::min<long long>(blocks, (long long)ctx->sm_count * g.ctas_per_sm);
+        cudaError_t e = cudaSuccess;
+#define TUNA_MULTI4(GV) \
+        if ((e = opt_in_smem<k_shell4_multi<GV, 2>>(ctx)) == cudaSuccess) { \
+            k_shell4_multi<GV, 2><<<(int)blocks, g.threads, g.smem, st>>>(g.d_jobs, g.d_unit_prefix, g.njobs, g.job_off, D, nD, Pc, Psym, Jc, Kc, ctx->ncart, tau, \
+                                                                       ctx->d_scalars, ctx->d_eval, ctx->shard_rank, ctx->shard_n); \
+            e = cudaGetLastError(); \
+        }
+        switch (g.G) {
+            case 1: TUNA_MULTI4(1) break;
+            case 2: TUNA_MULTI4(2) break;
+            case 4: TUNA_MULTI4(4) break;
+            case 8: TUNA_MULTI4(8) break;
+            case 16: TUNA_MULTI4(16) break;
+            case 32: TUNA_MULTI4(32) break;
+            case 64: TUNA_MULTI4(64) break;
+            case 128: TUNA_MULTI4(128) break;
+            default: TUNA_MULTI4(256) break;
+        }
+#undef TUNA_MULTI4
+        ctx->launches++;
+        if (e != cudaSuccess) FAIL(TUNA_ERR_CUDA, std::string("k_shell4_multi launch: ") + cudaGetErrorString(e));
     }
     for (int a = 0; a < ctx->naux; ++a) {
         CK(cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
