@@ -354,7 +354,8 @@ def bench_stored(torch, wl, steps, warmup, device):
            "eri_fill_ms": float(min(t_fill)), "cart_to_sph_ms": float(min(t_sph)),
            "eri_quartets_per_s": c["surviving_quartets"] / (min(t_fill) * 1e-3),
            "roofline": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": src, "kernel": "k_jk_stored_sym + k_sym_reduce (whole J/K build: both launches, CUDA events of the context)",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "traffic": (executed_fp64_table().get(f"stored:{wl['name']}") or {}).get("dram_bytes_per_launch"), "peak_source": src, "kernel": "k_jk_stored_sym + k_sym_reduce (whole J/K build: both launches, CUDA events of the context)",
                         "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes},
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * nD * n * n), "d2h_bytes_per_step": int(16 * nD * n * n)},
            "gpu_launches": int(launches)}
@@ -401,7 +402,8 @@ def bench_mo_transform(torch, ctx, wl, fp64_peak, flush):
     return {"workload": f"AO->MO transformation of the stored tensor (nbf {n}, square C), tuna_ci.py:204-255", "value": 1e3 / k_ms, "unit": "transforms/s",
             "ms_per_step": k_ms, "max_abs_diff_vs_oracle": err,
             "roofline": {"bound": "fp64", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": flops / (k_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None, "traffic": None, "kernel": "k_axis_gemm x4",
+                         "frac": flops / (k_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                         "traffic": (executed_fp64_table().get(f"mo:{wl['name']}") or {}).get("dram_bytes_per_launch"), "kernel": "k_axis_gemm x4",
                          "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes, "hbm_gbs": alg_bytes / (k_ms * 1e-3) / 1e9},
             "e2e": {"value": 1.0 / e2e_s, "unit": "transforms/s", "h2d_bytes_per_step": int(8 * n * n), "d2h_bytes_per_step": int(8 * n ** 4)},
             "cpu_baseline": {"value": 1.0 / min(tc), "unit": "transforms/s", "cores": host_threads(), "kind": "port",

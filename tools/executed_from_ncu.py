@@ -13,7 +13,26 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def traffic():
+    """--traffic <csv> <key> <kernel substring>: mean DRAM bytes (read + write) and duration per launch of the matching kernels."""
+    path, key, pat = sys.argv[2], sys.argv[3], sys.argv[4]
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit() and pat in r[4]]
+    t = collections.defaultdict(dict)
+    for r in rows:
+        t[int(r[0])][r[12]] = float(r[14].replace(",", ""))
+    n = max(1, len(t))
+    dram = sum(v.get("dram__bytes_read.sum", 0.0) + v.get("dram__bytes_write.sum", 0.0) for v in t.values()) / n
+    ns = sum(v.get("gpu__time_duration.sum", 0.0) for v in t.values()) / n
+    out = os.path.join(ROOT, "profiles", "executed_fp64.json")
+    table = json.load(open(out)) if os.path.exists(out) else {}
+    table[key] = {"dram_bytes_per_launch": dram, "ncu_us_per_launch": ns / 1e3, "launches": len(t), "kernel": pat, "source": os.path.relpath(os.path.abspath(path), ROOT)}
+    json.dump(table, open(out, "w"), indent=1)
+    print(json.dumps(table[key], indent=1))
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic()
     path, key = sys.argv[1], sys.argv[2]
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
     t = collections.defaultdict(dict)

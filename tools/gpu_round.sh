@@ -16,6 +16,8 @@ timeout 600 python bench.py > $O/${R}_bench_n1.json 2> $O/${R}_bench_n1.err; ste
 M=gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,dram__bytes_read.sum,dram__bytes_write.sum
 step "ncu per-class counters (one ET800 build)"
 TUNA_B200_DUMP_JOBS=$O/${R}_jobs800.csv timeout 500 ncu --metrics $M --clock-control none --csv --log-file $O/${R}_class_metrics.csv -k regex:k_shell4 -c 231 python tools/direct_timing.py child 800 > $O/${R}_ncu_c.log 2>&1; step "rc=$?"
+step "ncu DRAM traffic of the stored J/K and AO->MO kernels (N2/cc-pVTZ)"
+timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/${R}_stored_mo_traffic.csv -k regex:"k_jk_stored|k_sym_reduce|k_axis_gemm" python tools/stored_check.py profile n2_ccpvtz > $O/${R}_ncu_t.log 2>&1; step "rc=$?"
 step "ncu launch list of the bench command"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${R}_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-stored > $O/${R}_ncu_l.log 2>&1; step "rc=$?"
 step "ncu full capture of the heaviest class job"

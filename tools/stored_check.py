@@ -32,16 +32,17 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps({"name": name, "n": n, "kernel": os.environ.get("TUNA_B200_STORED_KERNEL", "sym"), "ms_median": float(np.median(ts)), "ms_min": float(min(ts)),
                       "GBps": 8.0 * n ** 4 / (np.median(ts) * 1e-3) / 1e9}))
 elif len(sys.argv) > 1 and sys.argv[1] == "profile":
-    # ncu target (tools/final_r01.sh): one stored J/K build (nD = 2) and one AO->MO transformation on Ne2 UHF/cc-pVQZ (nbf 110, 1.17 GB)
+    # ncu target (tools/gpu_round.sh): one stored J/K build and one AO->MO transformation of a golden workload (default Ne2 UHF/cc-pVQZ, 1.17 GB)
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
     import tuna_b200
     from util import load_golden, context_for
-    g = load_golden("ne2_uhf_ccpvqz")
+    wname = sys.argv[2] if len(sys.argv) > 2 else "ne2_uhf_ccpvqz"
+    g = load_golden(wname)
     ctx = context_for(g); ctx.set_transform(g["U"]); ctx.eri_fill_cart(); ctx.eri_cart_to_sph()
     n = int(g["nbf"])
     rng = np.random.default_rng(5)
-    P = rng.standard_normal((2, n, n)); P = P + P.transpose(0, 2, 1)
+    P = rng.standard_normal((2 if bool(g["unrestricted"]) else 1, n, n)); P = P + P.transpose(0, 2, 1)
     J, K = ctx.jk_stored(P)
     print("stored ms", ctx.last_kernel_ms(2), flush=True)
     C = np.linalg.qr(rng.standard_normal((n, n)))[0]
