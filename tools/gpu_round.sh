@@ -19,7 +19,7 @@ TUNA_B200_DUMP_JOBS=$O/${R}_jobs800.csv timeout 500 ncu --metrics $M --clock-con
 step "ncu DRAM traffic of the stored J/K and AO->MO kernels (N2/cc-pVTZ)"
 timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/${R}_stored_mo_traffic.csv -k regex:"k_jk_stored|k_sym_reduce|k_axis_gemm" python tools/stored_check.py profile n2_ccpvtz > $O/${R}_ncu_t.log 2>&1; step "rc=$?"
 step "ncu launch list of the bench command"
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${R}_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-stored > $O/${R}_ncu_l.log 2>&1; step "rc=$?"
+timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file $O/${R}_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-stored > $O/${R}_ncu_l.log 2>&1; step "rc=$?"
 step "ncu full capture of the heaviest class job"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_shell4_one -s 0 -c 1 -f -o $O/${R}_prof_shell python tools/direct_timing.py child 800 > $O/${R}_ncu_s.log 2>&1; step "rc=$?"
 ncu -i $O/${R}_prof_shell.ncu-rep --page raw --csv > $O/${R}_prof_shell_raw.csv 2>/dev/null

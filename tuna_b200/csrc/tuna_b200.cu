@@ -808,8 +808,11 @@ struct DevPolicy {
 // ---- generation-4 engine: one class job per launch, the descriptor travels as a kernel parameter ------------------------------
 // A CTA work unit (= multi-GPU sharding unit) is J.chunk consecutive shell quartets; the unit's quartets are decoded ONCE (item ->
 // bra / ket pair, Schwarz test, degeneracy weight) into shared-memory headers, then the CTA's groups take them NB at a time.
+// Register budget of the engine kernels.  Measured on the B200 (profiles/r02u_register_budget.log): 64 -> 1297 ms per ET800 build (208 B of
+// spills in the two-quartet instantiations), 72 -> 1254, 80 -> 1205, 88 -> 1231, 96 -> 1231: 80 registers remove the spills at 3/4 of the
+// thread occupancy, which the latency-bound phases tolerate.
 #ifndef TUNA_SHELL4_REGS
-#define TUNA_SHELL4_REGS 64
+#define TUNA_SHELL4_REGS 80
 #endif
 // One CTA work unit: decode the unit's work items ONCE (item -> bra / ket pair, Schwarz test, degeneracy weight, record offsets) into the
 // shared-memory headers, then let the CTA's groups take them NB at a time.
