@@ -175,3 +175,27 @@ def test_mode_selection_follows_the_reference_dispatch():
     finally:
         provider._free_device_bytes = saved
         provider.configure(mode="auto")
+
+
+def test_engine_sass_has_no_floating_point_atomics():
+    """North star part 4 / DESIGN.md section 4: the shell-quartet engine accumulates J/K as 64-bit INTEGER words (order independent, bitwise
+    reproducible); its kernels must contain no FP64 atomics.  (`k_jk_direct`, the per-component fallback for bases that do not group into
+    full shells, still uses them and is excluded.)  The AO->MO step must sit on the FP64 tensor cores (SASS DMMA)."""
+    import shutil
+    import subprocess
+    from tuna_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    fn, bad, seen_engine, dmma = "", set(), False, False
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            seen_engine = seen_engine or "k_shell4_" in fn
+        elif "k_shell4_" in fn and ("RED" in line or "ATOM" in line) and "F64" in line:
+            bad.add(fn)
+        elif "k_axis_gemm" in fn and "DMMA" in line:
+            dmma = True
+    assert seen_engine and not bad, sorted(bad)[:3]
+    assert dmma

@@ -880,7 +880,7 @@ k_shell4_one(Shell4Job J, ShellData D, int nD, const double* __restrict__ Pf, co
     double done = 0.0;
     for (long long gc = (long long)blockIdx.x * nranks + rank; gc < nunit; gc += (long long)gridDim.x * nranks)
         shell4_unit<GG, NB>(J, D, gc, nD, Pf, Psym, Jf, Kf, ncart, tau, dmax, smem_all, tab_chunk, done);
-    if (done != 0.0) atomicAdd(evaluated, done);
+    if (done != 0.0) atomicAdd(reinterpret_cast<unsigned long long*>(evaluated), (unsigned long long)(done + 0.5));      // integer counter: no FP64 atomics in the engine
 }
 
 // Light class jobs: ALL jobs of one launch geometry (group size, quartets per batch) in ONE persistent launch.  Small systems are bound by
@@ -915,7 +915,7 @@ k_shell4_multi(const Shell4Job* __restrict__ jobs, const long long* __restrict__
         }
         shell4_unit<GG, NB>(J, D, u - unit_prefix[lo], nD, Pf, Psym, Jf, Kf, ncart, tau, dmax, smem_all, tab_chunk, done);
     }
-    if (done != 0.0) atomicAdd(evaluated, done);
+    if (done != 0.0) atomicAdd(reinterpret_cast<unsigned long long*>(evaluated), (unsigned long long)(done + 0.5));      // integer counter: no FP64 atomics in the engine
 }
 
 // reproducible accumulation: (hi, lo) integer words -> FP64 (fixed_value), J and K in one launch
@@ -2436,9 +2436,7 @@ int tuna_get_counts(const tuna_ctx* c, int64_t counts[8]) {
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(&ev, ctx->d_scalars + 1, sizeof(ev), cudaMemcpyDeviceToHost);
         if (ctx->direct_engine == 1 && ctx->ss.ok && ctx->d_eval) {
-            double dv = 0.0;
-            cudaMemcpy(&dv, ctx->d_eval, sizeof(dv), cudaMemcpyDeviceToHost);
-            ev = (unsigned long long)(dv + 0.5);
+            cudaMemcpy(&ev, ctx->d_eval, sizeof(ev), cudaMemcpyDeviceToHost);      // the engine counts evaluated quartets in a 64-bit integer
         }
     }
     counts[0] = ctx->pt.npair; counts[1] = ctx->n_unique; counts[2] = ctx->n_surviving; counts[3] = ctx->n_primq;
