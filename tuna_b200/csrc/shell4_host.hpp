@@ -34,7 +34,7 @@ struct Class4Host {
 
 constexpr int S4_IT_BUDGET = 6144;     // doubles of shared memory for the integral buffer of a chunk
 constexpr int S4_S_BUDGET = 4096;      // doubles for the S slice of a chunk
-constexpr int S4_TERM_MAX = 3072;      // digestion terms up to which a single-chunk class keeps its term lists in shared memory (term mode)
+constexpr int S4_TERM_MAX = 4096;      // digestion terms up to which a single-chunk class keeps its term lists in shared memory (term mode)
 
 inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld, Class4Host& C, int it_budget = S4_IT_BUDGET,
                                 int s_budget = S4_S_BUDGET, int term_max = S4_TERM_MAX) {

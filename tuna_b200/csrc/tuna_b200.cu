@@ -109,9 +109,14 @@ struct tuna_ctx {
     // direct SCF alternates between thresholds rarely - none of that may rebuild lists or reallocate inside a Fock build
     struct Group4 { int G = 1, threads = 128, njobs = 0, job_off = 0, ctas_per_sm = 1; long long nunits = 0; size_t smem = 0;
                     Shell4Job* d_jobs = nullptr; long long* d_unit_prefix = nullptr; };      // light jobs of one group size in one persistent launch
-    struct JobSet4 { double tau = -1.0; int nD = 0, shard_n = 0; std::vector<Job4Host> jobs; std::vector<Group4> groups; long long* d_prefix = nullptr; };
+    struct JobSet4 { double tau = -1.0, dens_bound = 0.0; int nD = 0, shard_n = 0; std::vector<Job4Host> jobs; std::vector<Group4> groups; long long* d_prefix = nullptr; };
     std::vector<JobSet4> jobsets4;
     int cur_jobset4 = -1;
+    // The job lists are pre-screened on the host with tau / dens_bound, dens_bound = an upper bound of max |P| in the engine's working
+    // basis; the device applies the exact test Q_ab Q_cd max|P| < tau.  1e3 covers |P| <= ~10 in the spherical basis (the Cartesian
+    // back-rotation of an h shell can amplify by ~1e2).  tuna_jk_direct raises it for larger host densities; callers of the _dev entry
+    // point with larger densities scale them down (J and K are linear in P).
+    double dens_bound = 1e3;
     long long* d_fix = nullptr; size_t cap_fix = 0;      // reproducible accumulation: [J hi | J lo | K hi | K lo], nD * ncart^2 words each
     CsrDev Uf, Uft;                 // U * diag(f) and its transpose: per-component norms folded into the rotation
     int direct_engine = 1;          // 1 = shell engine when the basis groups into shells, 0 = per-component kernel
@@ -2042,7 +2047,10 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
     int rc;
     if ((rc = ensure_shell_pairs(ctx))) return rc;
     for (size_t i = 0; i < ctx->jobsets4.size(); ++i)
-        if (ctx->jobsets4[i].tau == tau && ctx->jobsets4[i].nD == nD && ctx->jobsets4[i].shard_n == ctx->shard_n) { ctx->cur_jobset4 = (int)i; return TUNA_OK; }
+        if (ctx->jobsets4[i].tau == tau && ctx->jobsets4[i].nD == nD && ctx->jobsets4[i].shard_n == ctx->shard_n && ctx->jobsets4[i].dens_bound >= ctx->dens_bound) {
+            ctx->cur_jobset4 = (int)i;
+            return TUNA_OK;
+        }
     if (ctx->jobsets4.size() >= 6) {
         CK(cudaStreamSynchronize(ctx->stream));
         dev_free(&ctx->jobsets4.front().d_prefix);
@@ -2052,7 +2060,7 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
     ctx->jobsets4.emplace_back();
     ctx->cur_jobset4 = (int)ctx->jobsets4.size() - 1;
     tuna_ctx::JobSet4& JS = ctx->jobsets4.back();
-    JS.tau = tau; JS.nD = nD; JS.shard_n = ctx->shard_n;
+    JS.tau = tau; JS.nD = nD; JS.shard_n = ctx->shard_n; JS.dens_bound = ctx->dens_bound;
     std::vector<tuna_ctx::Job4Host>& jobs4 = JS.jobs;
     const ShellSystem& S = ctx->ss;
     const int ncls = (int)S.classes.size();
@@ -2081,7 +2089,7 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             }
             { const char* dbg = getenv("TUNA_B200_DBG_SKIP"); J.dbg_skip = dbg ? atoi(dbg) : 0; }
             std::vector<long long> prefix;
-            J.nitems = build_item_prefix(S, cb, ck, tau * 1e-3, prefix);
+            J.nitems = build_item_prefix(S, cb, ck, tau / ctx->dens_bound, prefix);
             if (J.nitems == 0) continue;
             J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
             J.bra_list = ctx->d_class_lists + ctx->class_list_off[cb];
@@ -2391,6 +2399,7 @@ int tuna_jk_direct(tuna_ctx* ctx, int nD, const double* P, double* J, double* K,
                 amax = std::max(amax, std::fabs(x - y));
             }
     const bool general = amax > 1e-15 * pmax;
+    ctx->dens_bound = std::max(1e3, 1e3 * pmax);          // static pre-screening stays below the device's exact density-weighted test
     const int nDrun = general ? 2 * nD : nD;
     int rc;
     if ((rc = ensure_mats(ctx, nDrun, nb, ctx->ncart))) return rc;
