@@ -3,18 +3,18 @@
 // Same mathematics and the same phases 0-3 as shell_jk.cuh (Boys values -> R^n_w and the x/y convolution table -> ket z
 // contraction U -> bra z contraction S); replaces, at shell granularity, the primitive-quartet evaluation of
 // TUNA/tuna_integrals/tuna_integral.pyx:1142-1253 and the quartet driver :1312-1342, and digests straight into J/K
-// (TUNA/tuna_scf.py:27-72) so that no N^4 tensor exists.  What changed against generation 2, and why (ncu, profiles/r02a_*):
+// (TUNA/tuna_scf.py:27-72) so that no N^4 tensor exists.  What changed against the round-1 engine (streamed term tables), and why (ncu, profiles/r02a_*):
 //   * the streamed per-class term tables of the digestion are gone.  The integral buffer of a chunk is laid out as
 //       slot(beta, gamma) = Rb[beta] + Cg[gamma]      beta = bra pair function (ax+bx, ay+by, az, bz), gamma likewise for the ket,
 //     rows grouped by x/y parity class so that a row holds exactly the allowed gammas.  Every K accumulator walks
 //     (other bra component) x (other ket component) with two small shared-memory tables (components sorted by parity group, the
 //     inner group padded to pairs whose staged density is zero); J accumulators are contiguous row / strided column dot
-//     products.  Generation 2 streamed 4-8 bytes of table per FMA from L2 (the variant with half the instructions and twice the
+//     products.  The round-1 engine streamed 4-8 bytes of table per FMA from L2 (the variant with half the instructions and twice the
 //     table bytes was SLOWER, profiles/r02a_variants.log).
 //   * integral assembly is tiled over two z combinations that share the x/y operands (kept in registers, m' loop unrolled per
 //     trip count), and S is only formed for (lz12, lz34) blocks of even total parity (the others never feed an integral).
 //   * per-quartet bookkeeping (item decode, prefactor, record staging) is done once per quartet instead of once per lane.
-// The body is written against a Policy like generation 2: DevPolicy<G> is the sm_100a kernel, HostPolicy the CPU unit-test build.
+// The body is written against a Policy: DevPolicy<G> is the sm_100a kernel, HostPolicy the CPU unit-test build.
 #pragma once
 #include "shell_jk.cuh"
 

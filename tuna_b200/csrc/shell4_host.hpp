@@ -104,7 +104,7 @@ inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int L
     for (int pc = 1; pc < 4; ++pc) C.pgoff[pc] = C.pgoff[pc - 1] + C.ncols[pc - 1];
     C.zrow = std::max(std::max(C.ncols[0], C.ncols[1]), std::max(C.ncols[2], C.ncols[3]));
 
-    // ---- phase 1-2 work lists (as generation 2) ------------------------------------------------------------------------------
+    // ---- phase 1-2 work lists  ------------------------------------------------------------------------------
     for (int w = 0; w <= Ltot; ++w)
         for (int n = 0; 2 * n + w <= Ltot; ++n) C.t_rt.push_back((unsigned)(w * NS + n) | (unsigned)w << 16 | (unsigned)n << 24);
     for (int n12 = 0; n12 <= Lab; ++n12)

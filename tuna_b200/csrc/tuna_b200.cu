@@ -4,8 +4,12 @@
 //   k_eri_fill        FP64 ERI over class-sorted AO-pair quartets, 8-fold symmetric scatter into the dense tensor
 //   k_schwarz         Q_ij = sqrt((ij|ij))
 //   k_rotate_axis     one index of the Cartesian->spherical rotation (sparse U), used 4x for the tensor, 2x for matrices
-//   k_jk_stored<ND>   fused single-pass J+K over the resident dense tensor (HBM-bound), atomic-free
-//   k_jk_direct       integral-driven J/K with 8-fold symmetry + Schwarz screening (FP64-pipe-bound)
+//   k_jk_stored_sym / _tma / k_jk_stored   fused single-pass J+K over the resident dense tensor (HBM-bound), atomic-free
+//   k_shell4_one / k_shell4_multi          direct J/K: the shell-quartet engine of shell4.cuh (one class job per launch / all light
+//                                          class jobs of one group size in one persistent launch), reproducible integer accumulation
+//   k_jk_direct       per-component direct J/K for bases that do not group into full shells (FP64 atomics)
+//   k_axis_gemm, k_spin_block              AO->MO / spin-orbital transformation on the FP64 tensor cores (mo_transform.cuh)
+//   k_one_electron, k_cross_overlap        one-electron integrals (oneel_core.cuh)
 // Reference being replaced: TUNA/tuna_integrals/tuna_integral.pyx:1267-1355 (ERI driver), TUNA/tuna_kernel.py:504-523
 // (rotation), TUNA/tuna_scf.py:27-72 (J/K einsums).  No CPU fallback exists in this file.
 #include <cuda_runtime.h>
@@ -2042,7 +2046,7 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     return TUNA_OK;
 }
 
-// Job list of the generation-4 engine for threshold tau and nD densities (pair data shared with generation 2).
+// Job list of the shell-quartet engine for threshold tau and nD densities.
 static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
     int rc;
     if ((rc = ensure_shell_pairs(ctx))) return rc;

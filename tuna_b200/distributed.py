@@ -2,14 +2,14 @@
 
 J and K are linear in the integrals, so any partition of the unique-quartet list gives partial J/K that sum.
 Every rank holds the whole pair table and density; rank r evaluates the chunks c with c % nranks == r of every job's work list
-(`shard_chunks`; mirrored on the device by k_shell_jk with 4 shell quartets per group of the job's CTA shape per chunk and by k_jk_direct with
-1024 AO quartets per chunk, csrc/tuna_b200.cu), and the partial (J, K) stack — 2 * nD * nbf^2
+(`shard_chunks`; mirrored on the device by k_shell4_one / k_shell4_multi with one CTA work unit of 2-16 work items per group per chunk and by
+k_jk_direct with 1024 AO quartets per chunk, csrc/tuna_b200.cu), and the partial (J, K) stack — 2 * nD * nbf^2
 doubles — is summed with ONE NCCL all-reduce on the compute stream.  torch is plumbing here: device buffers,
 the stream, and torch.distributed.
 """
 import numpy as np
 
-CHUNK = 128    # shell quartets per scheduling chunk of k_shell_jk (k_jk_direct uses 1024 AO quartets)
+CHUNK = 128    # items per scheduling chunk of the host-side model of the sharding (tests/test_distributed_cpu.py)
 
 
 def shard_chunks(n_quartets: int, rank: int, nranks: int, chunk: int = CHUNK):
