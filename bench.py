@@ -353,6 +353,10 @@ def bench_stored(torch, wl, steps, warmup, device):
            "l2": L2_NOTE + "; the 8*nbf^4 tensor is read from HBM",
            "eri_fill_ms": float(min(t_fill)), "cart_to_sph_ms": float(min(t_sph)),
            "eri_quartets_per_s": c["surviving_quartets"] / (min(t_fill) * 1e-3),
+           "eri_fill": {"kernels": "k_shell4_multi / k_shell4_one (fill mode) + k_fill_scatter", "ms": float(min(t_fill)),
+                        "tensor_write_GBps": 8.0 * wl["ncart"] ** 4 / (min(t_fill) * 1e-3) / 1e9,
+                        "note": "Cartesian tensor of 8*ncart^4 bytes built by the shell-quartet engine (scratch rows of the unique integrals, then "
+                                "the eight images); not HBM-bound at this size: the class jobs are short latency chains"},
            "roofline": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                         "traffic": (executed_fp64_table().get(f"stored:{wl['name']}") or {}).get("dram_bytes_per_launch"), "peak_source": src, "kernel": "k_jk_stored_sym + k_sym_reduce (whole J/K build: both launches, CUDA events of the context)",

@@ -48,7 +48,10 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
  * (tuna_kernel.py:540-649).  Pass the identity for CARTHARM (tuna_kernel.py:481-483). */
 int tuna_set_transform(tuna_ctx* ctx, int nbf, const double* U);
 
-/* calculate_electron_repulsion_integrals (pyx:1267-1355): fill the dense Cartesian tensor ncart^4 on the device. */
+/* calculate_electron_repulsion_integrals (pyx:1267-1355): fill the dense Cartesian tensor ncart^4 on the device.  Contracted bases
+ * that group into shells run the shell-quartet engine in fill mode plus a fixed-order scatter pass (bitwise reproducible); other
+ * bases one thread per AO quartet (TUNA_B200_FILL_ENGINE=0/1 forces either).  Same tensor both ways: one value in all eight
+ * symmetric images, exact zeros where x/y parity forbids the integral (pyx:1324-1327). */
 int tuna_eri_fill_cart(tuna_ctx* ctx);
 /* transform_to_spherical_harmonics, ERI part (tuna_kernel.py:504-523): (U (x) U) ERI (U (x) U)^T on the device.
  * keep_cart != 0 keeps the Cartesian tensor resident as well. */

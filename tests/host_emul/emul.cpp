@@ -77,6 +77,8 @@ struct HostPolicy {
     static void sync_cta() {}
     static int cta_thread() { return 0; }
     static int cta_threads() { return 1; }
+    static long long& row0() { static long long r = 0; return r; }           // fill mode: work item of the batch's first header (set by the driver)
+    static long long work_item_of(const Shell4Job&, const Quartet4*) { return row0(); }
     static void accumulate(double* M, int idx, double v, long long fix_lo) {
         long long h, l;
         fixed_split(v, h, l);
@@ -131,7 +133,7 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
         for (int ck = 0; ck <= cb; ++ck) {
             Shell4Job J;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
-            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4; J.dbg_skip = 0;
+            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4; J.dbg_skip = 0; J.fill_scratch = nullptr; J.fill_base = 0; J.fill_pairs = nullptr;
             {   // TUNA_EMUL_PSPLIT_TARGET: split contracted shell quartets into work items of bra primitive pairs, as the device launcher does
                 const char* ept = getenv("TUNA_EMUL_PSPLIT_TARGET");
                 const int target = ept ? atoi(ept) : 16;
@@ -198,6 +200,88 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
                 Kout[d * nn + (size_t)i * ncart + j] = ff * (Kf[d * nn + (size_t)i * ncart + j] + Kf[d * nn + (size_t)j * ncart + i]);
             }
     if (stats) { stats[0] = (long long)S.shells.size(); stats[1] = (long long)S.pairA.size(); stats[2] = nitems_total; stats[3] = nskipped; stats[4] = ncls; stats[5] = nint_total; stats[6] = nterm_total; }
+    return 0;
+}
+
+// Dense Cartesian ERI tensor through the engine's fill mode: every work item (shell quartet x primitive chunk) writes its integrals to
+// a scratch row, shell4_fill_scatter sums the chunks and writes the eight images — the same two passes the device runs.
+extern "C" int emul_fill_shell4(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,
+                                const double* ceff, double* out) {
+    HostBasis B = make_basis(ncart, oz, lmn, nprim, off, exps, ceff);
+    PairTable PT;
+    build_pair_table(B, PT);
+    std::vector<double> boys, herm;
+    build_boys_table(boys);
+    build_hermite_poly_table(herm);
+    std::vector<double> aoQ(PT.npair, 1.0);             // no screening in fill mode; the factors only order the lists
+    ShellTab T;
+    build_shell_tab(T);
+    ShellSystem S;
+    if (!detect_shells(B, T, S)) return 1;
+    build_shell_pairs(S, T, PT, aoQ, ncart);
+    ShellData D;
+    D.pairA = S.pairA.data(); D.pairB = S.pairB.data(); D.pair_rec = S.pair_rec.data(); D.rec = S.rec.data(); D.pairQ = S.pairQ.data();
+    D.sh_ao = S.sh_ao.data(); D.boys = boys.data(); D.herm = herm.data(); D.fix_lo = 0;
+    const long long n = ncart;
+    std::memset(out, 0, sizeof(double) * n * n * n * n);      // parity-forbidden elements stay zero, as on the device
+    const int ncls = (int)S.classes.size();
+    for (int cb = 0; cb < ncls; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            Shell4Job J;
+            J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
+            J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4; J.dbg_skip = 0;
+            {
+                const char* ept = getenv("TUNA_EMUL_PSPLIT_TARGET");
+                const int target = ept ? atoi(ept) : 16;
+                const long long tot = (long long)J.nppAB * J.nppCD;
+                J.psplit = (target > 0 && tot > target) ? (int)std::min<long long>(J.nppAB, (tot + target - 1) / target) : 1;
+                J.clen = (J.nppAB + J.psplit - 1) / J.psplit;
+                J.psplit = (J.nppAB + J.clen - 1) / J.clen;
+            }
+            J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
+            std::vector<long long> prefix;
+            J.nitems = build_item_prefix(S, cb, ck, 0.0, prefix);
+            J.item_prefix = prefix.data(); J.nbra = (int)S.classes[cb].pairs.size(); J.same_class = (cb == ck);
+            Class4Host CH;
+            const char* eb = getenv("TUNA_EMUL_IT_BUDGET");
+            if (eb) build_class4_tables(T, J.La, J.Lb, J.Lc, J.Ld, CH, atoi(eb), atoi(eb), 0, true);
+            else build_class4_tables(T, J.La, J.Lb, J.Lc, J.Ld, CH, S4_IT_BUDGET, S4_S_BUDGET, 0, true);
+            J.ct = class4_view(CH, HostPtrOf());
+            shell4_job_layout(J, 0);
+            std::vector<double> scratch((size_t)(J.nitems * J.psplit) * J.ct.nfill, -7.0);       // poisoned: every entry must be written
+            J.fill_scratch = scratch.data(); J.fill_base = 0;
+            std::vector<int> fpairs;
+            for (int ib = 0; ib < J.nbra; ++ib)
+                for (long long k = 0; k < prefix[ib + 1] - prefix[ib]; ++k) { fpairs.push_back(J.bra_list[ib]); fpairs.push_back(J.ket_list[k]); }
+            J.fill_pairs = fpairs.data();
+            const char* enb = getenv("TUNA_EMUL_NB");
+            const int NBATCH = enb ? atoi(enb) : 2;
+            std::vector<double> sm((size_t)4 * J.total);
+            std::vector<unsigned> tab(CH.tab_words + 4);
+            int tab_chunk = -1;
+            Quartet4 hq[4];
+            const long long nwi = J.nitems * J.psplit;
+            for (long long w0 = 0; w0 < nwi; w0 += NBATCH) {
+                for (int q = 0; q < 4; ++q) { hq[q] = Quartet4(); hq[q].active = 0; }
+                for (int q = 0; q < NBATCH && w0 + q < nwi; ++q) {
+                    const long long item = (w0 + q) / J.psplit;
+                    const int pchunk = (int)((w0 + q) - item * J.psplit);
+                    int ib = 0, hi = J.nbra;
+                    while (hi - ib > 1) { const int mid = (ib + hi) >> 1; if (prefix[mid] <= item) ib = mid; else hi = mid; }
+                    const int AB = J.bra_list[ib], CD = J.ket_list[(int)(item - prefix[ib])];
+                    Quartet4& h = hq[q];
+                    h.active = 1; h.shA = S.pairA[AB]; h.shB = S.pairB[AB]; h.shC = S.pairA[CD]; h.shD = S.pairB[CD]; h.ia0 = pchunk * J.clen; h.w = 1.0;
+                    h.recA = S.pair_rec[AB]; h.recC = S.pair_rec[CD];
+                    h.pA = S.rec[h.recA]; h.zA = S.rec[h.recA + 1]; h.pC = S.rec[h.recC]; h.zC = S.rec[h.recC + 1];
+                }
+                HostPolicy::row0() = w0;
+                if (NBATCH == 4) shell4_quartets<HostPolicy, 4>(J, D, hq, sm.data(), tab.data(), tab_chunk, 0, nullptr, nullptr, nullptr, nullptr, ncart);
+                else if (NBATCH == 2) shell4_quartets<HostPolicy, 2>(J, D, hq, sm.data(), tab.data(), tab_chunk, 0, nullptr, nullptr, nullptr, nullptr, ncart);
+                else shell4_quartets<HostPolicy, 1>(J, D, hq, sm.data(), tab.data(), tab_chunk, 0, nullptr, nullptr, nullptr, nullptr, ncart);
+            }
+            for (int mode = 0; mode < 4; ++mode)
+                for (long long r = 0; r < J.nitems * J.ct.nfill; ++r) shell4_fill_scatter(J, D, r / J.ct.nfill, (int)(r % J.ct.nfill), mode, S.fnorm.data(), out, n);
+        }
     return 0;
 }
 

@@ -37,7 +37,7 @@ def test_h2_known_answers(tb, oracle):
 
 @pytest.mark.parametrize("name", ["n2_ccpvtz", "co_b3lyp_ccpvtz", "et100"])
 def test_eri_cart_vs_oracle(tb, oracle, name):
-    """Dense Cartesian tensor (k_eri_fill) against the oracle and the reference's own recorded values."""
+    """Dense Cartesian tensor (engine fill mode + k_fill_scatter) against the oracle and the reference's own recorded values."""
     g = load_golden(name)
     ctx = context_for(g)
     ctx.eri_fill_cart()
@@ -51,6 +51,27 @@ def test_eri_cart_vs_oracle(tb, oracle, name):
     assert np.array_equal(E, E.transpose(1, 0, 2, 3)) and np.array_equal(E, E.transpose(0, 1, 3, 2)) and np.array_equal(E, E.transpose(2, 3, 0, 1))
     c = ctx.counts()
     assert (c["unique_quartets"], c["surviving_quartets"]) == oracle.parity_surviving_quartets(g["lmn"])
+
+
+@pytest.mark.parametrize("name", ["n2_ccpvtz", "ne2_uhf_ccpvqz", "et100"])
+def test_engine_fill_matches_per_quartet_fill_and_is_reproducible(tb, name, monkeypatch):
+    """The dense tensor from the shell-quartet engine's fill mode (the default for contracted bases, forced here) against the
+    per-AO-quartet kernel (TUNA_B200_FILL_ENGINE=0): same values within the ERI tolerance, the same exact zeros, and two engine fills are
+    bitwise identical (fixed-order scatter pass)."""
+    g = load_golden(name)
+    ctx = context_for(g)
+    monkeypatch.setenv("TUNA_B200_FILL_ENGINE", "1")
+    ctx.eri_fill_cart()
+    E1 = ctx.eri_download(0)
+    ctx.eri_fill_cart()
+    E2 = ctx.eri_download(0)
+    assert np.array_equal(E1, E2)
+    assert np.array_equal(E1, E1.transpose(1, 0, 2, 3)) and np.array_equal(E1, E1.transpose(2, 3, 0, 1))
+    monkeypatch.setenv("TUNA_B200_FILL_ENGINE", "0")
+    ctx.eri_fill_cart()
+    E0 = ctx.eri_download(0)
+    _check_eri(E1, E0)
+    assert np.array_equal(E1 == 0.0, E0 == 0.0)
 
 
 def test_eri_ne2_ccpvqz_vs_compiled_reference(tb, oracle):

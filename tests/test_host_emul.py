@@ -72,6 +72,33 @@ def test_quartet_math_vs_oracle(emul, oracle, name):
     assert np.array_equal(out == 0.0, ref == 0.0)
 
 
+@pytest.mark.parametrize("name,nb,budget,target", [("h2_631g", 2, None, 16), ("n2_ccpvtz", 2, None, 16), ("n2_ccpvtz", 1, 96, 4), ("n2_ccpvtz", 4, 300, 0)])
+def test_engine_fill_mode_vs_oracle(emul, oracle, name, nb, budget, target, monkeypatch):
+    """Dense Cartesian tensor through the engine's fill mode (scratch rows per work item + the fixed-order scatter pass) against
+    the oracle: contracted shells split into primitive chunks, several integral-buffer chunks per class, 1 / 2 / 4 quartets per batch."""
+    monkeypatch.setenv("TUNA_EMUL_NB", str(nb))
+    monkeypatch.setenv("TUNA_EMUL_PSPLIT_TARGET", str(target))
+    if budget:
+        monkeypatch.setenv("TUNA_EMUL_IT_BUDGET", str(budget))
+    g = load_golden(name)
+    fb = oracle_basis(oracle, g)
+    n = fb.ncart
+    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    oz = np.ascontiguousarray(fb.origins[:, 2])
+    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
+    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
+    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
+    out = np.full((n,) * 4, np.nan)
+    rc = emul.emul_fill_shell4(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                               fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert rc == 0
+    ref = oracle.eri_fill(fb)
+    assert np.all(np.abs(out - ref) <= np.maximum(1e-12, 1e-13 * np.abs(ref)))
+    assert np.array_equal(out == 0.0, ref == 0.0)
+    assert np.array_equal(out, out.transpose(1, 0, 2, 3)) and np.array_equal(out, out.transpose(2, 3, 0, 1))      # one value for all eight images
+
+
 ENGINES = {"gen4": "emul_jk_shell4"}
 
 

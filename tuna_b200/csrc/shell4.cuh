@@ -71,6 +71,13 @@ struct Class4Dev {
     const unsigned short* omap;                   // [nwork] K accumulator -> (row | col << 8); 0xffff for J accumulators
     const unsigned* jst_ptr; const unsigned short* jst_list;   // [ngamma + nbeta + 1] CSR of component pairs: Pg (staging order) then Pb
     const unsigned* jflush; int njfl;             // (row | col << 8) | work position << 16
+    // fill mode (dense-tensor build, no densities): entry e of the class = {integral slot in its chunk's buffer, a | b << 8 | c << 16 | d << 24};
+    // chunk_f0[ch] = first entry of chunk ch.  Built only for the fill job set (nfill = 0 otherwise).
+    int nfill;
+    const unsigned* fill; const int* chunk_f0;
+    // scatter pass: fperm[(m - 1) * nfill + e'] = entry handled by position e' in mode m = 1, 2, 3 (entries ordered so that c, b or a is the
+    // fastest index; mode 0 is the list order, d fastest): consecutive lanes then write neighbouring elements of the images of that mode
+    const unsigned* fperm;
 };
 
 // Phase 4 tile (two z combinations zc, zc+1 of one x/y combination):
@@ -97,6 +104,11 @@ struct Shell4Job {
     // shared-memory layout of one group (offsets in doubles, each array interleaved over the NB quartets of a batch)
     int NS, NGZ, oB, oPz, oRt, oXY, oU, oS, oIt, oP, oOut, oRecA, oRecC, oAO, oPref, aostride, total;
     int tab_off, hdr_off;           // CTA-level areas behind the group slices (doubles): digestion tables, quartet headers
+    // fill mode: work item wi writes its nfill (partial, unnormalised) integrals to fill_scratch[fill_base + wi * nfill + e]; the scatter
+    // pass (shell4_fill_scatter) sums the primitive chunks of a shell quartet in a fixed order and writes the eight images
+    double* fill_scratch;
+    long long fill_base;
+    const int* fill_pairs;          // [2 * nitems] (bra pair, ket pair) of every shell quartet of the job: the scatter pass decodes an item with one load
 };
 
 inline void shell4_job_layout(Shell4Job& J, int nD) {
@@ -483,7 +495,16 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             }
         Pol::sync();
         // ---- phase 5: digestion of the chunk, one accumulator per lane; all addressing from the shared-memory tables
-        if (skip & 64) {
+        if (J.fill_scratch) {
+            // fill mode: the chunk's integrals go to the work items' scratch rows in list order (coalesced over the lanes)
+            const int f0 = CT.chunk_f0[ch], nf = CT.chunk_f0[ch + 1] - f0;
+            double* const row = J.fill_scratch + J.fill_base + Pol::work_item_of(J, hq) * (long long)CT.nfill + f0;      // hq[q] is work item work_item_of + q
+            for (int e = lane; e < nf; e += Pol::G) {
+                const QVec<NB> v = qld<NB>(Itq + CT.fill[2 * (f0 + e)] * NB);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) if (act[q]) row[(long long)q * CT.nfill + e] = v.v[q];
+            }
+        } else if (skip & 64) {
         } else if (CT.nterm2 > 0) {
             // term mode: (integral, density) byte-offset pairs of the accumulator, two terms per 16-byte shared load
             const char* const smB = reinterpret_cast<const char*>(sm);
@@ -669,6 +690,37 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
         }
     }
     Pol::sync();
+}
+
+// Fill mode, second pass: position ep of shell quartet `item` of a job in mode m.  Sums the primitive chunks in a fixed order (bitwise
+// reproducible, no atomics), applies the component norms and writes the canonical value to the two images of the dense n^4 tensor whose
+// LAST index is the component the mode's entry order varies fastest (m = 0: d, 1: c, 2: b, 3: a), so that the lanes of a warp write
+// neighbouring elements; the four modes together write all eight images.  Component quartets that another entry of the same block
+// represents (A = B with b > a, C = D with d > c, bra pair = ket pair with (c, d) > (a, b)) are skipped, so every element of the tensor
+// has one value.  (Parity-forbidden elements stay zero from the memset.)
+TUNA_HD void shell4_fill_scatter(const Shell4Job& J, const ShellData& D, long long item, int ep, int mode, const double* __restrict__ fnorm,
+                                 double* __restrict__ out, long long n) {
+    const int nf = J.ct.nfill;
+    const int e = mode == 0 ? ep : (int)J.ct.fperm[(size_t)(mode - 1) * nf + ep];
+    const int pab = J.fill_pairs[2 * item], pcd = J.fill_pairs[2 * item + 1];
+    const int shA = D.pairA[pab], shB = D.pairB[pab], shC = D.pairA[pcd], shD = D.pairB[pcd];
+    const unsigned m = J.ct.fill[2 * e + 1];
+    const int a = m & 255, b = (m >> 8) & 255, c = (m >> 16) & 255, d = m >> 24;
+    if (shA == shB && b > a) return;
+    if (shC == shD && d > c) return;
+    if (pab == pcd && (c > a || (c == a && d > b))) return;
+    const double* s = J.fill_scratch + J.fill_base + item * J.psplit * nf + e;
+    double v = 0.0;
+    for (int pc = 0; pc < J.psplit; ++pc) v += s[(long long)pc * nf];
+    const long long i = D.sh_ao[shA * SH_NCMAX + a], j = D.sh_ao[shB * SH_NCMAX + b], k = D.sh_ao[shC * SH_NCMAX + c], l = D.sh_ao[shD * SH_NCMAX + d];
+    v *= fnorm[i] * fnorm[j] * fnorm[k] * fnorm[l];
+    const long long n2 = n * n, n3 = n2 * n;
+    switch (mode) {
+        case 0: out[i * n3 + j * n2 + k * n + l] = v; out[j * n3 + i * n2 + k * n + l] = v; break;
+        case 1: out[i * n3 + j * n2 + l * n + k] = v; out[j * n3 + i * n2 + l * n + k] = v; break;
+        case 2: out[k * n3 + l * n2 + i * n + j] = v; out[l * n3 + k * n2 + i * n + j] = v; break;
+        default: out[k * n3 + l * n2 + j * n + i] = v; out[l * n3 + k * n2 + j * n + i] = v; break;
+    }
 }
 
 }  // namespace tuna

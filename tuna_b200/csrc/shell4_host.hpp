@@ -26,6 +26,9 @@ struct Class4Host {
     int tab_words = 0;                     // words of the CTA's table area in either mode
     std::vector<unsigned short> pmap, omap, jst_list, wlist;
     std::vector<unsigned> wfl;
+    std::vector<unsigned> fill;            // fill mode: {slot, a | b << 8 | c << 16 | d << 24} per parity-allowed component quartet, chunk by chunk
+    std::vector<int> chunk_f0;
+    std::vector<unsigned> fperm;           // [3][nfill] entry orders of the scatter modes 1..3 (c, b, a fastest)
     long long allowed = 0;                 // parity-allowed component quartets = integrals per shell quartet
     long long nterms = 0;                  // digestion terms (table statistics)
     bool terms_possible(int term_max) const { return nterms + nwork <= term_max && itmax < 65535 && nstage < 65535; }
@@ -37,7 +40,7 @@ constexpr int S4_S_BUDGET = 4096;      // doubles for the S slice of a chunk
 constexpr int S4_TERM_MAX = 4096;      // digestion terms up to which a single-chunk class keeps its term lists in shared memory (term mode)
 
 inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int Ld, Class4Host& C, int it_budget = S4_IT_BUDGET,
-                                int s_budget = S4_S_BUDGET, int term_max = S4_TERM_MAX) {
+                                int s_budget = S4_S_BUDGET, int term_max = S4_TERM_MAX, bool with_fill = false) {
     C = Class4Host();
     C.La = La; C.Lb = Lb; C.Lc = Lc; C.Ld = Ld;
     const int Lsh[4] = {La, Lb, Lc, Ld};
@@ -321,6 +324,33 @@ inline void build_class4_tables(const ShellTab& T, int La, int Lb, int Lc, int L
             }
         for (int b = 0; b < nbeta; ++b) tab[C.jbrow_off + b] = Rb[b] >= 0 ? (unsigned)Rb[b] : S4_ABSENT;
         for (int g = 0; g < ngamma; ++g) tab[C.jgcol_off + g] = (unsigned)Cg[g];
+        // fill list of the chunk: every allowed component quartet whose bra pair function lives in this chunk (d fastest)
+        if (with_fill) {
+            C.chunk_f0.push_back((int)C.fill.size() / 2);
+            for (int a = 0; a < nc[0]; ++a) for (int b = 0; b < nc[1]; ++b) {
+                const int be = bidx[a * nc[1] + b];
+                if (Rb[be] < 0) continue;
+                for (int c = 0; c < nc[2]; ++c) for (int d = 0; d < nc[3]; ++d) {
+                    if ((T.pg[La][a] ^ T.pg[Lb][b] ^ T.pg[Lc][c] ^ T.pg[Ld][d]) != 0) continue;
+                    C.fill.push_back((unsigned)(Rb[be] + Cg[gidx[c * nc[3] + d]]));
+                    C.fill.push_back((unsigned)a | (unsigned)b << 8 | (unsigned)c << 16 | (unsigned)d << 24);
+                }
+            }
+        }
+    }
+    if (with_fill) {
+        C.chunk_f0.push_back((int)C.fill.size() / 2);
+        const int nf = (int)C.fill.size() / 2;
+        std::vector<unsigned> idx(nf);
+        for (int mode = 1; mode <= 3; ++mode) {
+            for (int e = 0; e < nf; ++e) idx[e] = (unsigned)e;
+            auto key = [&](unsigned e) {
+                const unsigned m = C.fill[2 * e + 1], a = m & 255, b = (m >> 8) & 255, c = (m >> 16) & 255, d = m >> 24;
+                return mode == 1 ? std::make_tuple(a, b, d, c) : mode == 2 ? std::make_tuple(c, d, a, b) : std::make_tuple(c, d, b, a);
+            };
+            std::stable_sort(idx.begin(), idx.end(), [&](unsigned x, unsigned y) { return key(x) < key(y); });
+            C.fperm.insert(C.fperm.end(), idx.begin(), idx.end());
+        }
     }
 
     // ---- staging of the pair-function densities: Pg in (parity class, column) order, then Pb in the chunks' row order ----------------
@@ -470,6 +500,7 @@ inline Class4Dev class4_view(const Class4Host& C, PtrOf ptr) {
     V.wfl = ptr(C.wfl); V.wlist = ptr(C.wlist); V.nwlist = (int)C.wlist.size(); V.nout_sm = C.nterm2 > 0 ? 0 : C.nwork;
     V.acc = ptr(C.acc); V.pmap = ptr(C.pmap); V.omap = ptr(C.omap);
     V.jst_ptr = ptr(C.jst_ptr); V.jst_list = ptr(C.jst_list); V.jflush = ptr(C.jflush); V.njfl = (int)C.jflush.size();
+    V.nfill = (int)C.fill.size() / 2; V.fill = ptr(C.fill); V.chunk_f0 = ptr(C.chunk_f0); V.fperm = ptr(C.fperm);
     return V;
 }
 

@@ -1,7 +1,9 @@
 // tuna_b200.cu — sm_100a kernels + C ABI (include/tuna_b200.h) of the TUNA SCF two-electron provider.
 //
 // Kernels (DESIGN.md has the roofline of each):
-//   k_eri_fill        FP64 ERI over class-sorted AO-pair quartets, 8-fold symmetric scatter into the dense tensor
+//   k_fill_scatter    dense tensor, second pass: the engine's fill mode (k_shell4_*) leaves the unique integrals of every work item in
+//                     scratch rows; this sums the primitive chunks in a fixed order and writes the eight images
+//   k_eri_fill        the dense tensor with one thread per AO quartet (uncontracted bases, bases that do not group into shells)
 //   k_schwarz         Q_ij = sqrt((ij|ij))
 //   k_rotate_axis     one index of the Cartesian->spherical rotation (sparse U), used 4x for the tensor, 2x for matrices
 //   k_jk_stored_sym / _tma / k_jk_stored   fused single-pass J+K over the resident dense tensor (HBM-bound), atomic-free
@@ -113,7 +115,10 @@ struct tuna_ctx {
     // direct SCF alternates between thresholds rarely - none of that may rebuild lists or reallocate inside a Fock build
     struct Group4 { int G = 1, threads = 128, njobs = 0, job_off = 0, ctas_per_sm = 1; long long nunits = 0; size_t smem = 0;
                     Shell4Job* d_jobs = nullptr; long long* d_unit_prefix = nullptr; };      // light jobs of one group size in one persistent launch
-    struct JobSet4 { double tau = -1.0, dens_bound = 0.0; int nD = 0, shard_n = 0; std::vector<Job4Host> jobs; std::vector<Group4> groups; long long* d_prefix = nullptr; };
+    struct JobSet4 { double tau = -1.0, dens_bound = 0.0; int nD = 0, shard_n = 0; std::vector<Job4Host> jobs; std::vector<Group4> groups; long long* d_prefix = nullptr;
+                     // fill job set (nD == 0): scratch rows of all work items, every job's descriptor and the prefix of (shell quartet, fill entry) counts for the scatter pass
+                     double* d_scratch = nullptr; Shell4Job* d_all_jobs = nullptr; long long* d_scatter_pre = nullptr; long long scatter_total = 0;
+                     int* d_fill_pairs = nullptr; };
     std::vector<JobSet4> jobsets4;
     int cur_jobset4 = -1;
     // The job lists are pre-screened on the host with tau / dens_bound, dens_bound = an upper bound of max |P| in the engine's working
@@ -145,6 +150,9 @@ struct tuna_ctx {
     catch (...) { if (ctx) ctx->err = "internal error"; return TUNA_ERR_STATE; }
 
 static int check_pair_symmetry(tuna_ctx* ctx);
+static int ensure_shell4(tuna_ctx* ctx, double tau, int nD);
+static int launch_shell4_jobs(tuna_ctx* ctx, int nD, const double* Pc, const double* Psym, double* Jc, double* Kc, double tau, long long fix_lo);
+
 
 // Opt-in to more than 48 KB of dynamic shared memory.  The attribute is PER DEVICE (a process may hold contexts on several GPUs), so the
 // "already done" flag is a bit per device ordinal, one flag word per kernel instantiation.
@@ -174,6 +182,11 @@ static int dev_alloc(tuna_ctx* ctx, T** p, size_t count) {
 }
 template <typename T>
 static void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+static void free_jobset4(tuna_ctx::JobSet4& js) {
+    dev_free(&js.d_prefix); dev_free(&js.d_scratch); dev_free(&js.d_all_jobs); dev_free(&js.d_scatter_pre); dev_free(&js.d_fill_pairs);
+    for (auto& g : js.groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
+    js.groups.clear();
+}
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -804,6 +817,12 @@ struct DevPolicy {
     __device__ __forceinline__ static void sync_cta() { __syncthreads(); }
     __device__ __forceinline__ static int cta_thread() { return threadIdx.x; }
     __device__ __forceinline__ static int cta_threads() { return blockDim.x; }
+    // fill mode: index of the work item header hq points to (the unit's first work item is kept behind the headers, see shell4_unit)
+    __device__ __forceinline__ static long long work_item_of(const Shell4Job& J, const Quartet4* hq) {
+        extern __shared__ double smem_all[];
+        const Quartet4* hdr0 = reinterpret_cast<const Quartet4*>(smem_all + J.hdr_off);
+        return *reinterpret_cast<const long long*>(reinterpret_cast<const char*>(hdr0 + J.chunk) + 8) + (hq - hdr0);
+    }
     // M[idx] += v as the order-independent two-word integer accumulation of fixed_split (no floating-point atomics in the engine)
     __device__ __forceinline__ static void accumulate(double* M, int idx, double v, long long fix_lo) {
         long long h, l;
@@ -846,6 +865,7 @@ __device__ __forceinline__ void shell4_unit(const Shell4Job& J, const ShellData&
             if (J.item_prefix[mid] <= first_item) lo = mid; else hi = mid;
         }
         s_ib0 = lo;
+        *reinterpret_cast<long long*>(reinterpret_cast<char*>(hdr + CH) + 8) = first;      // read by DevPolicy::work_item_of (fill mode)
     }
     __syncthreads();
     for (int k = threadIdx.x; k < CH; k += blockDim.x) {
@@ -861,7 +881,7 @@ __device__ __forceinline__ void shell4_unit(const Shell4Job& J, const ShellData&
             h.active = !(tau > 0.0 && D.pairQ[pab] * D.pairQ[pcd] * dmax < tau);
             h.shA = D.pairA[pab]; h.shB = D.pairB[pab]; h.shC = D.pairA[pcd]; h.shD = D.pairB[pcd];
             const bool ab = h.shA == h.shB, cd = h.shC == h.shD, dg = pab == pcd;
-            h.w = (ab ? 0.5 : 1.0) * (cd ? 0.5 : 1.0) * (dg ? 0.5 : 1.0);
+            h.w = J.fill_scratch ? 1.0 : (ab ? 0.5 : 1.0) * (cd ? 0.5 : 1.0) * (dg ? 0.5 : 1.0);      // fill mode stores plain integrals
             h.recA = D.pair_rec[pab]; h.recC = D.pair_rec[pcd];
             if (h.active) {
                 h.pA = D.rec[h.recA]; h.zA = D.rec[h.recA + 1]; h.pC = D.rec[h.recC]; h.zC = D.rec[h.recC + 1];
@@ -925,6 +945,31 @@ k_shell4_multi(const Shell4Job* __restrict__ jobs, const long long* __restrict__
         shell4_unit<GG, NB>(J, D, u - unit_prefix[lo], nD, Pf, Psym, Jf, Kf, ncart, tau, dmax, smem_all, tab_chunk, done);
     }
     if (done != 0.0) atomicAdd(reinterpret_cast<unsigned long long*>(evaluated), (unsigned long long)(done + 0.5));      // integer counter: no FP64 atomics in the engine
+}
+
+// Dense fill, second pass (shell4_fill_scatter).  A block takes a group of whole shell quartets of one class job (256 / nfill of them, at
+// least one) and runs the four scatter modes over the group back to back, so the scratch rows come from DRAM once (the permuted re-reads
+// of modes 1-3 hit L2) and the lanes of every mode write runs of consecutive tensor elements.  group_pre = prefix of groups per job.
+__global__ void __launch_bounds__(256) k_fill_scatter(const Shell4Job* __restrict__ jobs, const long long* __restrict__ group_pre, int njobs, ShellData D,
+                                                      const double* __restrict__ fnorm, double* __restrict__ out, int n) {
+    const long long ngroups = group_pre[njobs];
+    for (long long t = blockIdx.x; t < ngroups; t += gridDim.x) {
+        int lo = 0, hi = njobs;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (group_pre[mid] <= t) lo = mid; else hi = mid;
+        }
+        const Shell4Job& J = jobs[lo];
+        const int nf = J.ct.nfill, ipg = nf >= 256 ? 1 : 256 / nf;
+        const long long item0 = (t - group_pre[lo]) * ipg;
+        const int cnt = (int)min((long long)ipg, J.nitems - item0) * nf;
+#pragma unroll 1
+        for (int mode = 0; mode < 4; ++mode)
+            for (int x = threadIdx.x; x < cnt; x += 256) {
+                const int k = x / nf;
+                shell4_fill_scatter(J, D, item0 + k, x - k * nf, mode, fnorm, out, n);
+            }
+    }
 }
 
 // reproducible accumulation: (hi, lo) integer words -> FP64 (fixed_value), J and K in one launch
@@ -1174,7 +1219,8 @@ int tuna_ctx_destroy(tuna_ctx* ctx) {
     dev_free(&ctx->d_fix);
     dev_free(&ctx->d_pairA); dev_free(&ctx->d_pairB); dev_free(&ctx->d_pair_rec); dev_free(&ctx->d_rec);
     dev_free(&ctx->d_pairQ); dev_free(&ctx->d_sh_ao); dev_free(&ctx->d_class_lists); dev_free(&ctx->d_finv);
-    for (auto& js : ctx->jobsets4) dev_free(&js.d_prefix); dev_free(&ctx->d_fnorm);
+    for (auto& js : ctx->jobsets4) free_jobset4(js);
+    dev_free(&ctx->d_fnorm);
     dev_free(&ctx->d_eval);
     dev_free(&ctx->Uf.rowptr); dev_free(&ctx->Uf.col); dev_free(&ctx->Uf.val);
     dev_free(&ctx->Uft.rowptr); dev_free(&ctx->Uft.col); dev_free(&ctx->Uft.val);
@@ -1239,7 +1285,7 @@ int tuna_set_basis(tuna_ctx* ctx, int ncart, const double* origins_z, const int3
     ctx->nbf = 0;
     build_shell_tab(ctx->stab);
     ctx->shell_ready = false;
-    for (auto& js : ctx->jobsets4) { dev_free(&js.d_prefix); for (auto& g : js.groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); } }
+    for (auto& js : ctx->jobsets4) free_jobset4(js);
     ctx->jobsets4.clear();
     ctx->cur_jobset4 = -1;
     detect_shells(ctx->hb, ctx->stab, ctx->ss);     // ss.ok == false -> direct mode uses the per-component kernel
@@ -1285,13 +1331,49 @@ int tuna_eri_fill_cart(tuna_ctx* ctx) try {
     const size_t n = ctx->ncart, count = n * n * n * n;
     int rc;
     if ((rc = ensure_pairs(ctx))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_eri_cart, count))) return rc;
+    // A basis that groups into shells AND has contracted shells is filled by the shell-quartet engine (shell4.cuh, fill mode: Boys values, R,
+    // the x/y table and the z contractions are shared by all components of a shell quartet, contracted quartets are split over work items)
+    // followed by the scatter pass; an uncontracted basis keeps the per-AO-quartet kernel, which is as fast there (ET100: 1.40 vs 1.52 ms;
+    // N2/cc-pVTZ: 3.7 vs 1.3 ms, Ne2/cc-pVQZ: 13.6 vs 5.9 ms).  TUNA_B200_FILL_ENGINE=1 / 0 forces one or the other.  Both leave the same
+    // tensor: one value written to all eight images, exact zeros for the parity-forbidden elements.
+    bool contracted = false;
+    for (const auto& sh : ctx->ss.shells) contracted = contracted || sh.nprim > 1;
+    const char* ef = getenv("TUNA_B200_FILL_ENGINE");
+    const bool engine = ctx->direct_engine == 1 && ctx->ss.ok && (ef ? atoi(ef) != 0 : contracted);
+    const int save_rank = ctx->shard_rank, save_n = ctx->shard_n;
+    if (engine) {
+        ctx->shard_rank = 0; ctx->shard_n = 1;        // the dense tensor is never sharded: every rank holds all of it
+        rc = ensure_shell4(ctx, 0.0, 0);
+        if (rc) { ctx->shard_rank = save_rank; ctx->shard_n = save_n; return rc; }
+    }
+    if ((rc = dev_alloc(ctx, &ctx->d_eri_cart, count))) { ctx->shard_rank = save_rank; ctx->shard_n = save_n; return rc; }
     CK(cudaMemsetAsync(ctx->d_eri_cart, 0, count * sizeof(double), ctx->stream));
     CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
-    k_eri_fill<<<grid_for(ctx, ctx->task_begin[4], 128, 16), 128, 0, ctx->stream>>>(table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_eri_cart, ctx->ncart);
-    ctx->launches++;
+    if (engine) {
+        const tuna_ctx::JobSet4& JS = ctx->jobsets4[ctx->cur_jobset4];
+        rc = launch_shell4_jobs(ctx, 0, nullptr, nullptr, nullptr, nullptr, 0.0, 0);
+        ctx->shard_rank = save_rank; ctx->shard_n = save_n;
+        if (rc) return rc;
+        if (JS.scatter_total > 0) {
+            ShellData D;
+            D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
+            D.sh_ao = ctx->d_sh_ao; D.boys = ctx->d_boys; D.herm = ctx->d_herm; D.fix_lo = 0;
+            k_fill_scatter<<<(unsigned)std::min<long long>(JS.scatter_total, (long long)ctx->sm_count * 64), 256, 0, ctx->stream>>>(JS.d_all_jobs, JS.d_scatter_pre, (int)JS.jobs.size(), D, ctx->d_fnorm,
+                                                                                            ctx->d_eri_cart, ctx->ncart);
+            ctx->launches++;
+        }
+    } else {
+        k_eri_fill<<<grid_for(ctx, ctx->task_begin[4], 128, 16), 128, 0, ctx->stream>>>(table_dev(ctx), ctx->d_boys, ctx->d_herm, ctx->d_eri_cart, ctx->ncart);
+        ctx->launches++;
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[0][1], ctx->stream));
+    if (engine) {       // the scratch rows (the unique integrals once per primitive chunk) are only needed until the scatter pass has run
+        CK(cudaStreamSynchronize(ctx->stream));
+        free_jobset4(ctx->jobsets4[ctx->cur_jobset4]);
+        ctx->jobsets4.erase(ctx->jobsets4.begin() + ctx->cur_jobset4);
+        ctx->cur_jobset4 = -1;
+    }
     return TUNA_OK;
 } TUNA_CATCH
 
@@ -1988,8 +2070,9 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
         const char* es = getenv("TUNA_B200_S_BUDGET");
         const char* etm = getenv("TUNA_B200_TERM_MAX");
         int itb = eb ? atoi(eb) : S4_IT_BUDGET, sb = es ? atoi(es) : S4_S_BUDGET;
-        const int tmax = etm ? atoi(etm) : S4_TERM_MAX;
-        build_class4_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb, tmax);
+        const bool fill = nD == 0;                 // the fill job set: explicit (slot, components) lists, separable tables, no densities
+        const int tmax = fill ? 0 : etm ? atoi(etm) : S4_TERM_MAX;
+        build_class4_tables(ctx->stab, La, Lb, Lc, Ld, E.host, itb, sb, tmax, fill);
         // a slice that does not fit one CTA is re-cut into more chunks; a slice between half and all of an SM's shared memory is
         // re-cut so that two CTAs fit (phases 0-2 then run once per chunk)
         const int tier2 = (225 * 1024 / 2 - 1024 - 64) / 8;
@@ -2003,13 +2086,13 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
             Class4Host trial;
             bool found = false;
             for (int want = nch + 1; want <= nch + 3 && !found; ++want) {
-                build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.nint / want + E.host.nint / (8 * want)), 65000, tmax);
+                build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.nint / want + E.host.nint / (8 * want)), 65000, tmax, fill);
                 if ((int)trial.chunk_row0.size() - 1 > nch && (shell4_slice_doubles(trial, nD) <= (too_big ? SHELL4_SMEM_DOUBLES : tier2))) found = true;
             }
             if (found) { E.host = trial; if (!too_big) break; }
             else if (!too_big) break;
             else if (pass == 5) FAIL(TUNA_ERR_STATE, "shell engine: class does not fit shared memory");
-            else { build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.itmax / 2), std::max(64, E.host.ssize / 2), tmax); E.host = trial; }
+            else { build_class4_tables(ctx->stab, La, Lb, Lc, Ld, trial, std::max(64, E.host.itmax / 2), std::max(64, E.host.ssize / 2), tmax, fill); E.host = trial; }
         }
     }
     const Class4Host& C = E.host;
@@ -2027,6 +2110,7 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     const size_t o_tabs = add(C.tabs.data(), C.tabs.size() * 4);
     const size_t o_tm = add(C.terms.data(), C.terms.size() * 4), o_tp = add(C.tptr.data(), C.tptr.size() * 4);
     const size_t o_wf = add(C.wfl.data(), C.wfl.size() * 4), o_wl = add(C.wlist.data(), C.wlist.size() * 2);
+    const size_t o_fl = add(C.fill.data(), C.fill.size() * 4), o_f0 = add(C.chunk_f0.data(), C.chunk_f0.size() * 4), o_fp = add(C.fperm.data(), C.fperm.size() * 4);
     std::vector<unsigned char> host(total, 0);
     for (const Piece& p : pieces) if (p.bytes) std::memcpy(host.data() + p.off, p.src, p.bytes);
     int rc;
@@ -2042,6 +2126,7 @@ static int get_class4_tables(tuna_ctx* ctx, int La, int Lb, int Lc, int Ld, int 
     V.jst_ptr = (const unsigned*)(E.blob + o_jp); V.jst_list = (const unsigned short*)(E.blob + o_jl); V.jflush = (const unsigned*)(E.blob + o_jf);
     V.terms = (const unsigned*)(E.blob + o_tm); V.tptr = (const unsigned*)(E.blob + o_tp);
     V.wfl = (const unsigned*)(E.blob + o_wf); V.wlist = (const unsigned short*)(E.blob + o_wl);
+    V.fill = (const unsigned*)(E.blob + o_fl); V.chunk_f0 = (const int*)(E.blob + o_f0); V.fperm = (const unsigned*)(E.blob + o_fp);
     *out = &E;
     return TUNA_OK;
 }
@@ -2057,8 +2142,7 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
         }
     if (ctx->jobsets4.size() >= 6) {
         CK(cudaStreamSynchronize(ctx->stream));
-        dev_free(&ctx->jobsets4.front().d_prefix);
-        for (auto& g : ctx->jobsets4.front().groups) { dev_free(&g.d_jobs); dev_free(&g.d_unit_prefix); }
+        free_jobset4(ctx->jobsets4.front());
         ctx->jobsets4.erase(ctx->jobsets4.begin());
     }
     ctx->jobsets4.emplace_back();
@@ -2070,6 +2154,9 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
     const int ncls = (int)S.classes.size();
     std::vector<long long> all_prefix;
     std::vector<size_t> prefix_off;
+    const bool fill = nD == 0;                  // dense-tensor fill: no densities, every work item writes a scratch row
+    long long fill_run = 0;
+    std::vector<std::pair<int, int>> job_cls;   // (bra class, ket class) of every job, in push order
     const char* env_div = getenv("TUNA_B200_G_DIV");
     const char* env_spl = getenv("TUNA_B200_SMEM_PER_LANE");
     const char* env_nb = getenv("TUNA_B200_NB");
@@ -2092,6 +2179,7 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
                 J.psplit = (J.nppAB + J.clen - 1) / J.clen;
             }
             { const char* dbg = getenv("TUNA_B200_DBG_SKIP"); J.dbg_skip = dbg ? atoi(dbg) : 0; }
+            J.fill_scratch = nullptr; J.fill_base = 0; J.fill_pairs = nullptr;
             std::vector<long long> prefix;
             J.nitems = build_item_prefix(S, cb, ck, tau / ctx->dens_bound, prefix);
             if (J.nitems == 0) continue;
@@ -2104,6 +2192,7 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             if ((rc = get_class4_tables(ctx, J.La, J.Lb, J.Lc, J.Ld, nD, &ctd))) return rc;
             J.ct = ctd->view;
             shell4_job_layout(J, nD);
+            if (fill) { J.fill_base = fill_run; fill_run += J.nitems * J.psplit * J.ct.nfill; }
             jh.allowed = (double)ctd->host.allowed;
             for (int u = 0; u < 6; ++u) J.uniq[u] = ctd->host.uniq[u];
             int nb = env_nb ? atoi(env_nb) : 2;
@@ -2131,11 +2220,29 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             jh.smem = ((size_t)J.hdr_off + (size_t)J.chunk * sizeof(Quartet4) / 8 + 2) * sizeof(double);
             if (jh.smem > 226 * 1024) FAIL(TUNA_ERR_STATE, "shell engine: shared-memory layout exceeds 226 KB");
             jobs4.push_back(jh);
+            job_cls.push_back({cb, ck});
         }
     if ((rc = dev_alloc(ctx, &JS.d_prefix, std::max<size_t>(all_prefix.size(), 1)))) return rc;
     CK(cudaMemcpyAsync(JS.d_prefix, all_prefix.data(), all_prefix.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (size_t j = 0; j < jobs4.size(); ++j) jobs4[j].job.item_prefix = JS.d_prefix + prefix_off[j];
+    if (fill) {
+        if ((rc = dev_alloc(ctx, &JS.d_scratch, (size_t)std::max<long long>(fill_run, 1)))) return rc;
+        // (bra pair, ket pair) of every item, job after job in the order of all_prefix
+        std::vector<int> fpairs;
+        std::vector<size_t> fp_off;
+        for (size_t j = 0; j < jobs4.size(); ++j) {
+            const int cb = job_cls[j].first, ck = job_cls[j].second;
+            const long long* pf = all_prefix.data() + prefix_off[j];
+            fp_off.push_back(fpairs.size());
+            for (size_t ib = 0; ib < S.classes[cb].pairs.size(); ++ib)
+                for (long long k = 0; k < pf[ib + 1] - pf[ib]; ++k) { fpairs.push_back(S.classes[cb].pairs[ib]); fpairs.push_back(S.classes[ck].pairs[(size_t)k]); }
+        }
+        if ((rc = dev_alloc(ctx, &JS.d_fill_pairs, std::max<size_t>(fpairs.size(), 1)))) return rc;
+        CK(cudaMemcpyAsync(JS.d_fill_pairs, fpairs.data(), fpairs.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t j = 0; j < jobs4.size(); ++j) { jobs4[j].job.fill_scratch = JS.d_scratch; jobs4[j].job.fill_pairs = JS.d_fill_pairs + fp_off[j]; }
+    }
     std::stable_sort(jobs4.begin(), jobs4.end(), [](const tuna_ctx::Job4Host& x, const tuna_ctx::Job4Host& y) {
         return x.allowed * (double)x.job.nitems > y.allowed * (double)y.job.nitems;
     });
@@ -2176,6 +2283,20 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             CK(cudaStreamSynchronize(ctx->stream));
             JS.groups.push_back(g);
         }
+    }
+    if (fill) {       // descriptors of ALL jobs and the prefix of their (shell quartet, fill entry) counts for the scatter pass
+        std::vector<Shell4Job> js;
+        std::vector<long long> pre(1, 0);
+        for (const auto& jh : jobs4) {      // groups of whole shell quartets (k_fill_scatter)
+            const long long nf = std::max(1, jh.job.ct.nfill), ipg = nf >= 256 ? 1 : 256 / nf;
+            js.push_back(jh.job); pre.push_back(pre.back() + (jh.job.nitems + ipg - 1) / ipg);
+        }
+        JS.scatter_total = pre.back();
+        if ((rc = dev_alloc(ctx, &JS.d_all_jobs, std::max<size_t>(js.size(), 1)))) return rc;
+        if ((rc = dev_alloc(ctx, &JS.d_scatter_pre, pre.size()))) return rc;
+        CK(cudaMemcpyAsync(JS.d_all_jobs, js.data(), js.size() * sizeof(Shell4Job), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(JS.d_scatter_pre, pre.data(), pre.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
     }
     if (const char* dump = getenv("TUNA_B200_DUMP_JOBS")) {       // development aid: the job table in launch order
         if (FILE* f = fopen(dump, "w")) {
