@@ -11,6 +11,9 @@
 #include <cstdint>
 #include <numeric>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "eri_core.cuh"
 
@@ -37,6 +40,15 @@ struct PairTable {
 
 // Hermite expansion coefficients E_t^{i j}, 0 <= t <= i + j, for one Cartesian direction.
 // E is filled for all i <= l1, j <= l2 at stride (l1+l2+2); returns pointer semantics via index helper.
+#ifdef _OPENMP
+inline int host_threads() { return omp_get_max_threads(); }
+inline int host_thread_id() { return omp_get_thread_num(); }
+#else
+inline int host_threads() { return 1; }
+inline int host_thread_id() { return 0; }
+#endif
+constexpr size_t HERMITE_SCRATCH_DOUBLES = 4096;      // >= (l1 + 1)(l2 + 1)(l1 + l2 + 2) for every table the host builds (l1 + l2 <= 10)
+
 inline void hermite_table(int l1, int l2, double R, double a, double b, std::vector<double>& E) {
     const int nt = l1 + l2 + 2;
     E.assign((size_t)(l1 + 1) * (l2 + 1) * nt, 0.0);
@@ -125,9 +137,13 @@ inline void build_pair_table(const HostBasis& B, PairTable& T) {
     }
     for (int g = 1; g < 5; ++g) T.group_begin[g] = std::max(T.group_begin[g], T.group_begin[g - 1]);
     T.pp.assign((size_t)total * PP_DOUBLES, 0.0);
+    // per-thread scratch is allocated OUTSIDE the parallel region (an allocation failure inside it could not be reported, only terminate);
+    // hermite_table stays within the reserved capacity
+    std::vector<std::vector<double>> scratch_of((size_t)host_threads());
+    for (auto& v : scratch_of) v.reserve(HERMITE_SCRATCH_DOUBLES);
 #pragma omp parallel
     {
-        std::vector<double> scratch;
+        std::vector<double>& scratch = scratch_of[(size_t)host_thread_id()];
 #pragma omp for schedule(dynamic, 256)
         for (int64_t a = 0; a < npair; ++a) {
             const int i = T.pi[a], j = T.pj[a];

@@ -131,9 +131,11 @@ inline void build_shell_pairs(ShellSystem& S, const ShellTab& T, const PairTable
         std::stable_sort(c.pairs.begin(), c.pairs.end(), [&](int x, int y) { return S.pairQ[x] > S.pairQ[y]; });
     S.rec.assign((size_t)rec_total, 0.0);
     const int np = (int)S.pairA.size();
+    std::vector<std::vector<double>> scratch_of((size_t)host_threads());      // allocated outside the parallel region (see build_pair_table)
+    for (auto& v : scratch_of) v.reserve(HERMITE_SCRATCH_DOUBLES);
 #pragma omp parallel
     {
-        std::vector<double> scratch;
+        std::vector<double>& scratch = scratch_of[(size_t)host_thread_id()];
 #pragma omp for schedule(dynamic, 64)
         for (int id = 0; id < np; ++id) {
             const HostShell& sa = S.shells[S.pairA[id]];
