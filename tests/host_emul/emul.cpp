@@ -134,13 +134,10 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
             Shell4Job J;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
             J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4; J.dbg_skip = 0; J.fill_scratch = nullptr; J.fill_base = 0; J.fill_pairs = nullptr;
-            {   // TUNA_EMUL_PSPLIT_TARGET: split contracted shell quartets into work items of bra primitive pairs, as the device launcher does
+            {   // TUNA_EMUL_PSPLIT_TARGET: split contracted shell quartets into work items of primitive pairs, as the device launcher does
                 const char* ept = getenv("TUNA_EMUL_PSPLIT_TARGET");
-                const int target = ept ? atoi(ept) : 16;
-                const long long tot = (long long)J.nppAB * J.nppCD;
-                J.psplit = (target > 0 && tot > target) ? (int)std::min<long long>(J.nppAB, (tot + target - 1) / target) : 1;
-                J.clen = (J.nppAB + J.psplit - 1) / J.psplit;
-                J.psplit = (J.nppAB + J.clen - 1) / J.clen;
+                const char* eks = getenv("TUNA_EMUL_KSPLIT");
+                shell4_split(J, ept ? atoi(ept) : 16, !(eks && atoi(eks) == 0));
             }
             J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
             std::vector<long long> prefix;
@@ -181,7 +178,7 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
                 if (AB == CD) w *= 0.5;
                 for (int pchunk = 0; pchunk < J.psplit; ++pchunk) {
                     Quartet4 h;
-                    h.active = 1; h.shA = S.pairA[AB]; h.shB = S.pairB[AB]; h.shC = S.pairA[CD]; h.shD = S.pairB[CD]; h.ia0 = pchunk * J.clen; h.w = w;
+                    h.active = 1; h.shA = S.pairA[AB]; h.shB = S.pairB[AB]; h.shC = S.pairA[CD]; h.shD = S.pairB[CD]; h.ia0 = (pchunk / J.ksplit) * J.clen | ((pchunk % J.ksplit) * J.klen) << 16; h.w = w;
                     h.recA = S.pair_rec[AB]; h.recC = S.pair_rec[CD];
                     h.pA = S.rec[h.recA]; h.zA = S.rec[h.recA + 1]; h.pC = S.rec[h.recC]; h.zC = S.rec[h.recC + 1];
                     hq[nb] = h;
@@ -230,13 +227,10 @@ extern "C" int emul_fill_shell4(int ncart, const double* oz, const int* lmn, con
             Shell4Job J;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
             J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp; J.chunk = 4; J.dbg_skip = 0;
-            {
+            {   // TUNA_EMUL_PSPLIT_TARGET: split contracted shell quartets into work items of primitive pairs, as the device launcher does
                 const char* ept = getenv("TUNA_EMUL_PSPLIT_TARGET");
-                const int target = ept ? atoi(ept) : 16;
-                const long long tot = (long long)J.nppAB * J.nppCD;
-                J.psplit = (target > 0 && tot > target) ? (int)std::min<long long>(J.nppAB, (tot + target - 1) / target) : 1;
-                J.clen = (J.nppAB + J.psplit - 1) / J.psplit;
-                J.psplit = (J.nppAB + J.clen - 1) / J.clen;
+                const char* eks = getenv("TUNA_EMUL_KSPLIT");
+                shell4_split(J, ept ? atoi(ept) : 16, !(eks && atoi(eks) == 0));
             }
             J.bra_list = S.classes[cb].pairs.data(); J.ket_list = S.classes[ck].pairs.data();
             std::vector<long long> prefix;
@@ -270,7 +264,7 @@ extern "C" int emul_fill_shell4(int ncart, const double* oz, const int* lmn, con
                     while (hi - ib > 1) { const int mid = (ib + hi) >> 1; if (prefix[mid] <= item) ib = mid; else hi = mid; }
                     const int AB = J.bra_list[ib], CD = J.ket_list[(int)(item - prefix[ib])];
                     Quartet4& h = hq[q];
-                    h.active = 1; h.shA = S.pairA[AB]; h.shB = S.pairB[AB]; h.shC = S.pairA[CD]; h.shD = S.pairB[CD]; h.ia0 = pchunk * J.clen; h.w = 1.0;
+                    h.active = 1; h.shA = S.pairA[AB]; h.shB = S.pairB[AB]; h.shC = S.pairA[CD]; h.shD = S.pairB[CD]; h.ia0 = (pchunk / J.ksplit) * J.clen | ((pchunk % J.ksplit) * J.klen) << 16; h.w = 1.0;
                     h.recA = S.pair_rec[AB]; h.recC = S.pair_rec[CD];
                     h.pA = S.rec[h.recA]; h.zA = S.rec[h.recA + 1]; h.pC = S.rec[h.recC]; h.zC = S.rec[h.recC + 1];
                 }

@@ -136,11 +136,13 @@ def test_shell_engine_vs_oracle(emul, oracle, name, gen):
             assert np.abs(J[d] - Jr).max() < 1e-11 and np.abs(K[d] - Kr).max() < 1e-11
 
 
-@pytest.mark.parametrize("target", ["0", "5", "16"])
-def test_shell_engine_primitive_split(emul, oracle, target, monkeypatch):
-    """Contracted classes: a shell quartet split into work items of bra primitive pairs (each digesting and flushing its partial integrals)
-    gives the same J/K as the unsplit walk (target 0) - N2/cc-pVTZ has shells of up to 8 primitives, i.e. 4096 primitive quartets in (ss|ss)."""
+@pytest.mark.parametrize("target,ket", [("0", "1"), ("5", "1"), ("16", "1"), ("16", "0"), ("7", "1")])
+def test_shell_engine_primitive_split(emul, oracle, target, ket, monkeypatch):
+    """Contracted classes: a shell quartet split into work items of bra primitive pairs - and, once every bra pair is its own item, of ket
+    primitive pairs (ket = 1) - each digesting and flushing its partial integrals, gives the same J/K as the unsplit walk (target 0).
+    N2/cc-pVTZ has shells of up to 8 primitives, i.e. 4096 primitive quartets in (ss|ss); target 7 leaves ragged last chunks on both sides."""
     monkeypatch.setenv("TUNA_EMUL_PSPLIT_TARGET", target)
+    monkeypatch.setenv("TUNA_EMUL_KSPLIT", ket)
     g = load_golden("n2_ccpvtz")
     fb = oracle_basis(oracle, g)
     n = fb.ncart

@@ -91,8 +91,10 @@ struct Shell4Job {
     // Contracted classes: the nppAB * nppCD primitive quartets of a shell quartet are walked serially (phases 0-4 each), which leaves a
     // handful of lanes busy for thousands of iterations in classes like (ss|ss) of cc-pVQZ.  J and K are linear in the integrals, so a
     // shell quartet is split into `psplit` work items of `clen` consecutive bra primitive pairs each (clen * psplit >= nppAB); every item
-    // digests and flushes its partial integrals on its own.
-    int psplit, clen;
+    // digests and flushes its partial integrals on its own.  When every bra primitive pair already is its own work item and the ket still
+    // has more than the target number of primitive pairs (an (s8 s8| s8 s8) quartet of cc-pVTZ walks 64 of them), the ket is split as well:
+    // psplit = (bra chunks) * ksplit work items per shell quartet, item chunk c -> bra chunk c / ksplit, ket chunk c % ksplit (klen pairs).
+    int psplit, clen, ksplit, klen;
     const int* bra_list; const int* ket_list;
     const long long* item_prefix;
     int nbra, same_class;
@@ -110,6 +112,22 @@ struct Shell4Job {
     long long fill_base;
     const int* fill_pairs;          // [2 * nitems] (bra pair, ket pair) of every shell quartet of the job: the scatter pass decodes an item with one load
 };
+
+// Work items of a shell quartet for a target number of primitive quartets per item (0 = never split).
+inline void shell4_split(Shell4Job& J, int target, bool split_ket) {
+    const long long tot = (long long)J.nppAB * J.nppCD;
+    int bra = (target > 0 && tot > target) ? (int)((tot + target - 1) / target) : 1;
+    if (bra > J.nppAB) bra = J.nppAB;
+    J.clen = (J.nppAB + bra - 1) / bra;
+    bra = (J.nppAB + J.clen - 1) / J.clen;
+    J.ksplit = 1; J.klen = J.nppCD;
+    if (split_ket && target > 0 && J.clen == 1 && J.nppCD > target) {
+        const int ks = (J.nppCD + target - 1) / target;
+        J.klen = (J.nppCD + ks - 1) / ks;
+        J.ksplit = (J.nppCD + J.klen - 1) / J.klen;
+    }
+    J.psplit = bra * J.ksplit;
+}
 
 inline void shell4_job_layout(Shell4Job& J, int nD) {
     const int Ltot = J.La + J.Lb + J.Lc + J.Ld, Lab = J.La + J.Lb, Lcd = J.Lc + J.Ld;
@@ -203,7 +221,7 @@ TUNA_HD void assemble4(const double* xyx, const double* xyy, const double* sp0, 
 
 // Header of one quartet of a batch, decoded once (by one lane) before the group starts on it.
 struct Quartet4 {
-    int active, shA, shB, shC, shD, ia0;      // the four shells (A, B of the bra pair, C, D of the ket pair); first bra primitive pair of this work item
+    int active, shA, shB, shC, shD, ia0;      // the four shells (A, B of the bra pair, C, D of the ket pair); first bra primitive pair of this work item | first ket primitive pair << 16
     double w;                                 // degeneracy weight
     long long recA, recC;                     // offsets of the pairs' first primitive records in ShellData::rec
     double pA, zA, pC, zC;                    // exponent sum and centre of the FIRST primitive pair of bra and ket (Boys argument without a memory round trip)
@@ -303,33 +321,35 @@ TUNA_HD void shell4_quartets(const Shell4Job& J, const ShellData& D, const Quart
             Pol::sync_cta();
         }
         for (int it = 0; it < J.clen; ++it)
-            for (int ic = 0; ic < J.nppCD; ++ic) {
-                // bra primitive pair of every quartet of the batch (a work item past the last primitive pair runs on the last one with weight 0)
-                int iaq[NB];
+            for (int kk = 0; kk < J.klen; ++kk) {
+                // primitive pairs of every quartet of the batch (a work item past the last primitive pair runs on the last one with weight 0)
+                int iaq[NB], icq[NB];
                 bool pvalid[NB];
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
-                    const int ia = hq[act[q] ? q : qa].ia0 + it;
-                    pvalid[q] = ia < J.nppAB;
-                    iaq[q] = pvalid[q] ? ia : J.nppAB - 1;
+                    const int i0 = hq[act[q] ? q : qa].ia0;
+                    const int ia = (i0 & 0xffff) + it, ic = (i0 >> 16) + kk;
+                    pvalid[q] = ia < J.nppAB && ic < J.nppCD;
+                    iaq[q] = ia < J.nppAB ? ia : J.nppAB - 1;
+                    icq[q] = ic < J.nppCD ? ic : J.nppCD - 1;
                 }
                 // ---- phase 0: the two primitive shell-pair records, Boys values scaled by (-2 rho)^m, powers of PQz
 #pragma unroll
                 for (int q = 0; q < NB && !(skip & 2); ++q) {
                     const double* rA = recA[q] + iaq[q] * recAsz;
-                    const double* rC = recC[q] + ic * recCsz;
-                    if (ic == 0) { for (int x = lane; x < recAsz; x += Pol::G) RAq[x * NB + q] = rA[x]; }
+                    const double* rC = recC[q] + icq[q] * recCsz;
+                    if (kk == 0) { for (int x = lane; x < recAsz; x += Pol::G) RAq[x * NB + q] = rA[x]; }
                     for (int x = lane; x < recCsz; x += Pol::G) RCq[x * NB + q] = rC[x];
                 }
                 for (int x = lane; x < NB * 32 && !(skip & 2); x += Pol::G) {
                     const int q = x >> 5, m = x & 31;
                     if (m <= Ltot) {
                         const double* rA = recA[0] + iaq[0] * recAsz;
-                        const double* rC = recC[0] + ic * recCsz;
-                        int qs = act[0] ? 0 : qa, ia = iaq[0];
+                        const double* rC = recC[0] + icq[0] * recCsz;
+                        int qs = act[0] ? 0 : qa, ia = iaq[0], ic = icq[0];
                         bool pv = pvalid[0];
 #pragma unroll
-                        for (int k = 1; k < NB; ++k) if (q == k) { rA = recA[k] + iaq[k] * recAsz; rC = recC[k] + ic * recCsz; qs = act[k] ? k : qa; ia = iaq[k]; pv = pvalid[k]; }
+                        for (int k = 1; k < NB; ++k) if (q == k) { rA = recA[k] + iaq[k] * recAsz; rC = recC[k] + icq[k] * recCsz; qs = act[k] ? k : qa; ia = iaq[k]; ic = icq[k]; pv = pvalid[k]; }
                         double p, qq, PQz;
                         if (ia == 0 && ic == 0) { p = hq[qs].pA; qq = hq[qs].pC; PQz = hq[qs].zA - hq[qs].zC; }
                         else { p = rA[0]; qq = rC[0]; PQz = rA[1] - rC[1]; }

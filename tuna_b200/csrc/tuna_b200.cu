@@ -875,7 +875,7 @@ __device__ __forceinline__ void shell4_unit(const Shell4Job& J, const ShellData&
         h.active = 0; h.shA = h.shB = h.shC = h.shD = 0; h.ia0 = 0; h.w = 0.0; h.recA = h.recC = 0; h.pA = h.pC = 1.0; h.zA = h.zC = 0.0;
         if (wi < nwi) {
             int ib = s_ib0;
-            h.ia0 = pchunk * J.clen;
+            { const int bchunk = pchunk / J.ksplit; h.ia0 = bchunk * J.clen | ((pchunk - bchunk * J.ksplit) * J.klen) << 16; }
             while (J.item_prefix[ib + 1] <= item) ++ib;
             const int pab = J.bra_list[ib], pcd = J.ket_list[(int)(item - J.item_prefix[ib])];
             h.active = !(tau > 0.0 && D.pairQ[pab] * D.pairQ[pcd] * dmax < tau);
@@ -1334,7 +1334,7 @@ int tuna_eri_fill_cart(tuna_ctx* ctx) try {
     // A basis that groups into shells AND has contracted shells is filled by the shell-quartet engine (shell4.cuh, fill mode: Boys values, R,
     // the x/y table and the z contractions are shared by all components of a shell quartet, contracted quartets are split over work items)
     // followed by the scatter pass; an uncontracted basis keeps the per-AO-quartet kernel, which is as fast there (ET100: 1.40 vs 1.52 ms;
-    // N2/cc-pVTZ: 3.7 vs 1.3 ms, Ne2/cc-pVQZ: 13.6 vs 5.9 ms).  TUNA_B200_FILL_ENGINE=1 / 0 forces one or the other.  Both leave the same
+    // N2/cc-pVTZ: 3.7 vs 0.87 ms, Ne2/cc-pVQZ: 13.6 vs 5.4 ms).  TUNA_B200_FILL_ENGINE=1 / 0 forces one or the other.  Both leave the same
     // tensor: one value written to all eight images, exact zeros for the parity-forbidden elements.
     bool contracted = false;
     for (const auto& sh : ctx->ss.shells) contracted = contracted || sh.nprim > 1;
@@ -2171,12 +2171,10 @@ static int ensure_shell4(tuna_ctx* ctx, double tau, int nD) {
             Shell4Job& J = jh.job;
             J.La = S.classes[cb].La; J.Lb = S.classes[cb].Lb; J.Lc = S.classes[ck].La; J.Ld = S.classes[ck].Lb;
             J.nppAB = S.classes[cb].npp; J.nppCD = S.classes[ck].npp;
-            {   // at most ~psplit_target primitive quartets per work item (TUNA_B200_PSPLIT_TARGET, 0 = never split)
+            {   // at most ~psplit_target primitive quartets per work item (TUNA_B200_PSPLIT_TARGET, 0 = never split; TUNA_B200_KSPLIT=0: bra only)
                 static const int target = getenv("TUNA_B200_PSPLIT_TARGET") ? atoi(getenv("TUNA_B200_PSPLIT_TARGET")) : 16;
-                const long long tot = (long long)J.nppAB * J.nppCD;
-                J.psplit = (target > 0 && tot > target) ? (int)std::min<long long>(J.nppAB, (tot + target - 1) / target) : 1;
-                J.clen = (J.nppAB + J.psplit - 1) / J.psplit;
-                J.psplit = (J.nppAB + J.clen - 1) / J.clen;
+                static const bool split_ket = !(getenv("TUNA_B200_KSPLIT") && atoi(getenv("TUNA_B200_KSPLIT")) == 0);
+                shell4_split(J, target, split_ket);
             }
             { const char* dbg = getenv("TUNA_B200_DBG_SKIP"); J.dbg_skip = dbg ? atoi(dbg) : 0; }
             J.fill_scratch = nullptr; J.fill_base = 0; J.fill_pairs = nullptr;
