@@ -200,6 +200,14 @@ extern "C" int emul_jk_shell4(int ncart, const double* oz, const int* lmn, const
     return 0;
 }
 
+// Work-item split of a contracted shell quartet (shell4_split): out = {psplit, clen, ksplit, klen}
+extern "C" void emul_split(int nppAB, int nppCD, int target, int split_ket, int* out) {
+    Shell4Job J;
+    J.nppAB = nppAB; J.nppCD = nppCD;
+    shell4_split(J, target, split_ket != 0);
+    out[0] = J.psplit; out[1] = J.clen; out[2] = J.ksplit; out[3] = J.klen;
+}
+
 // Dense Cartesian ERI tensor through the engine's fill mode: every work item (shell quartet x primitive chunk) writes its integrals to
 // a scratch row, shell4_fill_scatter sums the chunks and writes the eight images — the same two passes the device runs.
 extern "C" int emul_fill_shell4(int ncart, const double* oz, const int* lmn, const int* nprim, const int64_t* off, const double* exps,

@@ -163,6 +163,38 @@ def test_shell_engine_primitive_split(emul, oracle, target, ket, monkeypatch):
     assert np.abs(J[0] - oracle.coulomb(P[0], E)).max() < 1e-11 and np.abs(K[0] - oracle.exchange(P[0], E)).max() < 1e-11
 
 
+def test_primitive_split_covers_every_primitive_quartet_once(emul):
+    """shell4_split + the header decode of shell4_unit: the work items of a shell quartet visit every (bra, ket) primitive pair exactly once,
+    an item holds at most ~target primitive quartets once bra and ket are both split, and target 0 never splits."""
+    out = (ctypes.c_int * 4)()
+    for nab in (1, 2, 3, 5, 9, 16, 24, 64, 81):
+        for ncd in (1, 2, 3, 9, 17, 24, 64, 81):
+            for target in (0, 1, 4, 7, 16, 100):
+                for ket in (0, 1):
+                    emul.emul_split(nab, ncd, target, ket, out)
+                    psplit, clen, ksplit, klen = out[0], out[1], out[2], out[3]
+                    assert psplit % ksplit == 0 and psplit >= 1 and clen >= 1 and klen >= 1
+                    if target == 0:
+                        assert (psplit, clen, ksplit, klen) == (1, nab, 1, ncd)
+                    if not ket:
+                        assert ksplit == 1 and klen == ncd
+                    seen = np.zeros((nab, ncd), dtype=int)
+                    largest = 0
+                    for pchunk in range(psplit):
+                        ia0, ic0 = (pchunk // ksplit) * clen, (pchunk % ksplit) * klen      # as packed into Quartet4::ia0
+                        assert ia0 < 65536 and ic0 < 32768
+                        cnt = 0
+                        for it in range(clen):
+                            for kk in range(klen):
+                                if ia0 + it < nab and ic0 + kk < ncd:
+                                    seen[ia0 + it, ic0 + kk] += 1
+                                    cnt += 1
+                        largest = max(largest, cnt)
+                    assert (seen == 1).all(), (nab, ncd, target, ket)
+                    if target > 0 and ket:
+                        assert largest <= 2 * target, (nab, ncd, target, largest)      # ceil effects only
+
+
 @pytest.mark.parametrize("gen,nb,budget", [("gen4", None, None), ("gen4", "1", "1500"), ("gen4", "4", "700")])
 def test_shell_engine_h_shells(emul, oracle, gen, nb, budget, monkeypatch):
     """All shell types up to H, including the multi-chunk (hh|hh) class tables, on a synthetic two-centre basis; generation 4 also with
