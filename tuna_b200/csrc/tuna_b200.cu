@@ -803,8 +803,6 @@ __global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters, doub
 }
 
 // ---- shell-quartet engine (shell4.cuh) ------------------------------------------------------------------------------------
-constexpr int SHELL_ITEMS_PER_GROUP = 4;   // smallest CTA work unit (= multi-GPU sharding unit): shell quartets per group
-
 template <int GG>
 struct DevPolicy {
     static constexpr int G = GG;
@@ -1383,7 +1381,7 @@ int tuna_eri_cart_to_sph(tuna_ctx* ctx, int keep_cart) try {
     if (ctx->nbf == 0) FAIL(TUNA_ERR_STATE, "tuna_eri_cart_to_sph: call tuna_set_transform first");
     CK(cudaSetDevice(ctx->device));
     const int64_t nc = ctx->ncart, nb = ctx->nbf;
-    double* t1 = nullptr; double* t2 = nullptr; double* t3 = nullptr;
+    double* t1 = nullptr; double* t2 = nullptr;
     int rc;
     dev_free(&ctx->d_eri_sph);
     ctx->n_stored = 0;
