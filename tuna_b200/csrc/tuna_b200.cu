@@ -1337,21 +1337,25 @@ int tuna_eri_fill_cart(tuna_ctx* ctx) try {
     bool contracted = false;
     for (const auto& sh : ctx->ss.shells) contracted = contracted || sh.nprim > 1;
     const char* ef = getenv("TUNA_B200_FILL_ENGINE");
-    const bool engine = ctx->direct_engine == 1 && ctx->ss.ok && (ef ? atoi(ef) != 0 : contracted);
-    const int save_rank = ctx->shard_rank, save_n = ctx->shard_n;
+    bool engine = ctx->direct_engine == 1 && ctx->ss.ok && (ef ? atoi(ef) != 0 : contracted);
+    // the dense tensor is never sharded (every rank holds all of it): the fill runs as rank 0 of 1, whatever tuna_set_shard said
+    struct ShardGuard { tuna_ctx* c; int r, n; ~ShardGuard() { c->shard_rank = r; c->shard_n = n; } } guard{ctx, ctx->shard_rank, ctx->shard_n};
+    if ((rc = dev_alloc(ctx, &ctx->d_eri_cart, count))) return rc;
     if (engine) {
-        ctx->shard_rank = 0; ctx->shard_n = 1;        // the dense tensor is never sharded: every rank holds all of it
+        ctx->shard_rank = 0; ctx->shard_n = 1;
         rc = ensure_shell4(ctx, 0.0, 0);
-        if (rc) { ctx->shard_rank = save_rank; ctx->shard_n = save_n; return rc; }
+        if (rc) {       // drop the half-built fill job set; when only the scratch rows did not fit, the per-AO-quartet kernel (no scratch) takes over
+            if (!ctx->jobsets4.empty() && ctx->jobsets4.back().nD == 0) { free_jobset4(ctx->jobsets4.back()); ctx->jobsets4.pop_back(); }
+            ctx->cur_jobset4 = -1;
+            if (rc != TUNA_ERR_NOMEM) return rc;
+            engine = false;
+        }
     }
-    if ((rc = dev_alloc(ctx, &ctx->d_eri_cart, count))) { ctx->shard_rank = save_rank; ctx->shard_n = save_n; return rc; }
     CK(cudaMemsetAsync(ctx->d_eri_cart, 0, count * sizeof(double), ctx->stream));
     CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
     if (engine) {
         const tuna_ctx::JobSet4& JS = ctx->jobsets4[ctx->cur_jobset4];
-        rc = launch_shell4_jobs(ctx, 0, nullptr, nullptr, nullptr, nullptr, 0.0, 0);
-        ctx->shard_rank = save_rank; ctx->shard_n = save_n;
-        if (rc) return rc;
+        if ((rc = launch_shell4_jobs(ctx, 0, nullptr, nullptr, nullptr, nullptr, 0.0, 0))) return rc;
         if (JS.scatter_total > 0) {
             ShellData D;
             D.pairA = ctx->d_pairA; D.pairB = ctx->d_pairB; D.pair_rec = ctx->d_pair_rec; D.rec = ctx->d_rec; D.pairQ = ctx->d_pairQ;
