@@ -18,6 +18,9 @@ step "ncu per-class counters (one ET800 build)"
 TUNA_B200_DUMP_JOBS=$O/${R}_jobs800.csv timeout 500 ncu --metrics $M --clock-control none --csv --log-file $O/${R}_class_metrics.csv -k regex:k_shell4 -c 231 python tools/direct_timing.py child 800 > $O/${R}_ncu_c.log 2>&1; step "rc=$?"
 step "ncu DRAM traffic of the stored J/K and AO->MO kernels (N2/cc-pVTZ)"
 timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/${R}_stored_mo_traffic.csv -k regex:"k_jk_stored|k_sym_reduce|k_axis_gemm" python tools/stored_check.py profile n2_ccpvtz > $O/${R}_ncu_t.log 2>&1; step "rc=$?"
+step "dense fill: engine vs per-AO-quartet kernel; ncu time and DRAM bytes of the scatter pass"
+timeout 200 python tools/fill_timing.py > $O/${R}_fill_timing.log 2>&1; step "rc=$?"
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_fill_scatter -c 12 --csv --log-file $O/${R}_fill_scatter_ncu.csv python tools/fill_timing.py n2_ccpvtz ne2_uhf_ccpvqz > $O/${R}_ncu_f.log 2>&1; step "rc=$?"
 step "ncu launch list of the bench command"
 timeout 330 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file $O/${R}_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-stored > $O/${R}_ncu_l.log 2>&1; step "rc=$?"
 step "ncu full capture of the heaviest class job"
