@@ -226,6 +226,36 @@ def test_shell_engine_h_shells(emul, oracle, gen, nb, budget, monkeypatch):
     assert np.abs(J[0] - oracle.coulomb(P[0], E)).max() < 1e-11 and np.abs(K[0] - oracle.exchange(P[0], E)).max() < 1e-11
 
 
+@pytest.mark.parametrize("nb,budget", [(None, None), ("1", "1500")])
+def test_engine_fill_mode_h_shells(emul, oracle, nb, budget, monkeypatch):
+    """Fill mode on the synthetic two-centre basis with every shell type up to H (one contracted f shell): the multi-chunk (hh|hh)-type
+    classes write their scratch rows chunk by chunk; with the default budgets and with small ones (more chunks per class)."""
+    if nb:
+        monkeypatch.setenv("TUNA_EMUL_NB", nb)
+        monkeypatch.setenv("TUNA_EMUL_IT_BUDGET", budget)
+    from tuna_b200 import workloads as w
+    from tuna_b200.basis import from_arrays
+    shells_a = [(0, [1.3], [1.0]), (1, [0.9], [1.0]), (5, [1.1], [1.0])]
+    shells_b = [(2, [0.8], [1.0]), (4, [1.2], [1.0]), (5, [0.7], [1.0]), (3, [1.0, 0.4], [0.6, 0.5])]
+    b = w.shells_to_components([shells_a, shells_b], [0.0, 1.9])
+    fb = oracle.FlatBasis.from_reference_objects(from_arrays(b["origins"], b["lmn"], b["nprim"], b["exps"], b["raw_coefs"]))
+    n = fb.ncart
+    ref = oracle.eri_fill(fb)
+    dp, ip, lp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    oz = np.ascontiguousarray(fb.origins[:, 2])
+    lmn = np.ascontiguousarray(fb.lmn, dtype=np.int32)
+    npr = np.ascontiguousarray(fb.nprim, dtype=np.int32)
+    off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+    ceff = np.ascontiguousarray(fb.coefs * fb.norms)
+    out = np.full((n,) * 4, np.nan)
+    rc = emul.emul_fill_shell4(n, oz.ctypes.data_as(dp), lmn.ctypes.data_as(ip), npr.ctypes.data_as(ip), off.ctypes.data_as(lp),
+                               fb.exps.ctypes.data_as(dp), ceff.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert rc == 0
+    assert np.all(np.abs(out - ref) <= np.maximum(1e-12, 1e-13 * np.abs(ref)))
+    assert np.array_equal(out == 0.0, ref == 0.0)
+    assert np.array_equal(out, out.transpose(1, 0, 2, 3)) and np.array_equal(out, out.transpose(2, 3, 0, 1))
+
+
 @pytest.mark.parametrize("gen", list(ENGINES))
 def test_shell_engine_extreme_shells_of_the_headline_basis(emul, oracle, gen):
     """The tightest and the most diffuse shell of every angular momentum of the ET800 set (s exponent 2.1e5 ... h exponent 1.0) on both
